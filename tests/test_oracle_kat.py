@@ -1,0 +1,384 @@
+"""Pin the CPU oracle against the reference's own tests and derived known-answer vectors.
+
+* src/vec3.rs:343-428 — the reference's 9 unit tests, replicated verbatim (exact f64 equality).
+* SURVEY.md Appendix B (B1-B17) — vectors derived by hand from the cited reference formulas.
+* Philox-4x32-10 known-answer vectors (Random123 kat_vectors) — the RNG contract of Appendix D.
+The reference (Rust) cannot be built in this image, so these are the pins the oracle has.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from ray_tracing_series_rust_b200 import capi
+
+INF = float("inf")
+
+
+def v(*a):
+    return (C.c_double * 3)(*[float(x) for x in a])
+
+
+def trace1(scene, o, d, time=0.0, tmin=0.001, tmax=INF):
+    return scene.trace_batch(capi.make_rays([o], [d], time), tmin, tmax)[0]
+
+
+# ------------------------------------------------------------------ Philox
+def test_philox_known_answers(orc):
+    api = orc.api()
+    cases = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in cases:
+        out = (C.c_uint32 * 4)()
+        api.kat_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        assert tuple(out) == want
+
+
+# ------------------------------------------------------------------ B17: vec3.rs:343-428
+def test_vec3_general(orc):  # vec3.rs:347-358 general_vec3_stuff
+    a, b = (1, 2, 3), (4, 5, 6)
+    assert orc.vec3_op(0, a, b) == (5.0, 7.0, 9.0)
+    assert orc.vec3_op(1, a, b) == (-3.0, -3.0, -3.0)
+    assert orc.vec3_op(2, a, b) == (4.0, 10.0, 18.0)
+    assert orc.api().kat_vec3_scalar(0, v(*a), v(*b)) == 32.0
+    assert orc.api().kat_vec3_scalar(2, v(*a), v(*a)) == 14.0
+    assert orc.api().kat_vec3_scalar(1, v(3, 4, 0), v(0, 0, 0)) == 5.0
+
+
+def test_vec3_add_assign(orc):  # vec3.rs:360-370
+    assert orc.vec3_op(8, (1, 2, 3), (4, 5, 6)) == (5.0, 7.0, 9.0)
+
+
+def test_vec3_mul_assign(orc):  # vec3.rs:372-380: (3,2,1)*=5 -> (15,10,5); *=2.5 -> (37.5,25,12.5)
+    r = orc.vec3_op(9, (3, 2, 1), s=5)
+    assert r == (15.0, 10.0, 5.0)
+    assert orc.vec3_op(9, r, s=2.5) == (37.5, 25.0, 12.5)
+
+
+def test_vec3_div_assign(orc):  # vec3.rs:382-388: /= is *= (1/rhs)
+    assert orc.vec3_op(10, (4, 8, 16), s=4) == (1.0, 2.0, 4.0)
+    assert orc.vec3_op(10, (3, 2, 1), s=2) == (1.5, 1.0, 0.5)
+
+
+def test_vec3_f64_mul_and_div(orc):  # vec3.rs:390-399
+    assert orc.vec3_op(12, (1, 2, 3), s=2.0) == (2.0, 4.0, 6.0)
+    assert orc.vec3_op(3, (1, 2, 3), s=2.0) == (2.0, 4.0, 6.0)
+    assert orc.vec3_op(4, (2, 4, 6), s=2.0) == (1.0, 2.0, 3.0)
+
+
+def test_vec3_cross(orc):  # vec3.rs:401-406
+    assert orc.vec3_op(5, (2, 3, 4), (5, 6, 7)) == (-3.0, 6.0, -3.0)
+
+
+def test_vec3_neg_unit_near_zero(orc):
+    assert orc.vec3_op(6, (1, -2, 3)) == (-1.0, 2.0, -3.0)
+    u = orc.vec3_op(7, (0, 3, 4))
+    assert u == (0.0, 0.6, 0.8)
+    assert orc.api().kat_vec3_scalar(3, v(1e-9, -1e-9, 0), v(0, 0, 0)) == 1.0
+    assert orc.api().kat_vec3_scalar(3, v(1e-7, 0, 0), v(0, 0, 0)) == 0.0
+
+
+# ------------------------------------------------------------------ B1, B2 Sphere::hit
+def test_B1_B2_sphere(orc):
+    s = orc.new_scene()
+    m = s.lambertian((0.5, 0.5, 0.5))
+    s.set_root(s.list([s.sphere((0, 0, 0), 4.0, m)]))
+    s.commit()
+    h = trace1(s, (0, 0, 20), (0, 0, -1))
+    assert h["prim_id"] == 0 and h["t"] == 16.0
+    assert tuple(h["p"]) == (0.0, 0.0, 4.0) and tuple(h["normal"]) == (0.0, 0.0, 1.0)
+    assert h["front_face"] == 1
+    assert h["u"] == pytest.approx(0.25, abs=1e-15) and h["v"] == pytest.approx(0.5, abs=1e-15)
+    h = trace1(s, (0, 0, 0), (0, 0, -1))
+    assert h["t"] == 4.0 and tuple(h["p"]) == (0.0, 0.0, -4.0)
+    assert h["front_face"] == 0 and tuple(h["normal"]) == (0.0, 0.0, 1.0)
+    # inclusive interval ends (hit.rs:216-219): t_max == root is accepted
+    h = trace1(s, (0, 0, 20), (0, 0, -1), tmax=16.0)
+    assert h["prim_id"] == 0 and h["t"] == 16.0
+    h = trace1(s, (0, 0, 20), (0, 0, -1), tmin=16.0, tmax=16.0)
+    assert h["prim_id"] == 0
+    # un-normalised direction: t is in units of |d|
+    h = trace1(s, (0, 0, 20), (0, 0, -4))
+    assert h["t"] == 4.0
+
+
+# ------------------------------------------------------------------ B3 XyRect::hit
+def test_B3_rect(orc):
+    s = orc.new_scene()
+    m = s.lambertian((0.5, 0.5, 0.5))
+    s.set_root(s.list([s.xy_rect(3, 5, 1, 3, -2, m)]))
+    s.commit()
+    h = trace1(s, (4, 2, 0), (0, 0, -1))
+    assert h["t"] == 2.0 and h["u"] == 0.5 and h["v"] == 0.5
+    assert tuple(h["normal"]) == (0.0, 0.0, 1.0) and h["front_face"] == 1
+    # inclusive edges (hit.rs:483)
+    assert trace1(s, (3, 1, 0), (0, 0, -1))["prim_id"] == 0
+    assert trace1(s, (5.0000001, 1, 0), (0, 0, -1))["prim_id"] == -1
+
+
+# ------------------------------------------------------------------ B4, B5 Triangle::hit
+def test_B4_B5_triangle(orc):
+    s = orc.new_scene()
+    m = s.lambertian((1, 0, 0))
+    s.set_root(s.list([s.triangle((0, 5, 0), (5, 0, 0), (0, 0, 0), m)]))
+    s.commit()
+    h = trace1(s, (1, 1, 20), (0, 0, -1))
+    assert h["t"] == 20.0 and tuple(h["p"]) == (1.0, 1.0, 0.0)
+    assert h["front_face"] == 0 and tuple(h["normal"]) == (0.0, 0.0, 1.0)
+    assert h["u"] == 1.0 and h["v"] == 1.0
+    assert trace1(s, (4, 4, 20), (0, 0, -1))["prim_id"] == -1
+    # parallel cutoff |n.d| < 1e-4 scales with |d| (hit.rs:114)
+    assert trace1(s, (1, 1, 20), (1, 0, -0.00009))["prim_id"] == -1
+
+
+# ------------------------------------------------------------------ B6 Aabb::hit
+def test_B6_aabb(orc):
+    api = orc.api()
+    assert api.kat_aabb_hit(v(0, 0, 0), v(1, 1, 1), v(-1, 0.5, 0.5), v(1, 0, 0), 0.001, INF) == 1
+    assert api.kat_aabb_hit(v(0, 0, 0), v(1, 1, 1), v(-1, 1.5, 0.5), v(1, 0, 0), 0.001, INF) == 0
+    # zero-thickness box is never hit: t_max <= t_min (aabb.rs:56)
+    assert api.kat_aabb_hit(v(0, 0, 0), v(1, 1, 0), v(0.5, 0.5, 1), v(0, 0, -1), 0.001, INF) == 0
+
+
+# ------------------------------------------------------------------ B7, B8, B9
+def test_B7_reflectance(orc):
+    api = orc.api()
+    assert api.kat_reflectance(1.0, 1.5) == pytest.approx(0.04, abs=1e-15)
+    assert api.kat_reflectance(0.0, 1 / 1.5) == pytest.approx(1.0, abs=1e-15)
+
+
+def test_B8_refract(orc):
+    api = orc.api()
+    out = (C.c_double * 3)()
+    api.kat_refract(v(0, -1, 0), v(0, 1, 0), 1 / 1.5, out)
+    assert tuple(out) == (0.0, -1.0, 0.0)
+    r = math.sqrt(0.5)
+    api.kat_refract(v(r, -r, 0), v(0, 1, 0), 1 / 1.5, out)
+    assert out[0] == pytest.approx(0.47140452, abs=1e-8)
+    assert out[1] == pytest.approx(-0.88191710, abs=1e-8)
+    assert out[2] == 0.0
+
+
+def test_B9_reflect(orc):
+    out = (C.c_double * 3)()
+    orc.api().kat_reflect(v(1, -1, 0), v(0, 1, 0), out)
+    assert tuple(out) == (1.0, 1.0, 0.0)
+
+
+# ------------------------------------------------------------------ B10 get_normalized_color
+def test_B10_normalized_color(orc):
+    out = (C.c_double * 3)()
+    orc.api().kat_normalized_color(v(500, 125, 0), 500, out)
+    assert tuple(out) == (255.0, 127.0, 0.0)
+    orc.api().kat_normalized_color(v(1e9, float("nan"), -3.0), 10, out)
+    assert out[0] == 255.0 and out[1] == 0.0 and out[2] == 0.0  # clamp; NaN as i32 -> 0; sqrt(<0)=NaN -> 0
+
+
+# ------------------------------------------------------------------ B11 MovingSphere::get_center
+def test_B11_moving_center(orc):
+    out = (C.c_double * 3)()
+    orc.api().kat_moving_center(v(0, 0.2, 0), v(0, 5.2, 0), 0.0, 10.0, 2.5, out)
+    assert tuple(out) == (0.0, 1.45, 0.0)
+
+
+# ------------------------------------------------------------------ B12, B13 Camera::new
+def cam_fields(orc, scene):
+    out = (C.c_double * 24)()
+    orc.api().check(orc.api().kat_camera(scene.h, out))
+    a = np.array(out[:21]).reshape(7, 3)
+    return dict(origin=a[0], llc=a[1], horizontal=a[2], vertical=a[3], u=a[4], v=a[5], w=a[6],
+                lens_radius=out[21], time1=out[22], time2=out[23])
+
+
+def test_B12_camera_book1(orc):
+    s = orc.new_scene()
+    s.set_camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20, 16 / 9, 0.1, 10, 0, 10)
+    c = cam_fields(orc, s)
+    tol = dict(rtol=0, atol=2e-14)
+    np.testing.assert_allclose(c["w"], [0.9636241116594315, 0.14824986333222023, 0.22237479499833035], **tol)
+    np.testing.assert_allclose(c["u"], [0.22485950669875845, 0, -0.97439119569462], **tol)
+    np.testing.assert_allclose(c["v"], [-0.14445336159384606, 0.9889499370655616, -0.0333353911370414], **tol)
+    np.testing.assert_allclose(c["horizontal"], [1.4097350364368686, 0, -6.108851824559764], **tol)
+    np.testing.assert_allclose(c["vertical"], [-0.5094205020606202, 3.4875711294919385, -0.11755857739860466], **tol)
+    np.testing.assert_allclose(c["llc"], [2.913601616217562, -1.2262841980681716, 3.8894572509958807], **tol)
+    assert c["lens_radius"] == 0.05
+    d = c["llc"] + 0.5 * c["horizontal"] + 0.5 * c["vertical"] - c["origin"]
+    np.testing.assert_allclose(d, [-9.636241116594313, -1.4824986333222023, -2.223747949983304], **tol)
+    assert np.linalg.norm(d) == pytest.approx(10.0, abs=1e-13)
+
+
+def test_B13_camera_cornell(orc):
+    s = orc.new_scene()
+    s.set_camera((278, 278, -800), (278, 278, 0), (0, 1, 0), 40, 1.0, 0.0, 10, 0, 1)
+    c = cam_fields(orc, s)
+    tol = dict(rtol=0, atol=1e-12)
+    np.testing.assert_allclose(c["u"], [-1, 0, 0], **tol)
+    np.testing.assert_allclose(c["v"], [0, 1, 0], **tol)
+    np.testing.assert_allclose(c["w"], [0, 0, -1], **tol)
+    np.testing.assert_allclose(c["horizontal"], [-7.279404685324047, 0, 0], **tol)
+    np.testing.assert_allclose(c["vertical"], [0, 7.279404685324047, 0], **tol)
+    np.testing.assert_allclose(c["llc"], [281.639702342662, 274.360297657338, -790], **tol)
+
+
+# ------------------------------------------------------------------ B14 Checker, B15 Perlin
+def test_B14_checker(orc):
+    s = orc.new_scene()
+    t = s.tex_checker(s.tex_solid((0.2, 0.3, 0.1)), s.tex_solid((0.9, 0.9, 0.9)))
+    out = (C.c_double * 3)()
+    orc.api().kat_texture_value(s.h, t, 0, 0, v(0.1, 0.1, 0.1), out)
+    assert tuple(out) == (0.2, 0.3, 0.1)  # even
+    orc.api().kat_texture_value(s.h, t, 0, 0, v(0.1, 0.1, -0.1), out)
+    assert tuple(out) == (0.9, 0.9, 0.9)  # odd
+
+
+def test_B15_perlin_lattice(orc):
+    s = orc.new_scene()
+    t = s.tex_noise(0.1, seed=7)
+    n, tb = C.c_double(), C.c_double()
+    for p in [(0, 0, 0), (3, -2, 7), (255, 256, -257)]:
+        orc.api().check(orc.api().kat_perlin(s.h, t, v(*p), C.byref(n), C.byref(tb)))
+        assert n.value == 0.0 and tb.value == 0.0
+        out = (C.c_double * 3)()
+        orc.api().kat_texture_value(s.h, t, 0, 0, v(*p), out)
+        assert out[0] == pytest.approx(0.5 * (1 + math.sin(0.1 * p[2])), abs=1e-15)
+    # |noise| is bounded for unnormalised U[-1,1)^3 gradients: |c.w| <= sqrt(3)*sqrt(3)
+    rng = np.random.default_rng(1)
+    for p in rng.uniform(-50, 50, size=(200, 3)):
+        orc.api().kat_perlin(s.h, t, v(*p), C.byref(n), C.byref(tb))
+        assert abs(n.value) <= 3.0 and 0 <= tb.value <= 6.0
+
+
+def test_perlin_tables_shuffle_invariant(orc):
+    # perlin.rs:79: the shuffle runs i = 254..1, so perm[255] == 255 always; tables passed as data
+    s = orc.new_scene()
+    rv = np.zeros((256, 3))
+    rv[:, 0] = 1.0
+    ident = np.arange(256, dtype=np.int32)
+    t = s.tex_noise(1.0, tables=(rv, ident, ident, ident))
+    n, tb = C.c_double(), C.c_double()
+    # all gradients (1,0,0): noise(p) = trilinear of (u - i) => depends on x only
+    orc.api().kat_perlin(s.h, t, v(0.5, 0.3, 0.9), C.byref(n), C.byref(tb))
+    uu = 0.5 * 0.5 * (3 - 2 * 0.5)
+    assert n.value == pytest.approx((1 - uu) * 0.5 + uu * (0.5 - 1.0), abs=1e-15)
+
+
+# ------------------------------------------------------------------ B16 Translate o RotateY o RectPrism
+def test_B16_cornell_tall_box(orc):
+    s = orc.new_scene()
+    white = s.lambertian((0.73, 0.73, 0.73))
+    box = s.translate((265, 0, 295), s.rotate_y(15.0, s.box((0, 0, 0), (165, 330, 165), white)))
+    s.set_root(s.list([box]))
+    s.commit()
+    assert s.num_prims() == 6
+    h = trace1(s, (300, 100, 0), (0, 0, 1))
+    assert h["prim_id"] == 1  # second side: XyRect k = p0.z (hit.rs:730-737)
+    assert h["t"] == pytest.approx(285.62177826491074, abs=1e-10)
+    assert h["u"] == pytest.approx(0.2196040382688055, abs=1e-12)
+    assert h["v"] == pytest.approx(0.30303030303030304, abs=1e-15)
+    np.testing.assert_allclose(h["p"], [300, 100, 285.6217782649107], atol=1e-10)
+    np.testing.assert_allclose(h["normal"], [-0.25881904510252074, 0, -0.9659258262890683], atol=1e-14)
+    assert h["front_face"] == 1
+    # second crossing used by ConstantMedium (hit.rs:956-957): chord 140
+    h2 = trace1(s, (300, 100, 0), (0, 0, 1), tmin=h["t"] + 0.0001)
+    assert h2["prim_id"] == 5  # YzRect k = p0.x
+    assert h2["t"] == pytest.approx(425.62177826491074, abs=1e-10)
+
+
+# ------------------------------------------------------------------ structural pins
+def test_list_later_element_wins_ties(orc):  # hit.rs:675-683 + world.rs:714-721,739
+    s = orc.new_scene()
+    a = s.xz_rect(-100, 100, -100, 100, 55, s.metal((1, 1, 1), 0.0))
+    b = s.xz_rect(-100, 100, -100, 100, 55, s.diffuse_light((4, 4, 4)))
+    s.set_root(s.list([a, b]))
+    s.commit()
+    h = trace1(s, (0, 0, 0), (0.1, 1, 0.2))
+    assert h["prim_id"] == 1 and h["t"] == 55.0
+
+
+def test_bvh_equals_flat_list(orc):
+    # closest hit is topology independent (bvh.rs:97-112 vs hit.rs:660-690)
+    rng = np.random.default_rng(5)
+    cen = rng.uniform(-10, 10, size=(200, 3))
+    rad = rng.uniform(0.2, 1.0, size=200)
+
+    def build(use_bvh):
+        s = orc.new_scene()
+        m = s.lambertian((0.5, 0.5, 0.5))
+        ids = [s.sphere(c, r, m) for c, r in zip(cen, rad)]
+        s.set_root(s.bvh(ids, 0, 1) if use_bvh else s.list(ids))
+        s.commit()
+        return s
+
+    sb, sl = build(True), build(False)
+    o = rng.uniform(-15, 15, size=(5000, 3))
+    d = rng.normal(size=(5000, 3)) * rng.uniform(0.1, 10, size=(5000, 1))
+    rays = capi.make_rays(o, d)
+    hb, hl = sb.trace_batch(rays), sl.trace_batch(rays)
+    assert np.array_equal(hb["prim_id"], hl["prim_id"])
+    assert np.array_equal(hb["t"], hl["t"])
+    assert (hb["prim_id"] >= 0).sum() > 500
+
+
+def test_translate_loses_front_face_quirk(orc):  # hit.rs:810: re-face-forwarding => front_face true
+    s = orc.new_scene()
+    m = s.dielectric(1.5)
+    s.set_root(s.list([s.translate((1, 0, 0), s.sphere((0, 0, 0), 1.0, m))]))
+    s.commit()
+    h = trace1(s, (1, 0, 0), (0, 0, 1))  # from inside
+    assert h["t"] == 1.0 and h["front_face"] == 1
+    np.testing.assert_allclose(h["normal"], [0, 0, -1], atol=1e-15)
+
+
+def test_gravity_table(orc):  # hit.rs:346-359
+    n = 4000
+    out = (C.c_double * n)()
+    total = C.c_int32()
+    orc.api().kat_gravity_table(2.0, 0.0, 0.2, n, out, C.byref(total))
+    assert total.value in (100001, 100002)  # float accumulation of t += 0.001 up to 100
+    y, vel, ys = 2.0, 0.0, [2.0]
+    for _ in range(n - 1):
+        vel -= 0.000001
+        if y - 0.2 <= 0.0:
+            vel *= -0.92
+        y = max(0.2, y + vel)
+        ys.append(y)
+    assert list(out) == ys
+    assert min(ys) == 0.2  # it reaches the ground within 4000 steps (fall from 1.8 takes ~1900)
+
+
+def test_medium_sampling_distribution(orc):
+    # ConstantMedium (hit.rs:955-986): P(scatter inside chord L) = 1 - exp(-density * L)
+    s = orc.new_scene()
+    m = s.lambertian((0.5, 0.5, 0.5))
+    s.set_root(s.list([s.constant_medium((1, 1, 1), 0.5, s.sphere((0, 0, 0), 1.0, m))]))
+    s.commit()
+    n = 20000
+    rays = capi.make_rays(np.tile([0, 0, -5.0], (n, 1)), np.tile([0, 0, 2.0], (n, 1)))
+    h = s.trace_batch(rays, flags=capi.RT_TRACE_SEEDED_MEDIA, seed=99)
+    frac = (h["prim_id"] >= 0).mean()
+    want = 1 - math.exp(-0.5 * 2.0)
+    assert abs(frac - want) < 4 * math.sqrt(want * (1 - want) / n)
+    hit = h[h["prim_id"] >= 0]
+    assert np.all(hit["t"] >= 2.0) and np.all(hit["t"] <= 3.0)  # t in units of |d| = 2
+    assert np.all(hit["normal"] == 0) and np.all(hit["front_face"] == 1)
+    # skipped when the geometric flag is used
+    assert (s.trace_batch(rays)["prim_id"] == -1).all()
+
+
+def test_sampler_distributions(orc):
+    n = 30000
+    out = np.zeros((n, 3))
+    orc.api().kat_sampler(0, 3, 0, n, out.ctypes.data_as(capi.c_d3))
+    r2 = (out ** 2).sum(1)
+    assert r2.max() < 1.0 and abs(out.mean()) < 0.01
+    assert abs((r2 < 0.25).mean() - 0.125) < 0.01  # uniform in the ball
+    orc.api().kat_sampler(1, 3, 1, n, out.ctypes.data_as(capi.c_d3))
+    np.testing.assert_allclose((out ** 2).sum(1), 1.0, atol=1e-12)
+    assert np.abs(out.mean(0)).max() < 0.02
+    orc.api().kat_sampler(2, 3, 2, n, out.ctypes.data_as(capi.c_d3))
+    assert ((out[:, :2] ** 2).sum(1)).max() < 1.0 and np.all(out[:, 2] == 0)
