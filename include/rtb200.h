@@ -263,6 +263,20 @@ typedef struct rt_hit {
 RTB_EXPORT int32_t RTB_FN(trace_batch)(rt_scene* s, const rt_ray* rays, int64_t n, double t_min,
                                        double t_max, int32_t flags, uint64_t seed, rt_hit* out);
 
+#ifndef RTB_PREFIX_ORC
+/* ---------------------------------------------------------------- diagnostics (product only)
+ * rt_unit_op evaluates one device function on the GPU for unit-level parity checks (SURVEY.md
+ * Appendix E3): op 0 Texture::value, 1 Perlin::noise/turbulence, 2 Philox block, 3 camera ray.
+ * rt_scene_set_tuning sets the number of resident path slots of the wavefront (0 = keep). */
+RTB_EXPORT int32_t rt_unit_op(rt_scene* s, int32_t op, uint32_t ia, uint32_t ib, uint32_t ic,
+                              uint32_t id, const double* in8, double* out8);
+RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots);
+/* Host-only self check of the flattener and BVH builder (needs no GPU): out[0] nodes, [1] max depth,
+ * [2] main instances, [3] instances, [4] media, [5..10] primitives per rt_prim_type, [11] leaves,
+ * [12] invariant violations (0 = valid), [13] numbered prims. */
+RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]);
+#endif
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,9 +309,11 @@ int32_t orc_rotate_y(rt_scene* s, double angle, int32_t child) {
 }
 int32_t orc_constant_medium(rt_scene* s, const double rgb[3], double density, int32_t boundary) {
     CHECK_SCENE(s); CHECK_OBJ(s, boundary);
-    // ConstantMedium::from_color builds its own Isotropic(SolidColor) (hit.rs:945-951); the phase
-    // material takes the next material id, as in the product library.
-    MaterialPtr phase = std::make_shared<Isotropic>(std::make_shared<SolidColor>(Color(rgb[0], rgb[1], rgb[2])));
+    // ConstantMedium::from_color builds its own Isotropic(SolidColor) (hit.rs:945-951); its texture
+    // and material take the next texture / material ids, as in the product library.
+    TexturePtr solid = std::make_shared<SolidColor>(Color(rgb[0], rgb[1], rgb[2]));
+    add_tex(s, solid);
+    MaterialPtr phase = std::make_shared<Isotropic>(solid);
     add_mat(s, phase);
     return add_obj(s, std::make_shared<ConstantMedium>(phase, density, s->objs[(size_t)boundary]));
 }

@@ -1,0 +1,45 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (implemented in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/rtb200.h"
+#include "../rt_types.h"
+
+namespace rtb {
+
+struct RenderJob {
+    int32_t width, height, rows;      // rows = rendered rows (compat_threads quirk), rows <= height
+    int32_t spp_total;                // Config.samples_per_pixel (for path ids and the final divide)
+    int32_t sample_begin, sample_end; // this call's shard
+    int32_t max_depth;
+    uint64_t seed;
+};
+
+struct RenderTuning {
+    uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
+    int timed_extend = 0;           // 1: bracket every extend launch with CUDA events (for the roofline)
+    int count_events = 0;           // 1: count BVH node visits / primitive tests on the device
+};
+
+// Wavefront render of one shard into a device-resident int64 fixed-point accumulator (W*H*3).
+// Returns cudaSuccess or the first CUDA error; fills stats.
+cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const RenderTuning& tune, int64_t* d_accum, cudaStream_t stream,
+                          rt_stats* stats);
+
+// accum -> Screen-layout doubles (vec3.rs:89-107), rows >= rendered_rows stay 0
+cudaError_t launch_resolve(const int64_t* d_accum, double* d_screen, int32_t width, int32_t height, int32_t spp, int32_t rendered_rows,
+                           cudaStream_t stream);
+
+// world.hit for n rays (device pointers)
+cudaError_t launch_trace_batch(const DeviceScene& scene, const rt_ray* d_rays, int64_t n, double t_min, double t_max, int32_t flags, uint64_t seed,
+                               rt_hit* d_out, cudaStream_t stream);
+
+// unit-level device checks (E3): evaluates single device functions on small inputs
+// op 0: tex_value(tex = ia, u = in[0], v = in[1], p = in[2..5)) -> out[0..3)
+// op 1: perlin noise / turbulence of perlin table ia at p = in[0..3) -> out[0], out[1]
+// op 2: philox block ctr = (ia, ib, ic, id) key = (in[0], in[1]) as u32 -> out[0..4) as doubles
+// op 3: camera ray for (seed = ia|ib<<32, path_id = ic|id<<32, i = in[0], j = in[1], W = in[2], H = in[3]) -> out[0..7)
+cudaError_t launch_unit_op(const DeviceScene& scene, int op, uint32_t ia, uint32_t ib, uint32_t ic, uint32_t id, const double* in8, double* out8);
+
+} // namespace rtb

@@ -1,0 +1,641 @@
+// rt_device.cuh — device-side restatement of the reference hot path for sm_100a.
+//
+//   vec3.rs / ray.rs           -> D3 / Ray (f64)
+//   aabb.rs + bvh.rs           -> slab2() + trace_instance(): f32 slab test of sibling pairs fetched
+//                                 with two 128-bit read-only loads per node, short stack, ordered descent
+//   hit.rs  Hittable impls     -> hit_sphere / hit_rect / hit_box / hit_tri (f64), finalize_hit()
+//   hit.rs  Translate/RotateY  -> xform_ray() going in, chain post-processing coming out (quirks kept)
+//   hit.rs  ConstantMedium     -> medium_query()
+//   hit.rs  Material impls     -> scatter_*()
+//   texture.rs / perlin.rs     -> tex_value() / perlin_noise() / perlin_turbulence()
+//   camera.rs                  -> camera_get_ray()
+//   rand thread_rng()          -> PathRng (Philox-4x32-10, one counter step per draw)
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../rt_types.h"
+
+namespace rtb {
+
+#define RT_DEV __device__ __forceinline__
+#define RT_STACK 64
+
+// ------------------------------------------------------------------ D3 (vec3.rs)
+struct D3 {
+    double x, y, z;
+};
+RT_DEV D3 mk3(double x, double y, double z) { D3 r; r.x = x; r.y = y; r.z = z; return r; }
+RT_DEV D3 operator+(D3 a, D3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_DEV D3 operator-(D3 a, D3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_DEV D3 operator-(D3 a) { return mk3(-a.x, -a.y, -a.z); }
+RT_DEV D3 operator*(D3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_DEV D3 operator*(double s, D3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_DEV double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RT_DEV D3 cross(D3 a, D3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RT_DEV double length_squared(D3 a) { return dot(a, a); }
+RT_DEV D3 unit(D3 a) { return a * (1.0 / sqrt(length_squared(a))); }                 // vec3.rs:55-57
+RT_DEV D3 reflect(D3 v, D3 n) { return v - 2.0 * dot(v, n) * n; }                    // vec3.rs:64-66
+RT_DEV bool near_zero(D3 a) { const double s = 1e-8; return fabs(a.x) < s && fabs(a.y) < s && fabs(a.z) < s; } // vec3.rs:59-62
+RT_DEV D3 refract(D3 uv, D3 n, double etai_over_etat) {                              // vec3.rs:116-121
+    const double cos_theta = fmin(dot(-uv, n), 1.0);
+    const D3 r_out_perp = etai_over_etat * (uv + cos_theta * n);
+    const D3 r_out_parallel = -(sqrt(fabs(1.0 - length_squared(r_out_perp)))) * n;
+    return r_out_perp + r_out_parallel;
+}
+RT_DEV double axis_of(D3 a, int ax) { return ax == 0 ? a.x : (ax == 1 ? a.y : a.z); }
+
+struct Ray { // ray.rs:3-8
+    D3 o, d;
+    double time;
+};
+RT_DEV D3 ray_at(const Ray& r, double t) { return mk3(r.o.x + r.d.x * t, r.o.y + r.d.y * t, r.o.z + r.d.z * t); } // ray.rs:31-33 (mul then add)
+
+// ------------------------------------------------------------------ Philox-4x32-10 / PathRng
+RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        if (r) { k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    }
+    return c;
+}
+
+// Draw k of a path = word (k & 3) of block (path_lo, path_hi, k >> 2, 0) under key (seed_lo, seed_hi);
+// xi = u32 * 2^-32 (identical in oracle/rt_oracle.hpp PathCtx).
+struct PathRng {
+    uint2 key, path;
+    uint32_t draw, cached;
+    uint4 blk;
+    RT_DEV void init(uint64_t seed, uint64_t path_id, uint32_t draw0) {
+        key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        path = make_uint2((uint32_t)path_id, (uint32_t)(path_id >> 32));
+        draw = draw0;
+        cached = 0xffffffffu;
+    }
+    RT_DEV uint32_t next_u32() {
+        const uint32_t b = draw >> 2;
+        if (b != cached) {
+            blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
+            cached = b;
+        }
+        const uint32_t w = draw & 3u;
+        ++draw;
+        return w == 0 ? blk.x : (w == 1 ? blk.y : (w == 2 ? blk.z : blk.w));
+    }
+    RT_DEV double gen() { return (double)next_u32() * (1.0 / 4294967296.0); }
+    RT_DEV double gen_range(double a, double b) { return a + gen() * (b - a); }
+};
+RT_DEV double medium_xi(uint64_t seed, uint64_t path_id, uint32_t medium_prim_id, uint32_t segment) {
+    const uint4 o = philox4x32_10(make_uint4((uint32_t)path_id, (uint32_t)(path_id >> 32), medium_prim_id, 0x80000000u | segment),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return (double)o.x * (1.0 / 4294967296.0);
+}
+
+RT_DEV D3 random_in_unit_sphere(PathRng& g) { // vec3.rs:287-295
+    for (;;) {
+        const double a = g.gen_range(-1.0, 1.0), b = g.gen_range(-1.0, 1.0), c = g.gen_range(-1.0, 1.0);
+        const D3 p = mk3(a, b, c);
+        if (length_squared(p) < 1.0) return p;
+    }
+}
+RT_DEV D3 random_unit_vector(PathRng& g) { return unit(random_in_unit_sphere(g)); } // vec3.rs:297-299
+
+// ------------------------------------------------------------------ transforms (hit.rs:802-807, 893-904)
+RT_DEV void xform_ray(const XformOp* __restrict__ ops, uint32_t off, uint32_t len, Ray& r) {
+    for (uint32_t i = 0; i < len; ++i) {
+        const XformOp op = ops[off + i];
+        if (op.type == XF_TRANSLATE) {
+            r.o = mk3(r.o.x - op.a, r.o.y - op.b, r.o.z - op.c);
+        } else {
+            const double s = op.a, c = op.b;
+            r.o = mk3(c * r.o.x - s * r.o.z, r.o.y, s * r.o.x + c * r.o.z);
+            r.d = mk3(c * r.d.x - s * r.d.z, r.d.y, s * r.d.x + c * r.d.z);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ best-hit bookkeeping
+struct BestHit {
+    double t;        // closest_so_far
+    int32_t prim_id; // -1 = none; ties (equal t) go to the larger depth-first id = "later list element wins" (hit.rs:675-683)
+    uint32_t type, idx, side, inst;
+};
+
+#define RT_INF (__longlong_as_double(0x7ff0000000000000LL))
+
+RT_DEV void consider(const DeviceScene& S, BestHit& best, double t, uint32_t type, uint32_t idx, uint32_t side, uint32_t inst) {
+    if (!(t <= best.t) || !(t < RT_INF)) return; // NaN and +inf are rejected (documented divergence: the reference lets t = +inf through)
+    const int32_t pid = (int32_t)(__ldg(&S.meta[type][idx].prim_id) + side);
+    if (t < best.t || pid > best.prim_id) {
+        best.t = t; best.prim_id = pid; best.type = type; best.idx = idx; best.side = side; best.inst = inst;
+    }
+}
+
+// ------------------------------------------------------------------ primitive tests (f64)
+// Sphere / MovingSphere / GravitySphere::hit root selection (hit.rs:204-222, 282-300, 398-416)
+RT_DEV double sphere_root(const Ray& r, D3 c, double radius, double t_min, double t_max) {
+    const D3 oc = r.o - c;
+    const double a = length_squared(r.d);
+    const double half_b = dot(oc, r.d);
+    const double cc = length_squared(oc) - radius * radius;
+    const double disc = half_b * half_b - a * cc;
+    if (disc < 0.0) return RT_INF;
+    const double sqrtd = sqrt(disc);
+    const double inv_a = 1.0 / a;
+    double root = (-half_b - sqrtd) * inv_a;
+    if (root < t_min || t_max < root) {
+        root = (-half_b + sqrtd) * inv_a;
+        if (root < t_min || t_max < root) return RT_INF;
+    }
+    return root;
+}
+RT_DEV D3 moving_center(const DMoving& m, double time) { // hit.rs:275-278
+    const double f = (time - m.t0) / m.dt;
+    return mk3(m.c0[0] + f * m.dc[0], m.c0[1] + f * m.dc[1], m.c0[2] + f * m.dc[2]);
+}
+RT_DEV D3 gravity_center(const DeviceScene& S, const DGravity& g, double time) { // hit.rs:370-379
+    const double q = time / 0.001;
+    int64_t i = (q > 0.0) ? (int64_t)q : 0; // Rust `as usize`: saturating, negative/NaN -> 0
+    i -= g.idx0;
+    i = i < 0 ? 0 : (i >= g.n ? g.n - 1 : i); // window uploaded for the camera shutter; clamped
+    return mk3(g.x, __ldg(&S.gravity_table[g.table_off + (int32_t)i]), g.z);
+}
+// XyRect / XzRect / YzRect::hit (hit.rs:476-485, 541-550, 606-615): returns t or +inf
+RT_DEV double rect_t(const Ray& r, const DRect& q, double t_min, double t_max) {
+    const int ax = q.axis;
+    const int ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+    const double t = (q.k - axis_of(r.o, ax)) / axis_of(r.d, ax);
+    if (t < t_min || t > t_max) return RT_INF;
+    const double x = axis_of(r.o, ia) + t * axis_of(r.d, ia);
+    const double y = axis_of(r.o, ib) + t * axis_of(r.d, ib);
+    if (x < q.a0 || x > q.a1 || y < q.b0 || y > q.b1) return RT_INF;
+    return t;
+}
+// RectPrism = HittableList of six rects scanned in order with a shrinking closest_so_far
+// (hit.rs:722-769, 660-690): +z(p1.z), -z(p0.z), +y, -y, +x, -x.  Returns t and the winning side.
+RT_DEV double box_t(const Ray& r, const DBox& b, double t_min, double t_max, uint32_t& side_out) {
+    double closest = t_max;
+    bool any = false;
+    uint32_t side = 0;
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+        const int ax = s < 2 ? 2 : (s < 4 ? 1 : 0);
+        const int ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+        const double k = (s & 1) ? b.p0[ax] : b.p1[ax];
+        const double t = (k - axis_of(r.o, ax)) / axis_of(r.d, ax);
+        if (t < t_min || t > closest || !(t < RT_INF)) continue;
+        const double x = axis_of(r.o, ia) + t * axis_of(r.d, ia);
+        const double y = axis_of(r.o, ib) + t * axis_of(r.d, ib);
+        if (x < b.p0[ia] || x > b.p1[ia] || y < b.p0[ib] || y > b.p1[ib]) continue;
+        if (t != t) continue;
+        closest = t; any = true; side = (uint32_t)s;
+    }
+    side_out = side;
+    return any ? closest : RT_INF;
+}
+// Triangle::hit (hit.rs:111-149): plane hit + three inclusive edge tests; vertices/normal stored f32
+RT_DEV double tri_t(const Ray& r, const DTri* __restrict__ tp, double t_min, double t_max) {
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(tp));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(tp) + 1);
+    const float4 q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
+    const D3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q0.w, q1.x, q1.y), v2 = mk3(q1.z, q1.w, q2.x), n = mk3(q2.y, q2.z, q2.w);
+    const double nd = dot(n, r.d);
+    if (fabs(nd) < 0.0001) return RT_INF;
+    const double dd = -dot(n, v0);
+    const double t = -(dot(n, r.o) + dd) / nd;
+    if (t < t_min || t > t_max) return RT_INF;
+    const D3 p = ray_at(r, t);
+    if (dot(n, cross(v1 - v0, p - v0)) < 0.0) return RT_INF;
+    if (dot(n, cross(v2 - v1, p - v1)) < 0.0) return RT_INF;
+    if (dot(n, cross(v0 - v2, p - v2)) < 0.0) return RT_INF;
+    return t;
+}
+
+// ------------------------------------------------------------------ BVH traversal (aabb.rs:23-61, bvh.rs:97-112)
+struct RayF {
+    float idx, idy, idz, oodx, oody, oodz;
+};
+RT_DEV RayF make_rayf(const Ray& r) {
+    RayF f;
+    float dx = (float)r.d.x, dy = (float)r.d.y, dz = (float)r.d.z;
+    const float tiny = 1e-20f; // exact zeros become +-tiny so that no slab distance is inf - inf
+    dx = fabsf(dx) < tiny ? copysignf(tiny, dx) : dx;
+    dy = fabsf(dy) < tiny ? copysignf(tiny, dy) : dy;
+    dz = fabsf(dz) < tiny ? copysignf(tiny, dz) : dz;
+    f.idx = 1.0f / dx; f.idy = 1.0f / dy; f.idz = 1.0f / dz;
+    f.oodx = (float)r.o.x * f.idx; f.oody = (float)r.o.y * f.idy; f.oodz = (float)r.o.z * f.idz;
+    return f;
+}
+RT_DEV bool slab(const float4 lo, const float4 hi, const RayF& f, float t_min, float t_max, float& tn) {
+    const float x0 = fmaf(lo.x, f.idx, -f.oodx), x1 = fmaf(hi.x, f.idx, -f.oodx);
+    const float y0 = fmaf(lo.y, f.idy, -f.oody), y1 = fmaf(hi.y, f.idy, -f.oody);
+    const float z0 = fmaf(lo.z, f.idz, -f.oodz), z1 = fmaf(hi.z, f.idz, -f.oodz);
+    tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+    return tn <= tf;
+}
+RT_DEV float f32_up(double v) { return __double2float_ru(v); }
+RT_DEV float f32_down(double v) { return __double2float_rd(v); }
+
+struct TraceCounters {
+    uint32_t nodes, prims;
+};
+
+// Tests every primitive of one leaf against the object-space ray.
+RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t type, uint32_t first, uint32_t n, uint32_t inst) {
+    for (uint32_t i = first; i < first + n; ++i) {
+        switch (type) {
+        case PRIM_SPHERE: {
+            const double4 s = *reinterpret_cast<const double4*>(&S.spheres[i]);
+            consider(S, best, sphere_root(r, mk3(s.x, s.y, s.z), s.w, t_min, best.t), type, i, 0, inst);
+        } break;
+        case PRIM_MOVING: {
+            const DMoving m = S.movings[i];
+            consider(S, best, sphere_root(r, moving_center(m, r.time), m.r, t_min, best.t), type, i, 0, inst);
+        } break;
+        case PRIM_GRAVITY: {
+            const DGravity g = S.gravities[i];
+            consider(S, best, sphere_root(r, gravity_center(S, g, r.time), g.r, t_min, best.t), type, i, 0, inst);
+        } break;
+        case PRIM_RECT: {
+            const DRect q = S.rects[i];
+            consider(S, best, rect_t(r, q, t_min, best.t), type, i, 0, inst);
+        } break;
+        case PRIM_BOX: {
+            const DBox b = S.boxes[i];
+            uint32_t side;
+            const double t = box_t(r, b, t_min, best.t, side);
+            consider(S, best, t, type, i, side, inst);
+        } break;
+        default: { // PRIM_TRI
+            consider(S, best, tri_t(r, &S.tris[i], t_min, best.t), type, i, 0, inst);
+        } break;
+        }
+    }
+}
+
+// Closest hit inside one instance; `r` is already in the instance's space.
+template <bool COUNT>
+RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r, double t_min, BestHit& best, TraceCounters* cnt) {
+    const Instance* ip = &S.instances[inst_idx];
+    const RayF f = make_rayf(r);
+    const float tminf = f32_down(t_min);
+    const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
+    uint32_t stack[RT_STACK];
+    int sp = 0;
+    uint32_t cur = __ldg(&ip->root);
+    {   // root: its own box, then leaf or descend
+        const float4 lo = __ldg(nodes + 2 * cur), hi = __ldg(nodes + 2 * cur + 1);
+        float tn;
+        if (COUNT) cnt->nodes++;
+        if (!slab(lo, hi, f, tminf, f32_up(best.t), tn)) return;
+        const uint32_t count = __float_as_uint(hi.w);
+        if (count) {
+            if (COUNT) cnt->prims += count & 0xffffffu;
+            leaf_test(S, r, t_min, best, count >> 24, __float_as_uint(lo.w), count & 0xffffffu, inst_idx);
+            return;
+        }
+        cur = __float_as_uint(lo.w);
+    }
+    for (;;) {
+        // cur = index of the left child of an interior node: fetch both siblings (64 B)
+        const float4 lo0 = __ldg(nodes + 2 * cur), hi0 = __ldg(nodes + 2 * cur + 1);
+        const float4 lo1 = __ldg(nodes + 2 * cur + 2), hi1 = __ldg(nodes + 2 * cur + 3);
+        const float tmaxf = f32_up(best.t);
+        float tn0, tn1;
+        bool h0 = slab(lo0, hi0, f, tminf, tmaxf, tn0);
+        bool h1 = slab(lo1, hi1, f, tminf, tmaxf, tn1);
+        if (COUNT) cnt->nodes += 2;
+        const uint32_t c0 = __float_as_uint(hi0.w), c1 = __float_as_uint(hi1.w);
+        if (h0 && c0) {
+            if (COUNT) cnt->prims += c0 & 0xffffffu;
+            leaf_test(S, r, t_min, best, c0 >> 24, __float_as_uint(lo0.w), c0 & 0xffffffu, inst_idx);
+            h0 = false;
+        }
+        if (h1 && c1) {
+            // the first leaf may have shortened the ray
+            if (tn1 <= f32_up(best.t)) {
+                if (COUNT) cnt->prims += c1 & 0xffffffu;
+                leaf_test(S, r, t_min, best, c1 >> 24, __float_as_uint(lo1.w), c1 & 0xffffffu, inst_idx);
+            }
+            h1 = false;
+        }
+        if (h0 && h1) {
+            const uint32_t n0 = __float_as_uint(lo0.w), n1 = __float_as_uint(lo1.w);
+            const bool first0 = tn0 <= tn1;
+            cur = first0 ? n0 : n1;
+            if (sp < RT_STACK) stack[sp++] = first0 ? n1 : n0;
+        } else if (h0) {
+            cur = __float_as_uint(lo0.w);
+        } else if (h1) {
+            cur = __float_as_uint(lo1.w);
+        } else {
+            if (sp == 0) return;
+            cur = stack[--sp];
+        }
+    }
+}
+
+RT_DEV bool inst_box_hit(const Instance* ip, const Ray& r, double t_min, double t_max) {
+    const RayF f = make_rayf(r);
+    float tn;
+    const float4 lo = make_float4(__ldg(&ip->bmin[0]), __ldg(&ip->bmin[1]), __ldg(&ip->bmin[2]), 0.f);
+    const float4 hi = make_float4(__ldg(&ip->bmax[0]), __ldg(&ip->bmax[1]), __ldg(&ip->bmax[2]), 0.f);
+    return slab(lo, hi, f, f32_down(t_min), f32_up(t_max), tn);
+}
+
+// world.hit restricted to the instances [i0, i1): the main world or one medium's boundary.
+template <bool COUNT>
+RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, const Ray& world_ray, double t_min, BestHit& best, TraceCounters* cnt) {
+    for (uint32_t i = i0; i < i1; ++i) {
+        const Instance* ip = &S.instances[i];
+        const uint32_t len = __ldg(&ip->chain_len);
+        if (len == 0) {
+            trace_instance<COUNT>(S, i, world_ray, t_min, best, cnt);
+        } else {
+            Ray r = world_ray;
+            xform_ray(S.ops, __ldg(&ip->chain_off), len, r);
+            trace_instance<COUNT>(S, i, r, t_min, best, cnt);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ hit record (hit.rs:9-18)
+struct HitRec {
+    D3 p, n;
+    double t, u, v;
+    uint32_t mat, prim_id;
+    bool front;
+};
+RT_DEV void face_forward(D3 dir, D3 outward, D3& n, bool& front) { // hit.rs:69-79
+    front = dot(dir, outward) < 0.0;
+    n = front ? outward : -outward;
+}
+RT_DEV void sphere_uv(D3 p, double& u, double& v) { // hit.rs:195-200
+    const double PI = 3.14159265358979323846264338327950288;
+    const double theta = acos(-p.y);
+    const double phi = atan2(-p.z, p.x) + PI;
+    u = phi / (2.0 * PI);
+    v = theta / PI;
+}
+
+// Rebuild the full HitRecord of the winning primitive, then undo the wrapper chain from the inside
+// out exactly as Translate::hit / RotateY::hit do (hit.rs:808-820, 909-930), including their
+// re-face-forwarding quirks.
+template <bool WANT_UV>
+RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const BestHit& b) {
+    HitRec h;
+    const Instance* ip = &S.instances[b.inst];
+    const uint32_t coff = __ldg(&ip->chain_off), clen = __ldg(&ip->chain_len);
+    Ray r = world_ray;
+    xform_ray(S.ops, coff, clen, r);
+    const PrimMeta m = S.meta[b.type][b.idx];
+    h.mat = m.mat_id;
+    h.prim_id = m.prim_id + b.side;
+    h.t = b.t;
+    h.p = ray_at(r, b.t);
+    h.u = 0.0; h.v = 0.0;
+    D3 outward;
+    switch (b.type) {
+    case PRIM_SPHERE: {
+        const DSphere s = S.spheres[b.idx];
+        outward = (h.p - mk3(s.cx, s.cy, s.cz)) * (1.0 / s.r);
+        bool need_uv = WANT_UV;
+        if (!WANT_UV) need_uv = (__ldg(&S.materials[m.mat_id].flags) & 1u) != 0;
+        if (need_uv) sphere_uv(outward, h.u, h.v);
+    } break;
+    case PRIM_MOVING: {
+        const DMoving s = S.movings[b.idx];
+        outward = (h.p - moving_center(s, r.time)) * (1.0 / s.r); // u = v = 0 (hit.rs:310-311)
+    } break;
+    case PRIM_GRAVITY: {
+        const DGravity s = S.gravities[b.idx];
+        outward = (h.p - gravity_center(S, s, r.time)) * (1.0 / s.r);
+    } break;
+    case PRIM_RECT: {
+        const DRect q = S.rects[b.idx];
+        const int ax = q.axis, ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+        h.u = (axis_of(h.p, ia) - q.a0) / (q.a1 - q.a0); // hit.rs:486-487 (x, y recomputed as o + t*d = p)
+        h.v = (axis_of(h.p, ib) - q.b0) / (q.b1 - q.b0);
+        outward = mk3(ax == 0 ? 1.0 : 0.0, ax == 1 ? 1.0 : 0.0, ax == 2 ? 1.0 : 0.0);
+    } break;
+    case PRIM_BOX: {
+        const DBox q = S.boxes[b.idx];
+        const int s = (int)b.side;
+        const int ax = s < 2 ? 2 : (s < 4 ? 1 : 0), ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+        h.u = (axis_of(h.p, ia) - q.p0[ia]) / (q.p1[ia] - q.p0[ia]);
+        h.v = (axis_of(h.p, ib) - q.p0[ib]) / (q.p1[ib] - q.p0[ib]);
+        outward = mk3(ax == 0 ? 1.0 : 0.0, ax == 1 ? 1.0 : 0.0, ax == 2 ? 1.0 : 0.0);
+    } break;
+    default: { // PRIM_TRI: u = v = 1 (hit.rs:157-158)
+        const DTri* tp = &S.tris[b.idx];
+        const float4 q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
+        outward = mk3(q2.y, q2.z, q2.w);
+        h.u = 1.0; h.v = 1.0;
+    } break;
+    }
+    face_forward(r.d, outward, h.n, h.front);
+    // unwind the chain: r currently holds the innermost ray
+    D3 d_in = r.d;
+    for (int i = (int)clen - 1; i >= 0; --i) {
+        const XformOp op = S.ops[coff + i];
+        if (op.type == XF_TRANSLATE) {
+            h.p = mk3(h.p.x + op.a, h.p.y + op.b, h.p.z + op.c);
+            face_forward(d_in, h.n, h.n, h.front); // against moved_r (same direction), hit.rs:810
+        } else {
+            const double s = op.a, c = op.b;
+            h.p = mk3(c * h.p.x + s * h.p.z, h.p.y, -s * h.p.x + c * h.p.z);
+            const D3 nw = mk3(c * h.n.x + s * h.n.z, h.n.y, -s * h.n.x + c * h.n.z);
+            face_forward(d_in, nw, h.n, h.front); // world normal against the OBJECT-space ray, hit.rs:921
+            d_in = mk3(c * d_in.x + s * d_in.z, d_in.y, -s * d_in.x + c * d_in.z); // direction one level out
+        }
+    }
+    return h;
+}
+
+// ------------------------------------------------------------------ ConstantMedium::hit (hit.rs:955-986)
+template <bool COUNT>
+RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray, double t_min, double& closest, int32_t& winner, D3& p_out,
+                         uint64_t seed, uint64_t path_id, uint32_t segment, TraceCounters* cnt) {
+    const Medium md = S.media[mi];
+    Ray r = world_ray;
+    xform_ray(S.ops, md.chain_off, md.chain_len, r);
+    BestHit b1; b1.t = RT_INF; b1.prim_id = -1; b1.type = 0; b1.idx = 0; b1.side = 0; b1.inst = 0;
+    trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, -RT_INF, b1, cnt);
+    if (b1.prim_id < 0) return;
+    BestHit b2; b2.t = RT_INF; b2.prim_id = -1; b2.type = 0; b2.idx = 0; b2.side = 0; b2.inst = 0;
+    trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, b1.t + 0.0001, b2, cnt);
+    if (b2.prim_id < 0) return;
+    double t1 = fmax(b1.t, t_min);
+    const double t2 = fmin(b2.t, closest);
+    if (t1 >= t2) return;
+    if (t1 < 0.0) t1 = 0.0;
+    const double ray_length = sqrt(length_squared(r.d));
+    const double distance_inside_boundary = (t2 - t1) * ray_length;
+    const double hit_distance = md.neg_inv_density * log(medium_xi(seed, path_id, md.prim_id, segment));
+    if (hit_distance > distance_inside_boundary) return;
+    const double t = t1 + hit_distance / ray_length;
+    if (!(t <= closest)) return;
+    if (t == closest && (int32_t)md.prim_id < winner) return;
+    closest = t;
+    winner = (int32_t)mi;
+    // p = r.at(t) in the medium's space, brought back out through the medium's own chain
+    D3 p = ray_at(r, t);
+    for (int i = (int)md.chain_len - 1; i >= 0; --i) {
+        const XformOp op = S.ops[md.chain_off + i];
+        if (op.type == XF_TRANSLATE) p = mk3(p.x + op.a, p.y + op.b, p.z + op.c);
+        else p = mk3(op.b * p.x + op.a * p.z, p.y, -op.a * p.x + op.b * p.z);
+    }
+    p_out = p;
+}
+
+// world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
+// surface (order independent because medium draws are keyed).
+template <bool COUNT, bool WANT_UV>
+RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double t_max, bool media, uint64_t seed, uint64_t path_id, uint32_t segment,
+                      HitRec& h, TraceCounters* cnt) {
+    BestHit best; best.t = t_max; best.prim_id = -1; best.type = 0; best.idx = 0; best.side = 0; best.inst = 0;
+    trace_instances<COUNT>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
+    double closest = best.t;
+    int32_t mwin = -1;
+    D3 mp = mk3(0, 0, 0);
+    if (media) {
+        for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT>(S, mi, ray, t_min, closest, mwin, mp, seed, path_id, segment, cnt);
+    }
+    if (mwin >= 0) {
+        const Medium md = S.media[mwin];
+        h.p = mp; h.n = mk3(0, 0, 0); h.t = closest; h.u = 0.0; h.v = 0.0; h.front = true; // hit.rs:975-984
+        h.mat = md.mat_id; h.prim_id = md.prim_id;
+        return true;
+    }
+    if (best.prim_id < 0) return false;
+    h = finalize_hit<WANT_UV>(S, ray, best);
+    return true;
+}
+
+// ------------------------------------------------------------------ perlin.rs / texture.rs
+struct F3 { float x, y, z; };
+RT_DEV F3 mkf3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+
+RT_DEV double perlin_noise(const PerlinTable* __restrict__ pt, D3 p) { // perlin.rs:28-52, 85-106
+    const double fx = floor(p.x), fy = floor(p.y), fz = floor(p.z);
+    const double u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    const int i = (int)fx, j = (int)fy, k = (int)fz;
+    const double uu = u * u * (3.0 - 2.0 * u), vv = v * v * (3.0 - 2.0 * v), ww = w * w * (3.0 - 2.0 * w);
+    double accum = 0.0;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                const int idx = pt->perm_x[(i + di) & 255] ^ pt->perm_y[(j + dj) & 255] ^ pt->perm_z[(k + dk) & 255];
+                const double cx = pt->ranvec[idx][0], cy = pt->ranvec[idx][1], cz = pt->ranvec[idx][2];
+                const double wx = u - di, wy = v - dj, wz = w - dk;
+                accum += (di ? uu : (1.0 - uu)) * (dj ? vv : (1.0 - vv)) * (dk ? ww : (1.0 - ww)) * (cx * wx + cy * wy + cz * wz);
+            }
+    return accum;
+}
+RT_DEV double perlin_turbulence(const PerlinTable* __restrict__ pt, D3 p, int depth) { // perlin.rs:54-66
+    double accum = 0.0, weight = 1.0;
+    D3 tp = p;
+    for (int o = 0; o < depth; ++o) {
+        accum += weight * perlin_noise(pt, tp);
+        weight *= 0.5;
+        tp = tp * 2.0;
+    }
+    return fabs(accum);
+}
+
+RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p) { // texture.rs:7-9
+    for (int guard = 0; guard < 64; ++guard) {
+        const DTexture* t = &S.textures[tex];
+        const uint32_t type = __ldg(&t->type);
+        if (type == TEX_SOLID) return mkf3(__ldg(&t->rgb[0]), __ldg(&t->rgb[1]), __ldg(&t->rgb[2])); // texture.rs:27-31
+        if (type == TEX_CHECKER) { // texture.rs:54-64: sign of sin(10x) sin(10y) sin(10z)
+            const float sines = sinf((float)(10.0 * p.x)) * sinf((float)(10.0 * p.y)) * sinf((float)(10.0 * p.z));
+            tex = sines < 0.0f ? __ldg(&t->b) : __ldg(&t->a);
+            continue;
+        }
+        if (type == TEX_NOISE) { // texture.rs:80-88
+            const double s = 0.5 * (1.0 + sin(t->scale * p.z + 10.0 * perlin_turbulence(&S.perlin[t->a], p, 7)));
+            return mkf3((float)s, (float)s, (float)s);
+        }
+        // TEX_IMAGE, texture.rs:102-121: nearest texel, row 0 = top of file, v flipped
+        double uc = u < 0.0 ? 0.0 : (u > 1.0 ? 1.0 : u);
+        double vc = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+        vc = 1.0 - vc;
+        const int W = (int)t->w, H = (int)t->h;
+        int i = (int)(uc * (double)W), j = (int)(vc * (double)H);
+        i = min(i, W - 1); j = min(j, H - 1);
+        const float4 px = __ldg(&S.texels[t->a + (size_t)j * W + i]);
+        const float cs = 1.0f / 255.0f;
+        return mkf3(cs * px.x, cs * px.y, cs * px.z);
+    }
+    return mkf3(0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------ Material::scatter (hit.rs:1004-1152)
+// Returns true when the path continues; `dir` = scattered direction, `att` = attenuation.
+RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, PathRng& g, D3& dir, F3& att) {
+    D3 sd = n + random_unit_vector(g);
+    if (near_zero(sd)) sd = n;
+    dir = sd;
+    att = tex_value(S, m.tex, u, v, p);
+    return true;
+}
+RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, PathRng& g, D3& dir, F3& att) {
+    const D3 reflected = reflect(unit(d_in), n);
+    dir = reflected + m.fuzz_or_ir * random_in_unit_sphere(g); // the draw happens even when fuzz == 0
+    att = mkf3(m.albedo[0], m.albedo[1], m.albedo[2]);
+    return dot(dir, n) > 0.0;
+}
+RT_DEV double reflectance(double cosine, double ref_idx) { // hit.rs:1095-1099
+    double r0 = (1.0 - ref_idx) / (1.0 + ref_idx);
+    r0 = r0 * r0;
+    const double x = 1.0 - cosine;
+    return r0 + (1.0 - r0) * (x * x * x * x * x);
+}
+RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D3 n, bool front, PathRng& g, D3& dir, F3& att) {
+    att = mkf3(1.f, 1.f, 1.f);
+    const double ratio = front ? 1.0 / m.fuzz_or_ir : m.fuzz_or_ir;
+    const D3 ud = unit(d_in);
+    const double cos_theta = fmin(dot(-ud, n), 1.0);
+    const double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+    const bool cannot_refract = ratio * sin_theta > 1.0;
+    if (cannot_refract || reflectance(cos_theta, ratio) > g.gen()) dir = reflect(ud, n); // `||` short-circuit: draw only if refraction is possible
+    else dir = refract(ud, n, ratio);
+    return true;
+}
+RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, PathRng& g, D3& dir, F3& att) {
+    dir = random_in_unit_sphere(g); // not normalised (hit.rs:1007)
+    att = tex_value(S, m.tex, u, v, p);
+    return true;
+}
+
+// ------------------------------------------------------------------ Camera::get_ray (camera.rs:59-71)
+RT_DEV Ray camera_get_ray(const DCamera& c, double s, double t, PathRng& g) {
+    double rx, ry;
+    for (;;) { // random_in_unit_disk, vec3.rs:310-322 (runs even when lens_radius == 0)
+        rx = g.gen_range(-1.0, 1.0);
+        ry = g.gen_range(-1.0, 1.0);
+        if (rx * rx + ry * ry + 0.0 < 1.0) break;
+    }
+    rx *= c.lens_radius; ry *= c.lens_radius;
+    const D3 u = mk3(c.u[0], c.u[1], c.u[2]), v = mk3(c.v[0], c.v[1], c.v[2]);
+    const D3 offset = u * rx + v * ry;
+    const D3 origin = mk3(c.origin[0], c.origin[1], c.origin[2]);
+    const D3 llc = mk3(c.lower_left_corner[0], c.lower_left_corner[1], c.lower_left_corner[2]);
+    const D3 hor = mk3(c.horizontal[0], c.horizontal[1], c.horizontal[2]), ver = mk3(c.vertical[0], c.vertical[1], c.vertical[2]);
+    Ray r;
+    r.o = origin + offset;
+    r.d = llc + s * hor + t * ver - origin - offset;
+    r.time = g.gen_range(c.time1, c.time2);
+    return r;
+}
+
+} // namespace rtb

@@ -1,0 +1,1040 @@
+// scene.cpp — the C-ABI of include/rtb200.h: scene DAG recording, depth-first leaf numbering,
+// flattening into the device layout of rt_types.h, BVH build, upload, and the render / trace entry
+// points that launch the sm_100a kernels.  No CPU fallback: without a CUDA device commit / render /
+// trace return RT_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/rtb200.h"
+#include "../cuda/kernels.h"
+#include "../rt_types.h"
+#include "bvh_build.hpp"
+#include "io.hpp"
+#include "world.hpp"
+
+using namespace rtb;
+
+namespace {
+
+thread_local std::string g_err;
+int32_t fail(int32_t code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int32_t fail_cuda(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return RT_ERR_CUDA;
+}
+
+enum NodeKind { N_SPHERE, N_MOVING, N_GRAVITY, N_RECT, N_BOX, N_TRI, N_MESH, N_LIST, N_BVH, N_TRANSLATE, N_ROTY, N_MEDIUM };
+
+struct MeshData {
+    std::vector<double> verts;   // xyz
+    std::vector<uint32_t> faces; // 3 per triangle
+};
+
+struct Node {
+    NodeKind kind;
+    double d[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int32_t axis = 0;
+    int32_t mat = -1;
+    std::vector<int32_t> children;
+    std::shared_ptr<MeshData> mesh;
+    std::shared_ptr<std::vector<double>> grav; // GravitySphere::stored
+    int32_t prim_base = -1;                    // depth-first id of the first leaf this node produces
+};
+
+struct TexDesc {
+    uint32_t type;
+    double rgb[3] = {0, 0, 0};
+    int32_t a = 0, b = 0;
+    double scale = 0;
+    int32_t w = 0, h = 0;
+    std::shared_ptr<PerlinTable> perlin;
+    std::shared_ptr<std::vector<float>> texels; // rgba
+};
+struct MatDesc {
+    uint32_t type;
+    int32_t tex = 0;
+    double albedo[3] = {0, 0, 0};
+    double param = 0;
+};
+
+struct CameraDesc {
+    bool set = false;
+    DCamera cam;
+};
+
+struct DeviceBuffers {
+    std::vector<void*> allocs;
+    DeviceScene scene;
+    bool valid = false;
+    void release() {
+        for (void* p : allocs) cudaFree(p);
+        allocs.clear();
+        valid = false;
+    }
+};
+
+} // namespace
+
+struct rt_scene {
+    std::vector<TexDesc> tex;
+    std::vector<MatDesc> mats;
+    std::vector<Node> nodes;
+    int32_t root = -1;
+    CameraDesc camera;
+    double background[3] = {0, 0, 0};
+    int32_t n_prims = 0;
+    bool committed = false;
+    double span0 = 0.0, span1 = 1.0; // time span the moving-primitive bounds cover
+    double domain_radius = 0.0;
+    DeviceBuffers dev;
+    RenderTuning tuning;
+    ~rt_scene() { dev.release(); }
+};
+
+#define CHECK_SCENE(s) \
+    if (!(s)) return fail(RT_ERR_INVALID, "null scene")
+#define CHECK_TEX(s, id) \
+    if ((id) < 0 || (size_t)(id) >= (s)->tex.size()) return fail(RT_ERR_INVALID, "texture id out of range")
+#define CHECK_MAT(s, id) \
+    if ((id) < 0 || (size_t)(id) >= (s)->mats.size()) return fail(RT_ERR_INVALID, "material id out of range")
+#define CHECK_OBJ(s, id) \
+    if ((id) < 0 || (size_t)(id) >= (s)->nodes.size()) return fail(RT_ERR_INVALID, "hittable id out of range")
+
+namespace {
+
+int32_t add_node(rt_scene* s, Node&& n) {
+    s->nodes.push_back(std::move(n));
+    s->committed = false;
+    return (int32_t)s->nodes.size() - 1;
+}
+
+// ---------------------------------------------------------------- depth-first leaf numbering
+// Same walk as the oracle's number_leaves(): leaves get ids at first visit; a box takes 6, a mesh
+// one per triangle, a medium takes one id and then numbers its boundary.
+void number_leaves(rt_scene* s, int32_t id, int32_t& next) {
+    Node& n = s->nodes[(size_t)id];
+    switch (n.kind) {
+    case N_SPHERE: case N_MOVING: case N_GRAVITY: case N_RECT: case N_TRI:
+        if (n.prim_base < 0) { n.prim_base = next; next += 1; }
+        break;
+    case N_BOX:
+        if (n.prim_base < 0) { n.prim_base = next; next += 6; }
+        break;
+    case N_MESH:
+        if (n.prim_base < 0) { n.prim_base = next; next += (int32_t)(n.mesh->faces.size() / 3); }
+        break;
+    case N_LIST: case N_BVH: case N_TRANSLATE: case N_ROTY:
+        for (int32_t c : n.children) number_leaves(s, c, next);
+        break;
+    case N_MEDIUM:
+        if (n.prim_base < 0) { n.prim_base = next; next += 1; }
+        number_leaves(s, n.children[0], next);
+        break;
+    }
+}
+
+// ---------------------------------------------------------------- flattening
+struct FlatPrim {
+    uint32_t type;
+    int32_t node;     // source node
+    uint32_t sub;     // triangle index inside a mesh
+    uint32_t mat, prim_id;
+    double bmin[3], bmax[3];
+};
+struct InstBuild {
+    std::vector<int32_t> key; // transform node ids, outermost first
+    std::vector<XformOp> chain;
+    std::vector<FlatPrim> prims;
+};
+struct WorldBuild {
+    std::vector<InstBuild> inst;
+};
+struct MediumBuild {
+    int32_t node;
+    std::vector<XformOp> chain;
+    size_t world;
+};
+
+struct Flattener {
+    rt_scene* s;
+    std::vector<WorldBuild> worlds;
+    std::vector<MediumBuild> media;
+    std::string error;
+    int32_t status = RT_OK;
+
+    InstBuild& instance_for(size_t world, const std::vector<int32_t>& key, const std::vector<XformOp>& chain) {
+        for (InstBuild& ib : worlds[world].inst)
+            if (ib.key == key) return ib;
+        InstBuild ib;
+        ib.key = key;
+        ib.chain = chain;
+        worlds[world].inst.push_back(std::move(ib));
+        return worlds[world].inst.back();
+    }
+
+    void sphere_box(const double c[3], double r, double mn[3], double mx[3]) {
+        for (int a = 0; a < 3; ++a) { mn[a] = c[a] - std::fabs(r); mx[a] = c[a] + std::fabs(r); }
+    }
+
+    void add_leaf(size_t world, const std::vector<int32_t>& key, const std::vector<XformOp>& chain, int32_t id) {
+        const Node& n = s->nodes[(size_t)id];
+        InstBuild& ib = instance_for(world, key, chain);
+        FlatPrim p;
+        p.node = id; p.sub = 0; p.mat = (uint32_t)n.mat; p.prim_id = (uint32_t)n.prim_base;
+        switch (n.kind) {
+        case N_SPHERE: p.type = PRIM_SPHERE; sphere_box(n.d, n.d[3], p.bmin, p.bmax); break;
+        case N_MOVING: { // bounds over the span (MovingSphere::bounding_box, hit.rs:317-327; motion is linear)
+            p.type = PRIM_MOVING;
+            const double t0 = n.d[6], t1 = n.d[7], r = n.d[8];
+            double c0[3], c1[3], a0[3], a1[3], b0[3], b1[3];
+            for (int a = 0; a < 3; ++a) {
+                c0[a] = n.d[a] + ((s->span0 - t0) / (t1 - t0)) * (n.d[3 + a] - n.d[a]);
+                c1[a] = n.d[a] + ((s->span1 - t0) / (t1 - t0)) * (n.d[3 + a] - n.d[a]);
+            }
+            sphere_box(c0, r, a0, a1);
+            sphere_box(c1, r, b0, b1);
+            for (int a = 0; a < 3; ++a) { p.bmin[a] = std::fmin(a0[a], b0[a]); p.bmax[a] = std::fmax(a1[a], b1[a]); }
+        } break;
+        case N_GRAVITY: { // bounds over the uploaded window of the height table
+            p.type = PRIM_GRAVITY;
+            int64_t i0, i1;
+            gravity_window(*n.grav, i0, i1);
+            double ymin = 1e300, ymax = -1e300;
+            for (int64_t i = i0; i <= i1; ++i) { ymin = std::fmin(ymin, (*n.grav)[(size_t)i]); ymax = std::fmax(ymax, (*n.grav)[(size_t)i]); }
+            const double r = std::fabs(n.d[4]);
+            p.bmin[0] = n.d[0] - r; p.bmax[0] = n.d[0] + r;
+            p.bmin[1] = ymin - r; p.bmax[1] = ymax + r;
+            p.bmin[2] = n.d[2] - r; p.bmax[2] = n.d[2] + r;
+        } break;
+        case N_RECT: { // hit.rs:503-508, 568-573, 633-638
+            p.type = PRIM_RECT;
+            const int ax = n.axis, ia = ax == 0 ? 1 : 0, ib2 = ax == 2 ? 1 : 2;
+            p.bmin[ax] = n.d[4] - 0.0001; p.bmax[ax] = n.d[4] + 0.0001;
+            p.bmin[ia] = std::fmin(n.d[0], n.d[1]); p.bmax[ia] = std::fmax(n.d[0], n.d[1]);
+            p.bmin[ib2] = std::fmin(n.d[2], n.d[3]); p.bmax[ib2] = std::fmax(n.d[2], n.d[3]);
+        } break;
+        case N_BOX:
+            p.type = PRIM_BOX;
+            for (int a = 0; a < 3; ++a) { p.bmin[a] = std::fmin(n.d[a], n.d[3 + a]); p.bmax[a] = std::fmax(n.d[a], n.d[3 + a]); }
+            break;
+        case N_TRI:
+            p.type = PRIM_TRI;
+            for (int a = 0; a < 3; ++a) {
+                p.bmin[a] = std::fmin(n.d[a], std::fmin(n.d[3 + a], n.d[6 + a]));
+                p.bmax[a] = std::fmax(n.d[a], std::fmax(n.d[3 + a], n.d[6 + a]));
+            }
+            break;
+        case N_MESH: {
+            const MeshData& m = *n.mesh;
+            const size_t nt = m.faces.size() / 3;
+            ib.prims.reserve(ib.prims.size() + nt);
+            for (size_t t = 0; t < nt; ++t) {
+                FlatPrim q;
+                q.type = PRIM_TRI; q.node = id; q.sub = (uint32_t)t; q.mat = (uint32_t)n.mat; q.prim_id = (uint32_t)n.prim_base + (uint32_t)t;
+                const double* v0 = &m.verts[3 * (size_t)m.faces[3 * t]];
+                const double* v1 = &m.verts[3 * (size_t)m.faces[3 * t + 1]];
+                const double* v2 = &m.verts[3 * (size_t)m.faces[3 * t + 2]];
+                for (int a = 0; a < 3; ++a) {
+                    q.bmin[a] = std::fmin(v0[a], std::fmin(v1[a], v2[a]));
+                    q.bmax[a] = std::fmax(v0[a], std::fmax(v1[a], v2[a]));
+                }
+                ib.prims.push_back(q);
+            }
+            return;
+        }
+        default: return;
+        }
+        ib.prims.push_back(p);
+    }
+
+    void gravity_window(const std::vector<double>& tab, int64_t& i0, int64_t& i1) {
+        const double q0 = s->span0 / 0.001, q1 = s->span1 / 0.001;
+        i0 = q0 > 0.0 ? (int64_t)q0 : 0;
+        i1 = q1 > 0.0 ? (int64_t)q1 : 0;
+        i1 += 1; // time2 itself is exclusive, one guard entry
+        const int64_t last = (int64_t)tab.size() - 1;
+        i0 = std::min(std::max<int64_t>(i0, 0), last);
+        i1 = std::min(std::max<int64_t>(i1, i0), last);
+    }
+
+    void visit(int32_t id, size_t world, std::vector<int32_t>& key, std::vector<XformOp>& chain, bool in_boundary, int depth) {
+        if (status != RT_OK) return;
+        if (depth > 4096) { status = RT_ERR_UNSUPPORTED; error = "scene graph deeper than 4096 (cycle?)"; return; }
+        const Node& n = s->nodes[(size_t)id];
+        switch (n.kind) {
+        case N_LIST: case N_BVH:
+            for (int32_t c : n.children) visit(c, world, key, chain, in_boundary, depth + 1);
+            break;
+        case N_TRANSLATE: {
+            XformOp op; op.type = XF_TRANSLATE; op.pad_ = 0; op.a = n.d[0]; op.b = n.d[1]; op.c = n.d[2];
+            key.push_back(id); chain.push_back(op);
+            visit(n.children[0], world, key, chain, in_boundary, depth + 1);
+            key.pop_back(); chain.pop_back();
+        } break;
+        case N_ROTY: {
+            XformOp op; op.type = XF_ROTATE_Y; op.pad_ = 0; op.a = n.d[0]; op.b = n.d[1]; op.c = 0.0; // sin, cos
+            key.push_back(id); chain.push_back(op);
+            visit(n.children[0], world, key, chain, in_boundary, depth + 1);
+            key.pop_back(); chain.pop_back();
+        } break;
+        case N_MEDIUM: {
+            if (in_boundary) { status = RT_ERR_UNSUPPORTED; error = "ConstantMedium inside the boundary of another ConstantMedium is not supported"; return; }
+            MediumBuild mb;
+            mb.node = id;
+            mb.chain = chain;
+            worlds.emplace_back();
+            mb.world = worlds.size() - 1;
+            media.push_back(mb);
+            std::vector<int32_t> k2;
+            std::vector<XformOp> c2;
+            visit(n.children[0], mb.world, k2, c2, true, depth + 1);
+        } break;
+        default:
+            add_leaf(world, key, chain, id);
+            break;
+        }
+    }
+};
+
+template <class T>
+cudaError_t upload(DeviceBuffers& dev, const std::vector<T>& v, const T*& out) {
+    out = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    dev.allocs.push_back(p);
+    if (!v.empty()) {
+        e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+    }
+    out = reinterpret_cast<const T*>(p);
+    return cudaSuccess;
+}
+
+bool tex_reads_uv(const rt_scene* s, int32_t t, int depth = 0) {
+    if (depth > 64) return false;
+    const TexDesc& d = s->tex[(size_t)t];
+    if (d.type == TEX_IMAGE) return true;
+    if (d.type == TEX_CHECKER) return tex_reads_uv(s, d.a, depth + 1) || tex_reads_uv(s, d.b, depth + 1);
+    return false;
+}
+
+struct HostFlat {
+    std::vector<BvhNode32> nodes;
+    std::vector<DSphere> spheres; std::vector<DMoving> movings; std::vector<DGravity> gravities; std::vector<double> gtable;
+    std::vector<DRect> rects; std::vector<DBox> boxes; std::vector<DTri> tris;
+    std::vector<PrimMeta> meta[PRIM_TYPE_COUNT];
+    std::vector<Instance> instances;
+    std::vector<XformOp> ops;
+    std::vector<Medium> media;
+    std::vector<DMaterial> dmats;
+    std::vector<DTexture> dtex;
+    std::vector<PerlinTable> perlin;
+    std::vector<float4> texels;
+    uint32_t n_main_instances = 0;
+    int max_depth = 0;
+    double pad = 0.0;
+};
+
+// host half of rt_scene_commit: numbering, flattening, BVH build (no CUDA needed)
+int32_t flatten_host(rt_scene* s, HostFlat& HF) {
+    if (s->root < 0) return fail(RT_ERR_STATE, "no root set (rt_scene_set_root)");
+    int32_t next = s->n_prims;
+    number_leaves(s, s->root, next);
+    s->n_prims = next;
+    if (s->camera.set) { s->span0 = std::fmin(s->camera.cam.time1, s->camera.cam.time2); s->span1 = std::fmax(s->camera.cam.time1, s->camera.cam.time2); }
+    else { s->span0 = 0.0; s->span1 = 1.0; }
+
+    Flattener F;
+    F.s = s;
+    F.worlds.emplace_back();
+    {
+        std::vector<int32_t> key;
+        std::vector<XformOp> chain;
+        F.visit(s->root, 0, key, chain, false, 0);
+    }
+    if (F.status != RT_OK) return fail(F.status, F.error);
+
+    // domain radius: every coordinate the f32 slab test can see (boxes in instance space, camera origin)
+    double R = 1.0;
+    for (const WorldBuild& w : F.worlds)
+        for (const InstBuild& ib : w.inst)
+            for (const FlatPrim& p : ib.prims)
+                for (int a = 0; a < 3; ++a) { R = std::fmax(R, std::fabs(p.bmin[a])); R = std::fmax(R, std::fabs(p.bmax[a])); }
+    if (s->camera.set)
+        for (int a = 0; a < 3; ++a) R = std::fmax(R, 2.0 * std::fabs(s->camera.cam.origin[a]));
+    s->domain_radius = R;
+
+    std::vector<BvhNode32>& nodes = HF.nodes;
+    std::vector<DSphere>& spheres = HF.spheres; std::vector<DMoving>& movings = HF.movings; std::vector<DGravity>& gravities = HF.gravities;
+    std::vector<double>& gtable = HF.gtable;
+    std::vector<DRect>& rects = HF.rects; std::vector<DBox>& boxes = HF.boxes; std::vector<DTri>& tris = HF.tris;
+    std::vector<PrimMeta>* meta = HF.meta;
+    std::vector<Instance>& instances = HF.instances;
+    std::vector<XformOp>& ops = HF.ops;
+    std::vector<Medium>& media = HF.media;
+    uint32_t cursor[PRIM_TYPE_COUNT] = {0, 0, 0, 0, 0, 0};
+    int& max_depth = HF.max_depth;
+
+    BuildOptions bo;
+    bo.pad = R * (1.0 / 1048576.0); // 2^-20 * R, see DESIGN.md "f32 slab conservativeness"
+    HF.pad = bo.pad;
+    const char* env_leaf = std::getenv("RTB200_MAX_LEAF");
+    if (env_leaf) bo.max_leaf = std::max(1, std::atoi(env_leaf));
+
+    std::vector<std::pair<uint32_t, uint32_t>> world_range(F.worlds.size());
+    for (size_t wi = 0; wi < F.worlds.size(); ++wi) {
+        world_range[wi].first = (uint32_t)instances.size();
+        for (InstBuild& ib : F.worlds[wi].inst) {
+            if (ib.prims.empty()) continue;
+            std::vector<BuildPrim> bp(ib.prims.size());
+            for (size_t i = 0; i < ib.prims.size(); ++i) {
+                for (int a = 0; a < 3; ++a) { bp[i].bmin[a] = ib.prims[i].bmin[a]; bp[i].bmax[a] = ib.prims[i].bmax[a]; }
+                bp[i].type = ib.prims[i].type;
+                bp[i].src = (uint32_t)i;
+            }
+            BvhBuilder builder(nodes, bo);
+            BuildResult br = builder.build(bp, cursor);
+            max_depth = std::max(max_depth, br.max_depth);
+            for (uint32_t src : br.leaf_order) {
+                const FlatPrim& p = ib.prims[src];
+                const Node& n = s->nodes[(size_t)p.node];
+                PrimMeta pm; pm.mat_id = p.mat; pm.prim_id = p.prim_id;
+                meta[p.type].push_back(pm);
+                switch (p.type) {
+                case PRIM_SPHERE: { DSphere q; q.cx = n.d[0]; q.cy = n.d[1]; q.cz = n.d[2]; q.r = n.d[3]; spheres.push_back(q); } break;
+                case PRIM_MOVING: {
+                    DMoving q;
+                    for (int a = 0; a < 3; ++a) { q.c0[a] = n.d[a]; q.dc[a] = n.d[3 + a] - n.d[a]; }
+                    q.t0 = n.d[6]; q.dt = n.d[7] - n.d[6]; q.r = n.d[8]; q.pad_ = 0;
+                    movings.push_back(q);
+                } break;
+                case PRIM_GRAVITY: {
+                    DGravity q;
+                    int64_t i0, i1;
+                    F.gravity_window(*n.grav, i0, i1);
+                    q.x = n.d[0]; q.z = n.d[2]; q.r = n.d[4];
+                    q.table_off = (int32_t)gtable.size(); q.idx0 = (int32_t)i0; q.n = (int32_t)(i1 - i0 + 1); q.pad_ = 0;
+                    gtable.insert(gtable.end(), n.grav->begin() + i0, n.grav->begin() + i1 + 1);
+                    gravities.push_back(q);
+                } break;
+                case PRIM_RECT: { DRect q; q.a0 = n.d[0]; q.a1 = n.d[1]; q.b0 = n.d[2]; q.b1 = n.d[3]; q.k = n.d[4]; q.axis = n.axis; q.pad_ = 0; rects.push_back(q); } break;
+                case PRIM_BOX: { DBox q; for (int a = 0; a < 3; ++a) { q.p0[a] = n.d[a]; q.p1[a] = n.d[3 + a]; } boxes.push_back(q); } break;
+                default: {
+                    const double *v0, *v1, *v2;
+                    if (n.kind == N_MESH) {
+                        const MeshData& m = *n.mesh;
+                        v0 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub]];
+                        v1 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub + 1]];
+                        v2 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub + 2]];
+                    } else {
+                        v0 = &n.d[0]; v1 = &n.d[3]; v2 = &n.d[6];
+                    }
+                    // Triangle::new (hit.rs:96-107): unit normal of (v1-v0) x (v2-v0), computed in f64
+                    const double ax = v1[0] - v0[0], ay = v1[1] - v0[1], az = v1[2] - v0[2];
+                    const double bx = v2[0] - v0[0], by = v2[1] - v0[1], bz = v2[2] - v0[2];
+                    double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+                    const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+                    nx /= len; ny /= len; nz /= len;
+                    DTri q;
+                    for (int a = 0; a < 3; ++a) { q.v0[a] = (float)v0[a]; q.v1[a] = (float)v1[a]; q.v2[a] = (float)v2[a]; }
+                    q.n[0] = (float)nx; q.n[1] = (float)ny; q.n[2] = (float)nz;
+                    tris.push_back(q);
+                } break;
+                }
+            }
+            Instance in;
+            in.root = br.root;
+            in.chain_off = (uint32_t)ops.size();
+            in.chain_len = (uint32_t)ib.chain.size();
+            in.pad_ = 0;
+            for (int a = 0; a < 3; ++a) { in.bmin[a] = nodes[br.root].min[a]; in.bmax[a] = nodes[br.root].max[a]; }
+            ops.insert(ops.end(), ib.chain.begin(), ib.chain.end());
+            instances.push_back(in);
+        }
+        world_range[wi].second = (uint32_t)instances.size();
+    }
+    if (max_depth > RT_BVH_MAX_DEPTH) return fail(RT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+
+    // materials: user materials first (ids = builder order), the phase functions of media were
+    // appended to s->mats at rt_constant_medium time
+    for (const MediumBuild& mb : F.media) {
+        const Node& n = s->nodes[(size_t)mb.node];
+        Medium m;
+        m.inst_begin = world_range[mb.world].first;
+        m.inst_end = world_range[mb.world].second;
+        m.chain_off = (uint32_t)ops.size();
+        m.chain_len = (uint32_t)mb.chain.size();
+        ops.insert(ops.end(), mb.chain.begin(), mb.chain.end());
+        m.mat_id = (uint32_t)n.mat;
+        m.prim_id = (uint32_t)n.prim_base;
+        m.neg_inv_density = -1.0 / n.d[0]; // hit.rs:949
+        media.push_back(m);
+    }
+
+    std::vector<DMaterial>& dmats = HF.dmats;
+    dmats.resize(s->mats.size());
+    for (size_t i = 0; i < s->mats.size(); ++i) {
+        const MatDesc& m = s->mats[i];
+        DMaterial d;
+        std::memset(&d, 0, sizeof d);
+        d.type = m.type;
+        d.tex = (uint32_t)m.tex;
+        d.flags = 0;
+        if (m.type == MAT_LAMBERTIAN || m.type == MAT_LIGHT || m.type == MAT_ISOTROPIC) d.flags = tex_reads_uv(s, m.tex) ? 1u : 0u;
+        for (int a = 0; a < 3; ++a) d.albedo[a] = (float)m.albedo[a];
+        d.fuzz_or_ir = m.param;
+        dmats[i] = d;
+    }
+    std::vector<DTexture>& dtex = HF.dtex;
+    dtex.resize(s->tex.size());
+    std::vector<PerlinTable>& perlin = HF.perlin;
+    std::vector<float4>& texels = HF.texels;
+    for (size_t i = 0; i < s->tex.size(); ++i) {
+        const TexDesc& t = s->tex[i];
+        DTexture d;
+        std::memset(&d, 0, sizeof d);
+        d.type = t.type;
+        for (int a = 0; a < 3; ++a) d.rgb[a] = (float)t.rgb[a];
+        if (t.type == TEX_CHECKER) { d.a = (uint32_t)t.a; d.b = (uint32_t)t.b; }
+        else if (t.type == TEX_NOISE) { d.a = (uint32_t)perlin.size(); d.scale = t.scale; perlin.push_back(*t.perlin); }
+        else if (t.type == TEX_IMAGE) {
+            d.a = (uint32_t)texels.size(); d.w = (uint32_t)t.w; d.h = (uint32_t)t.h;
+            const std::vector<float>& px = *t.texels;
+            for (size_t k = 0; k + 3 < px.size() + 1; k += 4) texels.push_back(make_float4(px[k], px[k + 1], px[k + 2], px[k + 3]));
+        }
+        dtex[i] = d;
+    }
+
+    HF.n_main_instances = world_range[0].second - world_range[0].first;
+    return RT_OK;
+}
+
+int32_t do_commit(rt_scene* s) {
+    HostFlat HF;
+    const int32_t fr = flatten_host(s, HF);
+    if (fr != RT_OK) return fr;
+    int dev_count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&dev_count);
+    if (ce != cudaSuccess || dev_count == 0) return fail(RT_ERR_CUDA, "no CUDA device: librtb200 has no CPU fallback");
+    std::vector<BvhNode32>& nodes = HF.nodes;
+    std::vector<DSphere>& spheres = HF.spheres; std::vector<DMoving>& movings = HF.movings; std::vector<DGravity>& gravities = HF.gravities;
+    std::vector<double>& gtable = HF.gtable;
+    std::vector<DRect>& rects = HF.rects; std::vector<DBox>& boxes = HF.boxes; std::vector<DTri>& tris = HF.tris;
+    std::vector<PrimMeta>* meta = HF.meta;
+    std::vector<Instance>& instances = HF.instances;
+    std::vector<XformOp>& ops = HF.ops;
+    std::vector<Medium>& media = HF.media;
+    std::vector<DMaterial>& dmats = HF.dmats;
+    std::vector<DTexture>& dtex = HF.dtex;
+    std::vector<PerlinTable>& perlin = HF.perlin;
+    std::vector<float4>& texels = HF.texels;
+
+    s->dev.release();
+    DeviceScene& D = s->dev.scene;
+    std::memset(&D, 0, sizeof D);
+#define UP(vec, field)                                              \
+    if ((ce = upload(s->dev, vec, D.field)) != cudaSuccess) {       \
+        s->dev.release();                                           \
+        return fail_cuda(ce, "scene upload");                       \
+    }
+    UP(nodes, nodes) UP(spheres, spheres) UP(movings, movings) UP(gravities, gravities) UP(gtable, gravity_table)
+    UP(rects, rects) UP(boxes, boxes) UP(tris, tris)
+    for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) { UP(meta[t], meta[t]) }
+    UP(instances, instances) UP(ops, ops) UP(media, media) UP(dmats, materials) UP(dtex, textures) UP(perlin, perlin) UP(texels, texels)
+#undef UP
+    D.n_main_instances = HF.n_main_instances;
+    D.n_media = (uint32_t)media.size();
+    D.n_prims = (uint32_t)s->n_prims;
+    if (s->camera.set) D.cam = s->camera.cam;
+    for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
+    s->dev.valid = true;
+    s->committed = true;
+    return RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+rt_scene* rt_scene_create(void) {
+    rt_scene* s = new rt_scene();
+    const char* e = std::getenv("RTB200_WAVE_SLOTS");
+    if (e) s->tuning.wave_slots = (uint32_t)std::max(128L, std::atol(e));
+    return s;
+}
+void rt_scene_destroy(rt_scene* s) { delete s; }
+const char* rt_last_error(void) { return g_err.c_str(); }
+const char* rt_version(void) { return "rtb200 0.1 sm_100a (f64 rays / f32 slabs, wavefront)"; }
+
+// ---------------------------------------------------------------- textures
+int32_t rt_tex_solid(rt_scene* s, const double rgb[3]) {
+    CHECK_SCENE(s);
+    if (!rgb) return fail(RT_ERR_INVALID, "null colour");
+    TexDesc t; t.type = TEX_SOLID;
+    for (int a = 0; a < 3; ++a) t.rgb[a] = rgb[a];
+    s->tex.push_back(t);
+    return (int32_t)s->tex.size() - 1;
+}
+int32_t rt_tex_checker(rt_scene* s, int32_t even, int32_t odd) {
+    CHECK_SCENE(s); CHECK_TEX(s, even); CHECK_TEX(s, odd);
+    TexDesc t; t.type = TEX_CHECKER; t.a = even; t.b = odd;
+    s->tex.push_back(t);
+    return (int32_t)s->tex.size() - 1;
+}
+int32_t rt_tex_noise(rt_scene* s, double scale, const double* ranvec, const int32_t* px, const int32_t* py, const int32_t* pz, uint64_t seed) {
+    CHECK_SCENE(s);
+    PerlinTables gen;
+    if (!ranvec || !px || !py || !pz) {
+        perlin_generate(seed, gen);
+        ranvec = gen.ranvec; px = gen.perm_x; py = gen.perm_y; pz = gen.perm_z;
+    }
+    auto pt = std::make_shared<PerlinTable>();
+    for (int i = 0; i < 256; ++i) {
+        for (int a = 0; a < 3; ++a) pt->ranvec[i][a] = ranvec[3 * i + a];
+        if ((px[i] | py[i] | pz[i]) & ~255) return fail(RT_ERR_INVALID, "perm entry outside 0..255");
+        pt->perm_x[i] = (uint8_t)px[i]; pt->perm_y[i] = (uint8_t)py[i]; pt->perm_z[i] = (uint8_t)pz[i];
+    }
+    TexDesc t; t.type = TEX_NOISE; t.scale = scale; t.perlin = pt;
+    s->tex.push_back(t);
+    return (int32_t)s->tex.size() - 1;
+}
+int32_t rt_tex_image(rt_scene* s, int32_t w, int32_t h, const double* rgb) {
+    CHECK_SCENE(s);
+    if (w <= 0 || h <= 0 || !rgb) return fail(RT_ERR_INVALID, "bad image");
+    auto px = std::make_shared<std::vector<float>>((size_t)w * h * 4);
+    for (size_t i = 0; i < (size_t)w * h; ++i) {
+        (*px)[4 * i] = (float)rgb[3 * i]; (*px)[4 * i + 1] = (float)rgb[3 * i + 1]; (*px)[4 * i + 2] = (float)rgb[3 * i + 2]; (*px)[4 * i + 3] = 0.f;
+    }
+    TexDesc t; t.type = TEX_IMAGE; t.w = w; t.h = h; t.texels = px;
+    s->tex.push_back(t);
+    return (int32_t)s->tex.size() - 1;
+}
+int32_t rt_tex_image_ppm(rt_scene* s, const char* path) {
+    CHECK_SCENE(s);
+    if (!path) return fail(RT_ERR_INVALID, "null path");
+    int32_t w, h;
+    std::vector<double> rgb;
+    std::string err;
+    if (!read_ppm_p3(path, w, h, rgb, err)) return fail(RT_ERR_IO, err);
+    return rt_tex_image(s, w, h, rgb.data());
+}
+
+// ---------------------------------------------------------------- materials
+static int32_t add_mat(rt_scene* s, const MatDesc& m) {
+    s->mats.push_back(m);
+    return (int32_t)s->mats.size() - 1;
+}
+int32_t rt_mat_lambertian(rt_scene* s, int32_t tex) { CHECK_SCENE(s); CHECK_TEX(s, tex); MatDesc m; m.type = MAT_LAMBERTIAN; m.tex = tex; return add_mat(s, m); }
+int32_t rt_mat_metal(rt_scene* s, const double a[3], double fuzz) {
+    CHECK_SCENE(s);
+    if (!a) return fail(RT_ERR_INVALID, "null colour");
+    MatDesc m; m.type = MAT_METAL;
+    for (int i = 0; i < 3; ++i) m.albedo[i] = a[i];
+    m.param = fuzz < 1.0 ? fuzz : 1.0; // hit.rs:1063
+    return add_mat(s, m);
+}
+int32_t rt_mat_dielectric(rt_scene* s, double ir) { CHECK_SCENE(s); MatDesc m; m.type = MAT_DIELECTRIC; m.param = ir; return add_mat(s, m); }
+int32_t rt_mat_diffuse_light(rt_scene* s, int32_t tex) { CHECK_SCENE(s); CHECK_TEX(s, tex); MatDesc m; m.type = MAT_LIGHT; m.tex = tex; return add_mat(s, m); }
+int32_t rt_mat_isotropic(rt_scene* s, int32_t tex) { CHECK_SCENE(s); CHECK_TEX(s, tex); MatDesc m; m.type = MAT_ISOTROPIC; m.tex = tex; return add_mat(s, m); }
+
+// ---------------------------------------------------------------- hittables
+int32_t rt_sphere(rt_scene* s, const double c[3], double r, int32_t mat) {
+    CHECK_SCENE(s); CHECK_MAT(s, mat);
+    Node n; n.kind = N_SPHERE; n.mat = mat;
+    n.d[0] = c[0]; n.d[1] = c[1]; n.d[2] = c[2]; n.d[3] = r;
+    return add_node(s, std::move(n));
+}
+int32_t rt_moving_sphere(rt_scene* s, const double c0[3], const double c1[3], double t0, double t1, double r, int32_t mat) {
+    CHECK_SCENE(s); CHECK_MAT(s, mat);
+    Node n; n.kind = N_MOVING; n.mat = mat;
+    for (int a = 0; a < 3; ++a) { n.d[a] = c0[a]; n.d[3 + a] = c1[a]; }
+    n.d[6] = t0; n.d[7] = t1; n.d[8] = r;
+    return add_node(s, std::move(n));
+}
+int32_t rt_gravity_sphere(rt_scene* s, const double st[3], double time0, double r, int32_t mat) {
+    CHECK_SCENE(s); CHECK_MAT(s, mat);
+    Node n; n.kind = N_GRAVITY; n.mat = mat;
+    n.d[0] = st[0]; n.d[1] = st[1]; n.d[2] = st[2]; n.d[3] = time0; n.d[4] = r;
+    // GravitySphere::new (hit.rs:346-359): explicit Euler bounce table, one entry per 0.001 of time up to 100
+    auto tab = std::make_shared<std::vector<double>>();
+    tab->reserve(100002);
+    tab->push_back(st[1]);
+    const double incr = 0.001;
+    double t = time0, y = st[1], vel = 0.0;
+    while (t < 100.0) {
+        t += incr;
+        vel -= 0.000001;
+        if (y - 1.0 * r <= 0.0) vel *= -0.92;
+        y = std::fmax(1.0 * r, y + vel);
+        tab->push_back(y);
+    }
+    n.grav = tab;
+    return add_node(s, std::move(n));
+}
+static int32_t add_rect(rt_scene* s, int axis, double a0, double a1, double b0, double b1, double k, int32_t mat) {
+    Node n; n.kind = N_RECT; n.mat = mat; n.axis = axis;
+    n.d[0] = a0; n.d[1] = a1; n.d[2] = b0; n.d[3] = b1; n.d[4] = k;
+    return add_node(s, std::move(n));
+}
+int32_t rt_xy_rect(rt_scene* s, double x0, double x1, double y0, double y1, double k, int32_t mat) { CHECK_SCENE(s); CHECK_MAT(s, mat); return add_rect(s, 2, x0, x1, y0, y1, k, mat); }
+int32_t rt_xz_rect(rt_scene* s, double x0, double x1, double z0, double z1, double k, int32_t mat) { CHECK_SCENE(s); CHECK_MAT(s, mat); return add_rect(s, 1, x0, x1, z0, z1, k, mat); }
+int32_t rt_yz_rect(rt_scene* s, double y0, double y1, double z0, double z1, double k, int32_t mat) { CHECK_SCENE(s); CHECK_MAT(s, mat); return add_rect(s, 0, y0, y1, z0, z1, k, mat); }
+int32_t rt_box(rt_scene* s, const double p0[3], const double p1[3], int32_t mat) {
+    CHECK_SCENE(s); CHECK_MAT(s, mat);
+    Node n; n.kind = N_BOX; n.mat = mat;
+    for (int a = 0; a < 3; ++a) { n.d[a] = p0[a]; n.d[3 + a] = p1[a]; }
+    return add_node(s, std::move(n));
+}
+int32_t rt_triangle(rt_scene* s, const double v0[3], const double v1[3], const double v2[3], int32_t mat) {
+    CHECK_SCENE(s); CHECK_MAT(s, mat);
+    Node n; n.kind = N_TRI; n.mat = mat;
+    for (int a = 0; a < 3; ++a) { n.d[a] = v0[a]; n.d[3 + a] = v1[a]; n.d[6 + a] = v2[a]; }
+    return add_node(s, std::move(n));
+}
+int32_t rt_triangle_mesh(rt_scene* s, const double* verts, int64_t nv, const uint32_t* idx, int64_t nt, int32_t mat) {
+    CHECK_SCENE(s); CHECK_MAT(s, mat);
+    if (!verts || !idx || nv <= 0 || nt < 0) return fail(RT_ERR_INVALID, "bad mesh");
+    for (int64_t i = 0; i < 3 * nt; ++i)
+        if (idx[i] >= (uint64_t)nv) return fail(RT_ERR_INVALID, "mesh index out of range");
+    Node n; n.kind = N_MESH; n.mat = mat;
+    n.mesh = std::make_shared<MeshData>();
+    n.mesh->verts.assign(verts, verts + 3 * nv);
+    n.mesh->faces.assign(idx, idx + 3 * nt);
+    return add_node(s, std::move(n));
+}
+int32_t rt_ply_load(rt_scene* s, const char* path, double scale, int32_t mat) {
+    CHECK_SCENE(s); CHECK_MAT(s, mat);
+    if (!path) return fail(RT_ERR_INVALID, "null path");
+    Node n; n.kind = N_MESH; n.mat = mat;
+    n.mesh = std::make_shared<MeshData>();
+    std::string err;
+    if (!read_ply_ascii(path, scale, n.mesh->verts, n.mesh->faces, err)) return fail(RT_ERR_IO, err);
+    return add_node(s, std::move(n));
+}
+int32_t rt_list(rt_scene* s, const int32_t* ids, int32_t cnt) {
+    CHECK_SCENE(s);
+    if (cnt < 0 || (cnt > 0 && !ids)) return fail(RT_ERR_INVALID, "bad list");
+    Node n; n.kind = N_LIST;
+    for (int32_t i = 0; i < cnt; ++i) { CHECK_OBJ(s, ids[i]); n.children.push_back(ids[i]); }
+    return add_node(s, std::move(n));
+}
+int32_t rt_bvh(rt_scene* s, const int32_t* ids, int32_t cnt, double t0, double t1) {
+    CHECK_SCENE(s);
+    if (cnt < 0 || (cnt > 0 && !ids)) return fail(RT_ERR_INVALID, "bad list");
+    Node n; n.kind = N_BVH; n.d[0] = t0; n.d[1] = t1;
+    for (int32_t i = 0; i < cnt; ++i) { CHECK_OBJ(s, ids[i]); n.children.push_back(ids[i]); }
+    // BvhNode::new unwraps bounding boxes (bvh.rs:27-28): an empty group panics in the reference
+    bool empty = n.children.empty();
+    if (cnt == 1) {
+        const Node& c = s->nodes[(size_t)ids[0]];
+        if ((c.kind == N_LIST && c.children.empty()) || (c.kind == N_MESH && c.mesh->faces.empty())) empty = true;
+    }
+    if (empty) return fail(RT_ERR_EMPTY, "BvhNode over an empty list (the reference panics, bvh.rs:27-28)");
+    return add_node(s, std::move(n));
+}
+int32_t rt_translate(rt_scene* s, const double off[3], int32_t child) {
+    CHECK_SCENE(s); CHECK_OBJ(s, child);
+    Node n; n.kind = N_TRANSLATE; n.d[0] = off[0]; n.d[1] = off[1]; n.d[2] = off[2];
+    n.children.push_back(child);
+    return add_node(s, std::move(n));
+}
+int32_t rt_rotate_y(rt_scene* s, double angle_deg, int32_t child) {
+    CHECK_SCENE(s); CHECK_OBJ(s, child);
+    Node n; n.kind = N_ROTY;
+    const double angle = angle_deg * (3.14159265358979323846264338327950288 / 180.0); // f64::to_radians (hit.rs:844)
+    n.d[0] = std::sin(angle); n.d[1] = std::cos(angle);
+    n.children.push_back(child);
+    return add_node(s, std::move(n));
+}
+int32_t rt_constant_medium(rt_scene* s, const double rgb[3], double density, int32_t boundary) {
+    CHECK_SCENE(s); CHECK_OBJ(s, boundary);
+    // ConstantMedium::from_color builds its own Isotropic(SolidColor(c)) (hit.rs:945-951): it takes
+    // the next texture and material ids
+    const int32_t tex = rt_tex_solid(s, rgb);
+    if (tex < 0) return tex;
+    const int32_t mat = rt_mat_isotropic(s, tex);
+    Node n; n.kind = N_MEDIUM; n.mat = mat; n.d[0] = density;
+    n.children.push_back(boundary);
+    return add_node(s, std::move(n));
+}
+
+// ---------------------------------------------------------------- scene
+int32_t rt_scene_set_root(rt_scene* s, int32_t id) {
+    CHECK_SCENE(s); CHECK_OBJ(s, id);
+    s->root = id;
+    s->committed = false;
+    return RT_OK;
+}
+int32_t rt_scene_set_camera(rt_scene* s, const double lf[3], const double la[3], const double vup[3], double vfov, double aspect, double aperture,
+                            double focus_dist, double t1, double t2) {
+    CHECK_SCENE(s);
+    if (!lf || !la || !vup) return fail(RT_ERR_INVALID, "null camera vector");
+    // Camera::new (camera.rs:20-57)
+    const double theta = vfov * (3.14159265358979323846264338327950288 / 180.0);
+    const double h = std::tan(theta / 2.0);
+    const double viewport_height = 2.0 * h;
+    const double viewport_width = aspect * viewport_height;
+    double w[3] = {lf[0] - la[0], lf[1] - la[1], lf[2] - la[2]};
+    const double wl = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    for (int a = 0; a < 3; ++a) w[a] /= wl;
+    double u[3] = {vup[1] * w[2] - vup[2] * w[1], vup[2] * w[0] - vup[0] * w[2], vup[0] * w[1] - vup[1] * w[0]};
+    const double ul = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    for (int a = 0; a < 3; ++a) u[a] /= ul;
+    const double v[3] = {w[1] * u[2] - w[2] * u[1], w[2] * u[0] - w[0] * u[2], w[0] * u[1] - w[1] * u[0]};
+    DCamera& c = s->camera.cam;
+    for (int a = 0; a < 3; ++a) {
+        c.origin[a] = lf[a];
+        c.u[a] = u[a]; c.v[a] = v[a]; c.w[a] = w[a];
+        c.horizontal[a] = focus_dist * viewport_width * u[a];
+        c.vertical[a] = focus_dist * viewport_height * v[a];
+    }
+    for (int a = 0; a < 3; ++a) c.lower_left_corner[a] = c.origin[a] - c.horizontal[a] / 2.0 - c.vertical[a] / 2.0 - focus_dist * w[a];
+    c.lens_radius = aperture / 2.0;
+    c.time1 = t1; c.time2 = t2;
+    s->camera.set = true;
+    s->committed = false; // moving-primitive bounds depend on the shutter
+    return RT_OK;
+}
+int32_t rt_scene_set_background(rt_scene* s, const double rgb[3]) {
+    CHECK_SCENE(s);
+    if (!rgb) return fail(RT_ERR_INVALID, "null colour");
+    for (int a = 0; a < 3; ++a) s->background[a] = rgb[a];
+    if (s->dev.valid)
+        for (int a = 0; a < 3; ++a) s->dev.scene.background[a] = (float)rgb[a];
+    return RT_OK;
+}
+int32_t rt_scene_commit(rt_scene* s) {
+    CHECK_SCENE(s);
+    return do_commit(s);
+}
+int32_t rt_world_build(rt_scene* s, int32_t scene_id, uint64_t seed, int32_t param) {
+    CHECK_SCENE(s);
+    return build_world(s, scene_id, seed, param);
+}
+int32_t rt_scene_num_prims(rt_scene* s) {
+    CHECK_SCENE(s);
+    return s->n_prims;
+}
+
+// ---------------------------------------------------------------- render
+int32_t rt_image_height(const rt_render_config* cfg) {
+    if (!cfg || cfg->image_width <= 0 || !(cfg->aspect_ratio > 0)) return RT_ERR_INVALID;
+    const double h = (double)cfg->image_width / cfg->aspect_ratio; // world.rs:1192, `as i32` saturates
+    if (h != h) return 0;
+    if (h >= 2147483647.0) return 2147483647;
+    return (int32_t)h;
+}
+
+static int32_t make_job(rt_scene* s, const rt_render_config* cfg, RenderJob& job) {
+    if (!cfg) return fail(RT_ERR_INVALID, "null config");
+    if (!s->committed || !s->dev.valid) return fail(RT_ERR_STATE, "scene not committed");
+    if (!s->camera.set) return fail(RT_ERR_STATE, "no camera");
+    if (cfg->image_width <= 0 || cfg->samples_per_pixel <= 0 || cfg->max_depth <= 0) return fail(RT_ERR_INVALID, "Config::new assert (world.rs:36-40)");
+    const int32_t H = rt_image_height(cfg);
+    if (H <= 0) return fail(RT_ERR_INVALID, "image height <= 0 (Screen::new assert, screen.rs:14)");
+    if ((int64_t)cfg->image_width * H > (int64_t)1 << 30) return fail(RT_ERR_INVALID, "image too large");
+    job.width = cfg->image_width;
+    job.height = H;
+    job.rows = cfg->compat_threads > 0 ? (H / cfg->compat_threads) * cfg->compat_threads : H; // world.rs:1198-1202
+    job.spp_total = cfg->samples_per_pixel;
+    job.sample_begin = cfg->sample_begin;
+    job.sample_end = cfg->sample_end == 0 ? cfg->samples_per_pixel : cfg->sample_end;
+    if (job.sample_begin < 0 || job.sample_end > job.spp_total || job.sample_begin > job.sample_end) return fail(RT_ERR_INVALID, "bad sample range");
+    job.max_depth = cfg->max_depth;
+    job.seed = cfg->seed;
+    return RT_OK;
+}
+
+int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg, int64_t* d_accum, void* cuda_stream, rt_stats* stats) {
+    CHECK_SCENE(s);
+    if (!d_accum) return fail(RT_ERR_INVALID, "null accumulator");
+    RenderJob job;
+    const int32_t r = make_job(s, cfg, job);
+    if (r != RT_OK) return r;
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    const auto t0 = std::chrono::steady_clock::now();
+    RenderTuning tune = s->tuning;
+    tune.timed_extend = (cfg->flags & 1) ? 1 : 0;
+    tune.count_events = (cfg->flags & 2) ? 1 : 0;
+    const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats);
+    if (e != cudaSuccess) return fail_cuda(e, "render");
+    if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RT_OK;
+}
+
+int32_t rt_resolve_device(const int64_t* d_accum, double* d_screen, int32_t width, int32_t height, int32_t spp, int32_t rendered_rows, void* cuda_stream) {
+    if (!d_accum || !d_screen || width <= 0 || height <= 0 || spp <= 0) return fail(RT_ERR_INVALID, "bad resolve arguments");
+    const cudaError_t e = launch_resolve(d_accum, d_screen, width, height, spp, rendered_rows, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return fail_cuda(e, "resolve");
+    return RT_OK;
+}
+
+int32_t rt_render(rt_scene* s, const rt_render_config* cfg, double* out_screen, int64_t* out_accum, rt_stats* stats) {
+    CHECK_SCENE(s);
+    RenderJob job;
+    const int32_t r = make_job(s, cfg, job);
+    if (r != RT_OK) return r;
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t n = (size_t)job.width * job.height * 3;
+    int64_t* d_accum = nullptr;
+    double* d_screen = nullptr;
+    cudaError_t e = cudaMalloc(&d_accum, n * sizeof(int64_t));
+    if (e != cudaSuccess) return fail_cuda(e, "accumulator allocation");
+    int32_t rc = RT_OK;
+    do {
+        if ((e = cudaMemset(d_accum, 0, n * sizeof(int64_t))) != cudaSuccess) { rc = fail_cuda(e, "memset"); break; }
+        rc = rt_render_device(s, cfg, d_accum, nullptr, stats);
+        if (rc != RT_OK) break;
+        if (out_screen) {
+            if ((e = cudaMalloc(&d_screen, n * sizeof(double))) != cudaSuccess) { rc = fail_cuda(e, "screen allocation"); break; }
+            rc = rt_resolve_device(d_accum, d_screen, job.width, job.height, job.spp_total, job.rows, nullptr);
+            if (rc != RT_OK) break;
+            if ((e = cudaMemcpy(out_screen, d_screen, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = fail_cuda(e, "screen copy"); break; }
+        }
+        if (out_accum) {
+            if ((e = cudaMemcpy(out_accum, d_accum, n * sizeof(int64_t), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = fail_cuda(e, "accum copy"); break; }
+        }
+    } while (0);
+    cudaFree(d_accum);
+    if (d_screen) cudaFree(d_screen);
+    if (rc == RT_OK && stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+int32_t rt_write_ppm(const char* path, const double* screen, int32_t width, int32_t height) {
+    if (!screen || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad screen");
+    std::string err;
+    if (!write_ppm_p3(path, screen, width, height, err)) return fail(RT_ERR_IO, err);
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------- parity hook
+int32_t rt_trace_batch(rt_scene* s, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t flags, uint64_t seed, rt_hit* out) {
+    CHECK_SCENE(s);
+    if (!s->committed || !s->dev.valid) return fail(RT_ERR_STATE, "scene not committed");
+    if (n < 0 || (n > 0 && (!rays || !out))) return fail(RT_ERR_INVALID, "bad batch");
+    if (n == 0) return RT_OK;
+    // the f32 slab test is conservative for origins inside the committed domain and for times inside
+    // the span the moving bounds were built for
+    const double lim = 4.0 * s->domain_radius;
+    bool has_moving = false;
+    for (const Node& nd : s->nodes) has_moving = has_moving || nd.kind == N_MOVING || nd.kind == N_GRAVITY;
+    for (int64_t i = 0; i < n; ++i) {
+        for (int a = 0; a < 3; ++a)
+            if (!(std::fabs(rays[i].o[a]) <= lim)) return fail(RT_ERR_INVALID, "ray origin outside the committed scene domain (4x the scene radius)");
+        if (has_moving && !(rays[i].time >= s->span0 - 1e-12 && rays[i].time <= s->span1 + 1e-12))
+            return fail(RT_ERR_INVALID, "ray time outside the camera shutter the moving-primitive bounds were built for");
+    }
+    rt_ray* d_rays = nullptr;
+    rt_hit* d_out = nullptr;
+    cudaError_t e;
+    int32_t rc = RT_OK;
+    do {
+        if ((e = cudaMalloc(&d_rays, (size_t)n * sizeof(rt_ray))) != cudaSuccess) { rc = fail_cuda(e, "ray allocation"); break; }
+        if ((e = cudaMalloc(&d_out, (size_t)n * sizeof(rt_hit))) != cudaSuccess) { rc = fail_cuda(e, "hit allocation"); break; }
+        if ((e = cudaMemcpy(d_rays, rays, (size_t)n * sizeof(rt_ray), cudaMemcpyHostToDevice)) != cudaSuccess) { rc = fail_cuda(e, "ray upload"); break; }
+        if ((e = launch_trace_batch(s->dev.scene, d_rays, n, t_min, t_max, flags, seed, d_out, nullptr)) != cudaSuccess) { rc = fail_cuda(e, "trace launch"); break; }
+        if ((e = cudaMemcpy(out, d_out, (size_t)n * sizeof(rt_hit), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = fail_cuda(e, "hit download"); break; }
+    } while (0);
+    if (d_rays) cudaFree(d_rays);
+    if (d_out) cudaFree(d_out);
+    return rc;
+}
+
+// unit-level device checks (tests only; see kernels.h launch_unit_op)
+RTB_EXPORT int32_t rt_unit_op(rt_scene* s, int32_t op, uint32_t ia, uint32_t ib, uint32_t ic, uint32_t id, const double* in8, double* out8) {
+    CHECK_SCENE(s);
+    if (!s->committed || !s->dev.valid) return fail(RT_ERR_STATE, "scene not committed");
+    const cudaError_t e = launch_unit_op(s->dev.scene, op, ia, ib, ic, id, in8, out8);
+    if (e != cudaSuccess) return fail_cuda(e, "unit op");
+    return RT_OK;
+}
+
+// Host-only validation of the flattener + BVH builder (no CUDA): checks that every leaf primitive's
+// bounds lie inside its leaf box and every node inside its parent, that each typed slot is referenced
+// by exactly one leaf, and returns out[0] nodes, [1] max depth, [2] main instances, [3] all instances,
+// [4] media, [5..10] primitives per type, [11] leaves, [12] violations (0 = valid), [13] prims numbered.
+RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]) {
+    CHECK_SCENE(s);
+    if (!out) return fail(RT_ERR_INVALID, "null out");
+    HostFlat HF;
+    const int32_t fr = flatten_host(s, HF);
+    if (fr != RT_OK) return fr;
+    for (int i = 0; i < 16; ++i) out[i] = 0;
+    out[0] = (int64_t)HF.nodes.size(); out[1] = HF.max_depth; out[2] = HF.n_main_instances; out[3] = (int64_t)HF.instances.size();
+    out[4] = (int64_t)HF.media.size();
+    const size_t counts[PRIM_TYPE_COUNT] = {HF.spheres.size(), HF.movings.size(), HF.gravities.size(), HF.rects.size(), HF.boxes.size(), HF.tris.size()};
+    for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) out[5 + t] = (int64_t)counts[t];
+    std::vector<std::vector<uint8_t>> seen(PRIM_TYPE_COUNT);
+    for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) seen[(size_t)t].assign(counts[t], 0);
+    int64_t violations = 0, leaves = 0;
+    for (const Instance& in : HF.instances) {
+        struct Item { uint32_t node; float mn[3], mx[3]; };
+        std::vector<Item> st;
+        Item r; r.node = in.root;
+        for (int a = 0; a < 3; ++a) { r.mn[a] = -INFINITY; r.mx[a] = INFINITY; }
+        st.push_back(r);
+        while (!st.empty()) {
+            const Item it = st.back();
+            st.pop_back();
+            const BvhNode32& nd = HF.nodes[it.node];
+            for (int a = 0; a < 3; ++a)
+                if (nd.min[a] < it.mn[a] || nd.max[a] > it.mx[a] || !(nd.min[a] <= nd.max[a])) ++violations;
+            if (nd.count) {
+                ++leaves;
+                const uint32_t type = nd.count >> 24, n = nd.count & 0xffffffu;
+                for (uint32_t i = nd.first; i < nd.first + n; ++i) {
+                    if (type >= PRIM_TYPE_COUNT || i >= counts[type]) { ++violations; continue; }
+                    if (seen[type][i]++) ++violations;
+                    double mn[3], mx[3];
+                    bool have = true;
+                    switch (type) {
+                    case PRIM_SPHERE: { const DSphere& q = HF.spheres[i]; const double c[3] = {q.cx, q.cy, q.cz}; for (int a = 0; a < 3; ++a) { mn[a] = c[a] - std::fabs(q.r); mx[a] = c[a] + std::fabs(q.r); } } break;
+                    case PRIM_RECT: { const DRect& q = HF.rects[i]; const int ax = q.axis, ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2; mn[ax] = mx[ax] = q.k; mn[ia] = q.a0; mx[ia] = q.a1; mn[ib] = q.b0; mx[ib] = q.b1; } break;
+                    case PRIM_BOX: { const DBox& q = HF.boxes[i]; for (int a = 0; a < 3; ++a) { mn[a] = std::fmin(q.p0[a], q.p1[a]); mx[a] = std::fmax(q.p0[a], q.p1[a]); } } break;
+                    case PRIM_TRI: { const DTri& q = HF.tris[i]; for (int a = 0; a < 3; ++a) { mn[a] = std::fmin(q.v0[a], std::fmin(q.v1[a], q.v2[a])); mx[a] = std::fmax(q.v0[a], std::fmax(q.v1[a], q.v2[a])); } } break;
+                    default: have = false; break;
+                    }
+                    if (have)
+                        for (int a = 0; a < 3; ++a)
+                            if (mn[a] < (double)nd.min[a] || mx[a] > (double)nd.max[a]) ++violations;
+                }
+            } else {
+                for (uint32_t c = 0; c < 2; ++c) {
+                    Item ch; ch.node = nd.first + c;
+                    if (ch.node >= HF.nodes.size() || (nd.first & 1u)) { ++violations; continue; }
+                    for (int a = 0; a < 3; ++a) { ch.mn[a] = nd.min[a]; ch.mx[a] = nd.max[a]; }
+                    st.push_back(ch);
+                }
+            }
+        }
+    }
+    for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t)
+        for (uint8_t v : seen[(size_t)t])
+            if (v != 1) ++violations;
+    out[11] = leaves; out[12] = violations; out[13] = s->n_prims;
+    return RT_OK;
+}
+
+// wavefront tuning knobs (bench / profiling): wave_slots = resident path slots
+RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots) {
+    CHECK_SCENE(s);
+    if (wave_slots) s->tuning.wave_slots = wave_slots < 128 ? 128 : wave_slots;
+    return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,129 @@
+// rt_types.h — flattened scene layout shared by the host flattener and the device kernels.
+//
+// The reference's scene is a pointer graph of Arc<Box<dyn Hittable>> (src/hit.rs:82-85) walked by
+// virtual calls.  Here it is flattened at rt_scene_commit into:
+//   * typed primitive buffers in BVH-leaf order (SoA by type, "type tag" = which buffer),
+//   * one array of 32-byte BVH nodes (sibling pairs adjacent => one 64 B fetch tests both children),
+//   * a short list of instances = (transform chain, BVH root): every leaf is reached through
+//     exactly one chain of Translate / RotateY wrappers (hit.rs:787-936); leaves that share a chain
+//     share an instance, lists and BvhNodes merge into the enclosing instance (closest-hit is
+//     topology independent, bvh.rs:97-112 vs hit.rs:660-690),
+//   * media (ConstantMedium, hit.rs:938-990), each with its boundary as its own instance range,
+//   * material / texture tables, Perlin tables, image texels, the camera block.
+//
+// Precision: rays, hit points, normals and primitive tests are f64 (B200's FP64 pipe runs at half
+// the FP32 rate, so exactness against the f64 reference is affordable); BVH slab tests are f32 on
+// outward-padded boxes (conservative); colours / throughput are f32; mesh triangles are stored f32.
+#pragma once
+#include <stdint.h>
+#include <vector_types.h> // float4
+
+namespace rtb {
+
+#define RT_BVH_MAX_DEPTH 60 // traversal stack is 64 entries (rt_device.cuh RT_STACK)
+
+enum PrimType : uint32_t {
+    PRIM_SPHERE = 0, PRIM_MOVING = 1, PRIM_GRAVITY = 2, PRIM_RECT = 3, PRIM_BOX = 4, PRIM_TRI = 5,
+    PRIM_TYPE_COUNT = 6, PRIM_MEDIUM = 6
+};
+enum MatType : uint32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_LIGHT = 3, MAT_ISOTROPIC = 4, MAT_TYPE_COUNT = 5 };
+enum TexType : uint32_t { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3 };
+enum XformType : uint32_t { XF_TRANSLATE = 0, XF_ROTATE_Y = 1 };
+
+// 32-byte BVH node.  Interior: count == 0, first = index of the left child (right = first + 1).
+// Leaf: count > 0 primitives of one type, `first` = index into that type's buffer,
+// type stored in the top byte of count.
+struct alignas(32) BvhNode32 {
+    float min[3];
+    uint32_t first;
+    float max[3];
+    uint32_t count; // (type << 24) | n
+};
+
+struct alignas(16) DSphere { double cx, cy, cz, r; };                                  // hit.rs:180-184
+struct alignas(16) DMoving { double c0[3]; double dc[3]; double t0, dt, r, pad_; };   // hit.rs:247-254 (dc = center1 - center0, dt = time1 - time0)
+struct alignas(8) DGravity { double x, z, r; int32_t table_off; int32_t idx0; int32_t n; int32_t pad_; }; // hit.rs:330-336, window of `stored`
+struct alignas(16) DRect { double a0, a1, b0, b1, k; int32_t axis; int32_t pad_; };    // hit.rs:446-453 (axis 2 = Xy, 1 = Xz, 0 = Yz)
+struct alignas(16) DBox { double p0[3]; double p1[3]; };                              // hit.rs:713-717
+struct alignas(16) DTri { float v0[3], v1[3], v2[3], n[3]; };                          // hit.rs:87-93 (unit normal precomputed, hit.rs:96-107)
+
+struct PrimMeta { uint32_t mat_id; uint32_t prim_id; }; // per primitive, same order as its typed buffer
+
+struct XformOp { // one wrapper of the chain, outermost first
+    uint32_t type;
+    uint32_t pad_;
+    double a, b, c; // translate: offset xyz; rotate-y: sin_theta, cos_theta, unused
+};
+
+struct Instance {
+    uint32_t root;      // node index of this instance's BVH root
+    uint32_t chain_off; // into ops[]
+    uint32_t chain_len;
+    uint32_t pad_;
+    float bmin[3], bmax[3]; // padded bounds in the instance's own (innermost) space
+};
+
+struct Medium { // hit.rs:938-951
+    uint32_t inst_begin, inst_end; // the boundary's instances
+    uint32_t chain_off, chain_len; // wrappers around the ConstantMedium itself (usually 0)
+    uint32_t mat_id, prim_id;
+    double neg_inv_density;
+};
+
+struct DMaterial {
+    uint32_t type;
+    uint32_t tex;     // albedo / emit texture id (lambertian, light, isotropic)
+    uint32_t flags;   // bit 0: texture chain reads (u, v) -> the hit must carry sphere uv
+    uint32_t pad_;
+    float albedo[3];  // metal
+    float pad2_;
+    double fuzz_or_ir; // metal fuzz (clamped <= 1) / dielectric ir
+};
+
+struct DTexture {
+    uint32_t type;
+    uint32_t a, b;    // checker: even, odd texture ids; noise: perlin table index; image: texel offset
+    uint32_t w, h;    // image size
+    uint32_t pad_;
+    float rgb[3];     // solid
+    float pad2_;
+    double scale;     // noise
+};
+
+struct PerlinTable { // perlin.rs:8-13 (gradients f64 as given; perms as bytes)
+    double ranvec[256][3];
+    uint8_t perm_x[256], perm_y[256], perm_z[256];
+};
+
+struct DCamera { // camera.rs:6-17
+    double origin[3], lower_left_corner[3], horizontal[3], vertical[3], u[3], v[3], w[3];
+    double lens_radius, time1, time2;
+};
+
+struct DeviceScene {
+    const BvhNode32* nodes;
+    const DSphere* spheres;
+    const DMoving* movings;
+    const DGravity* gravities;
+    const double* gravity_table;
+    const DRect* rects;
+    const DBox* boxes;
+    const DTri* tris;
+    const PrimMeta* meta[PRIM_TYPE_COUNT];
+    const Instance* instances;
+    const XformOp* ops;
+    const Medium* media;
+    const DMaterial* materials;
+    const DTexture* textures;
+    const PerlinTable* perlin;
+    const float4* texels; // rgba f32, row 0 = top of file
+    uint32_t n_main_instances;
+    uint32_t n_media;
+    uint32_t n_prims;
+    uint32_t pad_;
+    DCamera cam;
+    float background[3];
+    float pad2_;
+};
+
+} // namespace rtb

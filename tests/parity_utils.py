@@ -1,0 +1,102 @@
+"""Shared helpers of the GPU parity tests: build the same scene in the product library and in the
+oracle, make deterministic ray batches, compare hit records."""
+import ctypes as C
+
+import numpy as np
+
+import ray_tracing_series_rust_b200 as rtb
+from ray_tracing_series_rust_b200 import capi
+
+T_REL = 1e-5   # BASELINE.json north_star: t and normals within 1e-5 relative
+N_ABS = 1e-5
+
+
+def build_pair(orc, scene_id, seed=0xB001, param=0, camera=None):
+    """-> (gpu scene, oracle scene), both committed, built by the same call sequence."""
+    g, o = rtb.new_scene(), orc.new_scene()
+    for s in (g, o):
+        s.world_build(scene_id, seed, param)
+        if camera is not None:
+            s.set_camera(*camera)
+        s.commit()
+    assert g.num_prims() == o.num_prims()
+    return g, o
+
+
+def camera_fields(orc, oscene):
+    out = (C.c_double * 24)()
+    orc.api().check(orc.api().kat_camera(oscene.h, out))
+    a = np.array(out[:21]).reshape(7, 3)
+    return dict(origin=a[0], llc=a[1], horizontal=a[2], vertical=a[3], lens_radius=out[21], time1=out[22], time2=out[23])
+
+
+def primary_rays(cam, W, H, time=None):
+    """(i) one centre-of-pixel primary ray per pixel, zero lens offset, time = time1."""
+    i, j = np.meshgrid(np.arange(W), np.arange(H))
+    u = ((i + 0.5) / (W - 1)).reshape(-1, 1)
+    v = ((j + 0.5) / (H - 1)).reshape(-1, 1)
+    d = cam["llc"] + u * cam["horizontal"] + v * cam["vertical"] - cam["origin"]
+    o = np.tile(cam["origin"], (d.shape[0], 1))
+    return capi.make_rays(o, d, cam["time1"] if time is None else time)
+
+
+def random_rays(n, lo, hi, seed, time_range=None):
+    """(ii) origins uniform in a box, directions uniform on the sphere scaled by U[0.1, 10]."""
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= rng.uniform(0.1, 10.0, size=(n, 1))
+    r = capi.make_rays(o, d)
+    if time_range is not None:
+        r["time"] = rng.uniform(time_range[0], time_range[1], size=n)
+    return r
+
+
+def secondary_rays(hits, seed, time=None):
+    """(iii) rays leaving the surface points of a previous batch (exercises t_min = 0.001)."""
+    rng = np.random.default_rng(seed)
+    h = hits[hits["prim_id"] >= 0]
+    d = rng.normal(size=(h.shape[0], 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = h["normal"] + d  # Lambertian-like, un-normalised
+    d[np.abs(d).sum(1) < 1e-3] = (0, 1, 0)
+    r = capi.make_rays(h["p"], d)
+    if time is not None:
+        r["time"] = time
+    return r
+
+
+def compare_hits(hg, ho, label=""):
+    """Returns a dict of mismatch counts; asserts nothing."""
+    n = hg.shape[0]
+    id_bad = hg["prim_id"] != ho["prim_id"]
+    both = (~id_bad) & (ho["prim_id"] >= 0)
+    t_bad = np.zeros(n, bool)
+    n_bad = np.zeros(n, bool)
+    p_bad = np.zeros(n, bool)
+    uv_bad = np.zeros(n, bool)
+    ff_bad = np.zeros(n, bool)
+    mat_bad = np.zeros(n, bool)
+    tg, to = hg["t"][both], ho["t"][both]
+    t_bad[both] = np.abs(tg - to) > T_REL * np.maximum(1.0, np.abs(to))
+    n_bad[both] = np.abs(hg["normal"][both] - ho["normal"][both]).max(1) > N_ABS
+    scale = np.maximum(1.0, np.abs(ho["p"][both]).max(1))
+    p_bad[both] = np.abs(hg["p"][both] - ho["p"][both]).max(1) > T_REL * scale
+    du = np.abs(hg["u"][both] - ho["u"][both])
+    du = np.minimum(du, 1.0 - du)  # u wraps at the sphere seam
+    uv_bad[both] = (du > 1e-5) | (np.abs(hg["v"][both] - ho["v"][both]) > 1e-5)
+    ff_bad[both] = hg["front_face"][both] != ho["front_face"][both]
+    mat_bad[both] = hg["mat_id"][both] != ho["mat_id"][both]
+    return dict(label=label, n=n, hits=int((ho["prim_id"] >= 0).sum()), id=int(id_bad.sum()), t=int(t_bad.sum()), normal=int(n_bad.sum()),
+                p=int(p_bad.sum()), uv=int(uv_bad.sum()), front=int(ff_bad.sum()), mat=int(mat_bad.sum()), id_bad_idx=np.nonzero(id_bad)[0])
+
+
+def assert_parity(hg, ho, label="", max_id_frac=0.0):
+    r = compare_hits(hg, ho, label)
+    msg = {k: v for k, v in r.items() if k != "id_bad_idx"}
+    assert r["hits"] > 0, msg
+    assert r["id"] <= max_id_frac * r["n"], (msg, r["id_bad_idx"][:10])
+    for k in ("t", "normal", "p", "uv", "front", "mat"):
+        assert r[k] == 0, msg
+    return r

@@ -1,0 +1,202 @@
+"""CPU-side checks of the product library (no GPU needed): the C-ABI loads and exports every symbol
+include/rtb200.h declares, the builder validates its arguments like the reference's asserts/panics,
+and the host half of rt_scene_commit (flatten + BVH build) satisfies its invariants on every scene
+of the reference's scene library.  No compute call is made here; without a device commit/render
+must fail loudly with RT_ERR_CUDA (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ray_tracing_series_rust_b200 as rtb
+from ray_tracing_series_rust_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def has_cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module")
+def api():
+    if not os.path.exists(rtb.LIB_PATH):
+        rtb.build()
+    return rtb.load()
+
+
+def test_exports_every_declared_symbol(api):
+    hdr = open(os.path.join(ROOT, "include", "rtb200.h")).read()
+    names = set(re.findall(r"RTB_FN\((\w+)\)\s*\(", hdr))
+    names = {"rt_" + n for n in names} | set(re.findall(r"\b(rt_\w+)\s*\(", hdr))
+    names -= {"rt_scene", "rt_status", "rt_render_config", "rt_stats", "rt_ray", "rt_hit", "rt_prim_type", "rt_mat_type"}
+    assert len(names) >= 44
+    lib = C.CDLL(rtb.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in api.version()
+
+
+def test_struct_layouts_match_header():
+    # rt_render_config / rt_stats / rt_ray / rt_hit as ctypes/numpy see them
+    assert C.sizeof(capi.RenderConfig) == 56
+    assert C.sizeof(capi.Stats) == 8 * (3 + 8 + 5 + 1 + 2) + 3 * 8
+    assert capi.RAY_DTYPE.itemsize == 56 and capi.HIT_DTYPE.itemsize == 88
+
+
+def test_builder_ids_and_errors(api):
+    s = rtb.new_scene()
+    t0 = s.tex_solid((0.1, 0.2, 0.3))
+    t1 = s.tex_checker(t0, t0)
+    assert (t0, t1) == (0, 1)
+    m0 = s.lambertian(t1)
+    m1 = s.metal((1, 1, 1), 7.0)
+    assert (m0, m1) == (0, 1)
+    a = s.sphere((0, 0, 0), 1.0, m0)
+    b = s.box((0, 0, 0), (1, 1, 1), m1)
+    assert (a, b) == (0, 1)
+    with pytest.raises(capi.RtError) as e:
+        s.sphere((0, 0, 0), 1.0, 99)
+    assert e.value.code == -1 and "material" in str(e.value)
+    with pytest.raises(capi.RtError):
+        s.tex_checker(0, 42)
+    with pytest.raises(capi.RtError):
+        s.translate((0, 0, 0), 1234)
+    with pytest.raises(capi.RtError) as e:
+        s.bvh([], 0, 1)  # bvh.rs:27-28: BvhNode over nothing panics in the reference
+    assert e.value.code == -6
+    with pytest.raises(capi.RtError) as e:
+        s.commit()  # no root
+    assert e.value.code == -2
+    # a medium takes the next texture AND material ids (ConstantMedium::from_color, hit.rs:945-951)
+    med = s.constant_medium((1, 1, 1), 0.01, b)
+    assert s.tex_solid((0, 0, 0)) == 3 and s.dielectric(1.5) == 3 and med == 2
+
+
+def test_config_asserts_and_image_height(api):
+    cfg = capi.make_config(800, 1.5, 500, 50)
+    assert api.image_height(C.byref(cfg)) == 533  # (800 / 1.5) as i32
+    assert api.image_height(C.byref(capi.make_config(600, 1.6, 1, 1))) == 375
+    assert api.image_height(C.byref(capi.make_config(0, 1.6, 1, 1))) < 0
+
+
+def host_check(api, scene):
+    out = (C.c_int64 * 16)()
+    api.check(api.lib.rt_scene_host_check(C.c_void_p(scene.h), out))
+    return list(out)
+
+
+@pytest.mark.parametrize("scene_id,param", [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (5, 0), (6, 0), (7, 0), (8, 0), (9, 0),
+                                            (10, 0), (12, 0), (13, 0), (99, 0), (14, 24)])
+def test_flatten_and_bvh_invariants(api, scene_id, param):
+    api.lib.rt_scene_host_check.restype = C.c_int32
+    s = rtb.new_scene()
+    s.world_build(scene_id, 0xB001, param)
+    st = host_check(api, s)
+    nodes, depth, n_main, n_inst, n_media = st[0:5]
+    per_type = st[5:11]
+    assert st[12] == 0, f"BVH invariant violations: {st}"
+    assert depth <= 60 and nodes >= 2 and n_main >= 1
+    expect = {
+        4: dict(inst=3, media=0, rect=6, box=2),
+        5: dict(inst=3, media=2, rect=6, box=2),         # walls + two boundary worlds
+        6: dict(inst=4, media=2, box=400, rect=1, moving=1),
+        13: dict(inst=1, media=0),
+        14: dict(inst=1, media=0, tri=2 * 24 * 24, rect=7),
+    }.get(scene_id)
+    if expect:
+        assert n_inst == expect["inst"] and n_media == expect["media"]
+        if "rect" in expect:
+            assert per_type[3] == expect["rect"]
+        if "box" in expect:
+            assert per_type[4] == expect["box"]
+        if "tri" in expect:
+            assert per_type[5] == expect["tri"]
+        if "moving" in expect:
+            assert per_type[1] == expect["moving"]
+    if scene_id == 6:
+        assert per_type[0] == 1000 + 8  # cluster + 6 visible spheres + 2 medium boundaries
+        assert st[13] == 400 * 6 + 1 + 1 + 6 + 2 + 2 + 1000  # numbered leaves incl. the two media
+    if scene_id == 8:
+        assert per_type[2] > 400 and per_type[0] == 4  # gravity spheres + ground + three big spheres
+
+
+def test_nested_transforms_flatten_to_chains(api):
+    api.lib.rt_scene_host_check.restype = C.c_int32
+    s = rtb.new_scene()
+    m = s.lambertian((0.5, 0.5, 0.5))
+    inner = s.list([s.sphere((0, 0, 0), 1, m), s.rotate_y(30, s.box((0, 0, 0), (1, 2, 3), m))])
+    root = s.list([s.translate((5, 0, 0), inner), s.sphere((9, 9, 9), 1, m), s.translate((5, 0, 0), inner)])
+    s.set_root(root)
+    st = host_check(api, s)
+    # chains: [], [T1], [T1,R], [T2], [T2,R]  (the two translates are distinct objects)
+    assert st[3] == 5 and st[12] == 0
+    assert st[13] == 1 + 6 + 1  # shared leaves are numbered once
+
+
+def test_medium_inside_medium_boundary_is_unsupported(api):
+    s = rtb.new_scene()
+    m = s.lambertian((0.5, 0.5, 0.5))
+    inner = s.constant_medium((1, 1, 1), 0.1, s.sphere((0, 0, 0), 1, m))
+    s.set_root(s.constant_medium((1, 1, 1), 0.1, inner))
+    out = (C.c_int64 * 16)()
+    api.lib.rt_scene_host_check.restype = C.c_int32
+    assert api.lib.rt_scene_host_check(C.c_void_p(s.h), out) == -3
+
+
+def test_ply_and_ppm_io_roundtrip(api, orc, tmp_path):
+    # ASCII PLY subset of model.rs:13-62: product loader vs oracle loader on the same file
+    ply = tmp_path / "m.ply"
+    ply.write_text("ply\nformat ascii 1.0\ncomment x\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+                   "element face 2\nproperty list uchar int vertex_indices\nend_header\n"
+                   "0 0 0\n1 0 0\n1 1 0.5\n0 1 0 9 9\n3 0 1 2\n3 0 2 3\n")
+    s = rtb.new_scene()
+    m = s.lambertian((0.2, 0.2, 0.2))
+    mesh = s.ply_load(ply, 100.0, m)
+    s.set_root(s.bvh([mesh], 0, 1))
+    api.lib.rt_scene_host_check.restype = C.c_int32
+    st = host_check(api, s)
+    assert st[10] == 2 and st[12] == 0 and st[13] == 2
+    with pytest.raises(capi.RtError) as e:
+        s.ply_load(tmp_path / "missing.ply", 1.0, m)
+    assert e.value.code == -4
+    bad = tmp_path / "bad.ply"
+    bad.write_text("ply\nelement vertex 1\nelement face 1\nend_header\n0 0 0\n3 0 1 2\n")
+    with pytest.raises(capi.RtError):
+        s.ply_load(bad, 1.0, m)
+    # P3 writer: byte-identical between product and oracle, rows reversed (screen.rs:40-48)
+    rng = np.random.default_rng(0)
+    scr = rng.integers(0, 256, size=(5, 7, 3)).astype(np.float64)
+    pa, pb = tmp_path / "a.ppm", tmp_path / "b.ppm"
+    capi.write_ppm(api, pa, scr)
+    capi.write_ppm(orc.api(), pb, scr)
+    ta = pa.read_bytes()
+    assert ta == pb.read_bytes()
+    lines = ta.decode().split("\n")
+    assert lines[0] == "P3" and lines[1] == "7 5" and lines[2] == "255"
+    assert lines[3] == " ".join(str(int(x)) for x in scr[4, 0])  # first emitted row = top = Screen row H-1
+    # P3 reader (screen.rs:61-95) through Image::from_ppm: both libraries accept the file they wrote
+    s2, o2 = rtb.new_scene(), orc.new_scene()
+    assert s2.tex_image_ppm(pa) == 0 and o2.tex_image_ppm(pa) == 0
+    out = (C.c_double * 3)()
+    orc.api().kat_texture_value(o2.h, 0, 0.0, 1.0, (C.c_double * 3)(0, 0, 0), out)  # u=0, v=1 -> file row 0, col 0
+    assert tuple(out) == tuple(scr[4, 0] / 255.0)
+
+
+@pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
+def test_commit_fails_loudly_without_gpu(api):
+    s = rtb.new_scene()
+    s.world_build(4, 1)
+    with pytest.raises(capi.RtError) as e:
+        s.commit()
+    assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+    cfg = capi.make_config(32, 1.0, 1, 5)
+    with pytest.raises(capi.RtError) as e:
+        s.render(cfg)
+    assert e.value.code == -2

@@ -1,0 +1,38 @@
+"""Ad-hoc GPU exploration (not part of the product): times full-size renders of the BASELINE configs."""
+import sys, time, os, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+import ray_tracing_series_rust_b200 as rtb
+from ray_tracing_series_rust_b200 import capi
+
+def run(scene_id, W, aspect, spp, depth=50, param=0, slots=None, flags=0, label=""):
+    g = rtb.new_scene()
+    t0 = time.time(); g.world_build(scene_id, 0xB001, param); t1 = time.time(); g.commit(); t2 = time.time()
+    if slots:
+        import ctypes as C
+        rtb.load().lib.rt_scene_set_tuning(C.c_void_p(g.h), slots)
+    cfg = capi.make_config(W, aspect, spp, depth, seed=1, flags=flags)
+    scr, acc, st = g.render(cfg)
+    out = dict(label=label, scene=scene_id, W=W, spp=spp, slots=slots, build_s=round(t1 - t0, 3), commit_s=round(t2 - t1, 3),
+               ms_device=round(st["ms_device"], 2), ms_total=round(st["ms_total"], 2), ms_extend=round(st["ms_extend"], 2),
+               paths=st["paths"], seg_per_path=round(st["segments"] / max(st["paths"], 1), 3),
+               Mpaths_s=round(st["paths"] / st["ms_device"] / 1e3, 2), Mseg_s=round(st["segments"] / st["ms_device"] / 1e3, 2),
+               iters=st["iterations"], nodes_per_seg=round(st["box_tests"] / max(st["segments"], 1), 2),
+               prims_per_seg=round(st["prim_tests"][0] / max(st["segments"], 1), 2), mean=[round(float(x), 2) for x in scr.mean(axis=(0, 1))])
+    print(json.dumps(out), flush=True)
+    return scr
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "quick"
+    if what == "quick":
+        run(13, 800, 1.5, 50, label="C1a warm")
+        run(13, 800, 1.5, 500, label="C1a full")
+        run(13, 800, 1.5, 50, flags=3, label="C1a counted+timed")
+        run(99, 800, 1.5, 100, label="C1b")
+        run(5, 600, 1.0, 100, label="C2 smoke")
+        run(6, 1000, 1.0, 20, label="C3 final")
+        run(14, 1000, 1.0, 10, param=200, label="C4 mesh 80k")
+    elif what == "slots":
+        for s in (1 << 16, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22):
+            run(13, 800, 1.5, 100, slots=s, label="slots")
