@@ -4,7 +4,7 @@
 // ray_color world.rs:52-93 -> Hittable::hit / Material::scatter / Texture::value) with a pool of
 // N resident path slots advanced one segment per iteration:
 //
-//   k_generate   newpath queue -> camera rays (pixel jitter + Camera::get_ray, Philox)      [a1,a2,a23]
+//   k_shade_all  (regeneration part) new camera rays: pixel jitter + Camera::get_ray, Philox    [a1,a2,a23]
 //   k_extend     every live slot: world.hit(ray, 0.001, inf) incl. instances and media;
 //                miss -> background * throughput into the pixel; hit -> HitRecord into the slot and the
 //                slot index into the queue of its material type (warp-aggregated push)      [a3-a15]
@@ -19,6 +19,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <vector>
+
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 4
+#endif
 
 #include "rt_device.cuh"
 
@@ -38,11 +42,14 @@ struct PathState {
     uint8_t* alive;
 };
 
-enum CounterSlot { C_NEWQ0 = 0, C_NEWQ1 = 1, C_MATQ0 = 2, C_DEAD = 7, C_NUM = 8 };
+// Queues: one per material type plus the miss queue.  Counts are double buffered by iteration parity:
+// k_extend(i) fills counts[p], k_shade_all(i+1) drains counts[p] and clears counts[p^1].
+#define Q_MISS MAT_TYPE_COUNT
+#define Q_COUNT (MAT_TYPE_COUNT + 1)
 struct Queues {
-    uint32_t* newq[2];
-    uint32_t* matq[MAT_TYPE_COUNT];
-    uint32_t* counts;            // CounterSlot
+    uint32_t* q[Q_COUNT];
+    uint32_t* counts;            // [2][8]
+    uint32_t* dead;              // slots that found no more work
     unsigned long long* next_path;
     unsigned long long* stats;   // [0] segments, [1] nodes, [2] prims, [3] medium queries, [4..8] scatters by material
 };
@@ -59,13 +66,13 @@ struct JobDev {
 RT_DEV uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // warp-aggregated queue push: lanes of the warp that push to the same counter share one atomic
-RT_DEV uint32_t agg_reserve(uint32_t* counter, uint32_t key) {
+RT_DEV uint32_t agg_reserve(uint32_t* counters, uint32_t key) {
     const unsigned act = __activemask();
     const unsigned grp = __match_any_sync(act, key);
     const int leader = __ffs(grp) - 1;
     const uint32_t rank = __popc(grp & ((1u << lane_id()) - 1u));
     uint32_t base = 0;
-    if ((int)lane_id() == leader) base = atomicAdd(counter, (uint32_t)__popc(grp));
+    if ((int)lane_id() == leader) base = atomicAdd(counters + key, (uint32_t)__popc(grp));
     base = __shfl_sync(grp, base, leader);
     return base + rank;
 }
@@ -84,52 +91,57 @@ RT_DEV void accumulate(int64_t* __restrict__ accum, uint32_t pixel, float r, flo
     }
 }
 
-// ------------------------------------------------------------------ k_generate
-__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q, int cur) {
-    const uint32_t n = Q.counts[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int m = 0; m < MAT_TYPE_COUNT; ++m) Q.counts[C_MATQ0 + m] = 0; // consumed by last iteration's shade kernels
-    }
+// ------------------------------------------------------------------ k_init: every slot starts as a "miss" with zero throughput,
+// so that the first k_shade_all launch does nothing but generate the first camera rays.
+__global__ void k_init(PathState P, Queues Q, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = Q.newq[cur][i];
-        // claim the next path index (warp-aggregated)
-        const unsigned act = __activemask();
-        const int leader = __ffs(act) - 1;
-        unsigned long long base = 0;
-        if ((int)lane_id() == leader) base = atomicAdd(Q.next_path, (unsigned long long)__popc(act));
-        base = __shfl_sync(act, base, leader);
-        const unsigned long long L = base + __popc(act & ((1u << lane_id()) - 1u));
-        if (L >= J.total_paths) {
-            P.alive[slot] = 0;
-            atomicAdd(&Q.counts[C_DEAD], 1u);
-            continue;
-        }
-        const uint32_t s_local = (uint32_t)(L / J.npix_rendered);
-        const uint32_t pix = (uint32_t)(L % J.npix_rendered);
-        const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix % (uint32_t)J.W);
-        const uint64_t path_id = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
-        PathRng g;
-        g.init(J.seed, path_id, 0);
-        const double u = ((double)ii + g.gen()) / (double)(J.W - 1); // world.rs:1212
-        const double v = ((double)j + g.gen()) / (double)(J.H - 1);  // world.rs:1213
-        const Ray r = camera_get_ray(S.cam, u, v, g);
-        P.ox[slot] = r.o.x; P.oy[slot] = r.o.y; P.oz[slot] = r.o.z;
-        P.dx[slot] = r.d.x; P.dy[slot] = r.d.y; P.dz[slot] = r.d.z;
-        P.time[slot] = r.time;
-        P.tr[slot] = 1.f; P.tg[slot] = 1.f; P.tb[slot] = 1.f;
-        P.pixel[slot] = pix;
-        P.path_id[slot] = path_id;
-        P.draw[slot] = g.draw;
-        P.segment[slot] = 0;
-        P.alive[slot] = 1;
+        Q.q[Q_MISS][i] = i;
+        P.tr[i] = 0.f; P.tg[i] = 0.f; P.tb[i] = 0.f;
+        P.pixel[i] = 0;
+        P.alive[i] = 1;
     }
+    if (blockIdx.x == 0 && threadIdx.x < 16) Q.counts[threadIdx.x] = (threadIdx.x == Q_MISS) ? n : 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *Q.dead = 0; *Q.next_path = 0ull; }
+    if (blockIdx.x == 0 && threadIdx.x < 9) Q.stats[threadIdx.x] = 0ull;
 }
 
-// ------------------------------------------------------------------ k_extend
-__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q,
-                                                int64_t* __restrict__ accum, int cur) {
-    const int nxt = cur ^ 1;
-    if (blockIdx.x == 0 && threadIdx.x == 0) Q.counts[cur] = 0; // k_generate has consumed newq[cur]
+// New camera path into `slot` (pixel jitter world.rs:1212-1213 + Camera::get_ray), or retire the slot.
+RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queues& Q, uint32_t slot) {
+    const unsigned act = __activemask();
+    const int leader = __ffs(act) - 1;
+    unsigned long long base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(Q.next_path, (unsigned long long)__popc(act));
+    base = __shfl_sync(act, base, leader);
+    const unsigned long long L = base + __popc(act & ((1u << lane_id()) - 1u));
+    if (L >= J.total_paths) {
+        P.alive[slot] = 0;
+        atomicAdd(Q.dead, 1u);
+        return;
+    }
+    // sample-major order: consecutive path indices are neighbouring pixels of one sample => coherent primary rays
+    const uint32_t s_local = (uint32_t)(L / J.npix_rendered);
+    const uint32_t pix = (uint32_t)(L % J.npix_rendered);
+    const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix % (uint32_t)J.W);
+    const uint64_t path_id = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
+    PathRng g;
+    g.init(J.seed, path_id, 0);
+    const double u = ((double)ii + g.gen()) / (double)(J.W - 1); // world.rs:1212
+    const double v = ((double)j + g.gen()) / (double)(J.H - 1);  // world.rs:1213
+    const Ray r = camera_get_ray(S.cam, u, v, g);
+    P.ox[slot] = r.o.x; P.oy[slot] = r.o.y; P.oz[slot] = r.o.z;
+    P.dx[slot] = r.d.x; P.dy[slot] = r.d.y; P.dz[slot] = r.d.z;
+    P.time[slot] = r.time;
+    P.tr[slot] = 1.f; P.tg[slot] = 1.f; P.tb[slot] = 1.f;
+    P.pixel[slot] = pix;
+    P.path_id[slot] = path_id;
+    P.draw[slot] = g.draw;
+    P.segment[slot] = 0;
+}
+
+// ------------------------------------------------------------------ k_extend: world.hit(ray, 0.001, inf) for every live slot
+template <bool MEDIA, bool COUNT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q, int parity) {
+    uint32_t* counts = Q.counts + 8 * parity;
     uint32_t my_segments = 0;
     TraceCounters tc; tc.nodes = 0; tc.prims = 0;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < J.n_slots; slot += gridDim.x * blockDim.x) {
@@ -138,79 +150,202 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DeviceSc
         r.o = mk3(P.ox[slot], P.oy[slot], P.oz[slot]);
         r.d = mk3(P.dx[slot], P.dy[slot], P.dz[slot]);
         r.time = P.time[slot];
-        const uint64_t path_id = S.n_media ? P.path_id[slot] : 0ull;
-        const uint32_t segment = S.n_media ? P.segment[slot] : 0u;
+        uint64_t path_id = 0;
+        uint32_t segment = 0;
+        if (MEDIA) { path_id = P.path_id[slot]; segment = P.segment[slot]; }
         HitRec h;
-        bool hit;
-        if (J.count_events) hit = world_hit<true, false>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
-        else hit = world_hit<false, false>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        const bool hit = world_hit<COUNT, false, MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
         ++my_segments;
-        if (!hit) {
-            // world.rs:86-89: output += product * background; break
-            accumulate(accum, P.pixel[slot], P.tr[slot] * S.background[0], P.tg[slot] * S.background[1], P.tb[slot] * S.background[2]);
-            Q.newq[nxt][agg_reserve(&Q.counts[nxt], 0u)] = slot;
-            continue;
+        uint32_t qi = Q_MISS;
+        if (hit) {
+            P.ox[slot] = h.p.x; P.oy[slot] = h.p.y; P.oz[slot] = h.p.z;
+            P.nx[slot] = h.n.x; P.ny[slot] = h.n.y; P.nz[slot] = h.n.z;
+            P.hu[slot] = (float)h.u; P.hv[slot] = (float)h.v;
+            P.hmat[slot] = h.mat | (h.front ? 0x80000000u : 0u);
+            qi = __ldg(&S.materials[h.mat].type);
         }
-        P.ox[slot] = h.p.x; P.oy[slot] = h.p.y; P.oz[slot] = h.p.z;
-        P.nx[slot] = h.n.x; P.ny[slot] = h.n.y; P.nz[slot] = h.n.z;
-        P.hu[slot] = (float)h.u; P.hv[slot] = (float)h.v;
-        P.hmat[slot] = h.mat | (h.front ? 0x80000000u : 0u);
-        const uint32_t mt = __ldg(&S.materials[h.mat].type);
-        Q.matq[mt][agg_reserve(&Q.counts[C_MATQ0 + mt], 1u + mt)] = slot;
+        Q.q[qi][agg_reserve(counts, qi)] = slot;
     }
     // statistics: one atomic per warp
     const unsigned full = 0xffffffffu;
     uint32_t segs = my_segments;
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(full, segs, o);
     if (lane_id() == 0 && segs) atomicAdd(&Q.stats[0], (unsigned long long)segs);
-    if (J.count_events) {
+    if (COUNT) {
         uint32_t a = tc.nodes, b = tc.prims;
         for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(full, a, o); b += __shfl_xor_sync(full, b, o); }
         if (lane_id() == 0) { atomicAdd(&Q.stats[1], (unsigned long long)a); atomicAdd(&Q.stats[2], (unsigned long long)b); }
     }
 }
 
-// ------------------------------------------------------------------ k_shade<M>
-template <uint32_t M>
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q,
-                                               int64_t* __restrict__ accum, int cur) {
-    const int nxt = cur ^ 1;
-    const uint32_t n = Q.counts[C_MATQ0 + M];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&Q.stats[4 + M], (unsigned long long)n);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t slot = Q.matq[M][i];
-        const uint32_t hm = P.hmat[slot];
-        const DMaterial m = S.materials[hm & 0x7fffffffu];
-        const D3 p = mk3(P.ox[slot], P.oy[slot], P.oz[slot]);
-        bool scattered = false;
-        D3 dir = mk3(0, 0, 0);
-        F3 att = mkf3(0.f, 0.f, 0.f), emitted = mkf3(0.f, 0.f, 0.f);
-        PathRng g;
-        if (M == MAT_LIGHT) {
-            emitted = tex_value(S, m.tex, (double)P.hu[slot], (double)P.hv[slot], p); // hit.rs:1146-1151
-        } else {
-            g.init(J.seed, P.path_id[slot], P.draw[slot]);
-            const D3 n3 = mk3(P.nx[slot], P.ny[slot], P.nz[slot]);
-            if (M == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, p, n3, (double)P.hu[slot], (double)P.hv[slot], g, dir, att);
-            else if (M == MAT_METAL) scattered = scatter_metal(m, mk3(P.dx[slot], P.dy[slot], P.dz[slot]), n3, g, dir, att);
-            else if (M == MAT_DIELECTRIC) scattered = scatter_dielectric(m, mk3(P.dx[slot], P.dy[slot], P.dz[slot]), n3, (hm >> 31) != 0, g, dir, att);
-            else scattered = scatter_isotropic(S, m, p, (double)P.hu[slot], (double)P.hv[slot], g, dir, att);
-        }
-        if (scattered) {
-            const uint32_t seg = P.segment[slot] + 1;
-            if ((int32_t)seg < J.max_depth) { // world.rs:64-67: at most max_depth hit queries per path
-                P.tr[slot] *= att.x; P.tg[slot] *= att.y; P.tb[slot] *= att.z; // world.rs:75
-                P.dx[slot] = dir.x; P.dy[slot] = dir.y; P.dz[slot] = dir.z;     // origin is already rec.p
-                P.draw[slot] = g.draw;
-                P.segment[slot] = seg;
-                continue;
-            }
-            // depth exhausted: the path keeps what it accumulated (nothing, emitters do not scatter)
-        } else if (M == MAT_LIGHT) {
-            accumulate(accum, P.pixel[slot], P.tr[slot] * emitted.x, P.tg[slot] * emitted.y, P.tb[slot] * emitted.z); // world.rs:78-84
-        }
-        Q.newq[nxt][agg_reserve(&Q.counts[nxt], 0u)] = slot;
+// ------------------------------------------------------------------ k_shade_all: one launch drains every material queue and the miss queue.
+// The flat work index space is the concatenation of the queues, each padded to a multiple of 32, so a
+// warp only ever holds entries of ONE queue (material-coherent warps without one launch per material).
+// Paths that end here (miss, light, absorbed, depth exhausted) add their radiance to the pixel and the
+// slot is refilled in place with the next camera path.
+__global__ void __launch_bounds__(256) k_shade_all(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q,
+                                                   int64_t* __restrict__ accum, int parity) {
+    const uint32_t* counts = Q.counts + 8 * parity;
+    uint32_t start[Q_COUNT + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int q = 0; q < Q_COUNT; ++q) start[q + 1] = start[q] + ((counts[q] + 31u) & ~31u);
+    const uint32_t total = start[Q_COUNT];
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        Q.counts[8 * (parity ^ 1) + threadIdx.x] = 0; // next k_extend fills the other buffer
+        if (threadIdx.x < MAT_TYPE_COUNT && counts[threadIdx.x]) atomicAdd(&Q.stats[4 + threadIdx.x], (unsigned long long)counts[threadIdx.x]);
     }
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
+        int q = 0;
+#pragma unroll
+        for (int k = 1; k < Q_COUNT; ++k) q += (f >= start[k]) ? 1 : 0;
+        const uint32_t i = f - start[q];
+        if (i >= counts[q]) continue; // padding lane
+        const uint32_t slot = Q.q[q][i];
+        F3 contrib = mkf3(0.f, 0.f, 0.f);
+        bool ended = true;
+        if (q == Q_MISS) {
+            // world.rs:86-89: output += product * background
+            contrib = mkf3(P.tr[slot] * S.background[0], P.tg[slot] * S.background[1], P.tb[slot] * S.background[2]);
+        } else {
+            const uint32_t hm = P.hmat[slot];
+            const DMaterial m = S.materials[hm & 0x7fffffffu];
+            const D3 p = mk3(P.ox[slot], P.oy[slot], P.oz[slot]);
+            if (q == MAT_LIGHT) {
+                const F3 e = tex_value(S, m.tex, (double)P.hu[slot], (double)P.hv[slot], p); // hit.rs:1146-1151, world.rs:78-84
+                contrib = mkf3(P.tr[slot] * e.x, P.tg[slot] * e.y, P.tb[slot] * e.z);
+            } else {
+                PathRng g;
+                g.init(J.seed, P.path_id[slot], P.draw[slot]);
+                const D3 n3 = mk3(P.nx[slot], P.ny[slot], P.nz[slot]);
+                D3 dir = mk3(0, 0, 0);
+                F3 att = mkf3(0.f, 0.f, 0.f);
+                bool scattered;
+                if (q == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, p, n3, (double)P.hu[slot], (double)P.hv[slot], g, dir, att);
+                else if (q == MAT_METAL) scattered = scatter_metal(m, mk3(P.dx[slot], P.dy[slot], P.dz[slot]), n3, g, dir, att);
+                else if (q == MAT_DIELECTRIC) scattered = scatter_dielectric(m, mk3(P.dx[slot], P.dy[slot], P.dz[slot]), n3, (hm >> 31) != 0, g, dir, att);
+                else scattered = scatter_isotropic(S, m, p, (double)P.hu[slot], (double)P.hv[slot], g, dir, att);
+                const uint32_t seg = P.segment[slot] + 1;
+                if (scattered && (int32_t)seg < J.max_depth) { // world.rs:64-67: at most max_depth hit queries per path
+                    P.tr[slot] *= att.x; P.tg[slot] *= att.y; P.tb[slot] *= att.z; // world.rs:75
+                    P.dx[slot] = dir.x; P.dy[slot] = dir.y; P.dz[slot] = dir.z;     // the origin already is rec.p
+                    P.draw[slot] = g.draw;
+                    P.segment[slot] = seg;
+                    ended = false;
+                }
+                // absorbed (Metal) or depth exhausted: the path keeps what it has (nothing: emitters do not scatter)
+            }
+        }
+        if (ended) {
+            accumulate(accum, P.pixel[slot], contrib.x, contrib.y, contrib.z);
+            regenerate(S, J, P, Q, slot);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ k_mega: persistent fused variant (RT_MODE_FUSED)
+// One thread owns one path at a time and keeps its whole state in registers: generate -> world.hit ->
+// scatter -> ... until the path ends, then the lane pulls the next path index.  No path state and no
+// queues in HBM, one launch per render.  Path indices are claimed per warp in chunks of CHUNK
+// consecutive indices (= neighbouring pixels of one sample), so a warp's primary rays stay spatially
+// close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
+// two modes produce bit-identical images.
+#define RT_MEGA_CHUNK 512u
+template <bool MEDIA, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
+                                                      int64_t* __restrict__ accum) {
+    const unsigned full = 0xffffffffu;
+    unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform
+    Ray r;
+    r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.time = 0.0;
+    float tr = 0.f, tg = 0.f, tb = 0.f;
+    uint32_t pixel = 0, draw = 0, segment = 0;
+    uint64_t path_id = 0;
+    bool alive = false, exhausted = false;
+    uint32_t my_segments = 0;
+    for (;;) {
+        // ---- refill idle lanes
+        const unsigned need = __ballot_sync(full, !alive && !exhausted);
+        if (need) {
+            const uint32_t n_need = __popc(need);
+            // make sure the warp's chunk covers the request; leftover indices of the old chunk are used first
+            unsigned long long avail = chunk_end - chunk_next;
+            unsigned long long second_base = 0;
+            if (avail < n_need) {
+                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)RT_MEGA_CHUNK);
+                second_base = __shfl_sync(full, second_base, 0);
+            }
+            if (!alive && !exhausted) {
+                const uint32_t rank = __popc(need & ((1u << lane_id()) - 1u));
+                unsigned long long L = (rank < avail) ? chunk_next + rank : second_base + (rank - avail);
+                if (L >= J.total_paths) {
+                    exhausted = true;
+                } else {
+                    const uint32_t s_local = (uint32_t)(L / J.npix_rendered);
+                    pixel = (uint32_t)(L % J.npix_rendered);
+                    const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel % (uint32_t)J.W);
+                    path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
+                    PathRng g;
+                    g.init(J.seed, path_id, 0);
+                    const double u = ((double)ii + g.gen()) / (double)(J.W - 1); // world.rs:1212
+                    const double v = ((double)j + g.gen()) / (double)(J.H - 1);  // world.rs:1213
+                    r = camera_get_ray(S.cam, u, v, g);
+                    draw = g.draw;
+                    tr = tg = tb = 1.f;
+                    segment = 0;
+                    alive = true;
+                }
+            }
+            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + RT_MEGA_CHUNK; }
+            else chunk_next += n_need;
+        }
+        if (!__any_sync(full, alive)) break;
+        if (!alive) continue;
+        // ---- one ray_color iteration (world.rs:63-91)
+        HitRec h;
+        const bool hit = world_hit<false, false, MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        ++my_segments;
+        F3 contrib = mkf3(0.f, 0.f, 0.f);
+        bool ended = true;
+        if (!hit) {
+            contrib = mkf3(tr * S.background[0], tg * S.background[1], tb * S.background[2]);
+        } else {
+            const DMaterial m = S.materials[h.mat];
+            if (m.type == MAT_LIGHT) {
+                const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
+                contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
+            } else {
+                PathRng g;
+                g.init(J.seed, path_id, draw);
+                D3 dir = mk3(0, 0, 0);
+                F3 att = mkf3(0.f, 0.f, 0.f);
+                bool scattered;
+                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
+                else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
+                else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                if (scattered && (int32_t)(segment + 1) < J.max_depth) {
+                    tr *= att.x; tg *= att.y; tb *= att.z;
+                    r.o = h.p; r.d = dir;
+                    draw = g.draw;
+                    ++segment;
+                    ended = false;
+                }
+            }
+        }
+        if (ended) {
+            accumulate(accum, pixel, contrib.x, contrib.y, contrib.z);
+            alive = false;
+        }
+    }
+    uint32_t segs = my_segments;
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(full, segs, o);
+    if (lane_id() == 0 && segs) atomicAdd(&Q.stats[0], (unsigned long long)segs);
+}
+
+__global__ void k_mega_init(Queues Q) {
+    if (threadIdx.x == 0) { *Q.next_path = 0ull; *Q.dead = 0; }
+    if (threadIdx.x < 9) Q.stats[threadIdx.x] = 0ull;
 }
 
 // ------------------------------------------------------------------ resolve (vec3.rs:89-107 + Screen layout)
@@ -241,7 +376,7 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Dev
         r.d = mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
         r.time = rays[i].time;
         HitRec h;
-        const bool hit = world_hit<false, true>(S, r, t_min, t_max, (flags & RT_TRACE_SEEDED_MEDIA) != 0, seed, (uint64_t)i, 0u, h, nullptr);
+        const bool hit = world_hit<false, true, true>(S, r, t_min, t_max, (flags & RT_TRACE_SEEDED_MEDIA) != 0, seed, (uint64_t)i, 0u, h, nullptr);
         rt_hit o;
         if (hit) {
             o.prim_id = (int32_t)h.prim_id; o.mat_id = (int32_t)h.mat; o.t = h.t;
@@ -277,10 +412,6 @@ __global__ void k_unit_op(const __grid_constant__ DeviceScene S, int op, uint32_
         const Ray r = camera_get_ray(S.cam, u, v, g);
         out[0] = r.o.x; out[1] = r.o.y; out[2] = r.o.z; out[3] = r.d.x; out[4] = r.d.y; out[5] = r.d.z; out[6] = r.time;
     }
-}
-
-__global__ void k_iota(uint32_t* q, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) q[i] = i;
 }
 
 // ------------------------------------------------------------------ host side
@@ -321,10 +452,14 @@ done:
     return err;
 }
 
-namespace {
-struct Arena { // one allocation for the whole path state + queues
+struct Workspace { // path state + queues, cached per scene between renders
     char* base = nullptr;
-    size_t used = 0, cap = 0;
+    size_t cap = 0, used = 0;
+    uint32_t n_slots = 0;
+    PathState P;
+    Queues Q;
+    unsigned int* h_flag = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
     template <class T> T* take(size_t n) {
         used = (used + 255) & ~(size_t)255;
         T* p = reinterpret_cast<T*>(base + used);
@@ -332,10 +467,60 @@ struct Arena { // one allocation for the whole path state + queues
         return p;
     }
 };
-} // namespace
+
+void free_workspace(Workspace* w) {
+    if (!w) return;
+    if (w->base) cudaFree(w->base);
+    if (w->h_flag) cudaFreeHost(w->h_flag);
+    if (w->ev_begin) cudaEventDestroy(w->ev_begin);
+    if (w->ev_end) cudaEventDestroy(w->ev_end);
+    if (w->ev_poll[0]) cudaEventDestroy(w->ev_poll[0]);
+    if (w->ev_poll[1]) cudaEventDestroy(w->ev_poll[1]);
+    delete w;
+}
+
+static cudaError_t ensure_workspace(Workspace*& w, uint32_t N) {
+    if (w && w->n_slots == N) return cudaSuccess;
+    free_workspace(w);
+    w = new Workspace();
+    cudaError_t err = cudaSuccess;
+    const size_t per_slot = 7 * 8 + 3 * 8 + 2 * 4 + 4 + 3 * 4 + 4 + 8 + 4 + 4 + 1 + Q_COUNT * 4;
+    w->cap = (size_t)N * per_slot + 64 * 256 + 4096;
+    if ((err = cudaMalloc(&w->base, w->cap)) != cudaSuccess) return err;
+    PathState& P = w->P;
+    Queues& Q = w->Q;
+    P.ox = w->take<double>(N); P.oy = w->take<double>(N); P.oz = w->take<double>(N);
+    P.dx = w->take<double>(N); P.dy = w->take<double>(N); P.dz = w->take<double>(N); P.time = w->take<double>(N);
+    P.nx = w->take<double>(N); P.ny = w->take<double>(N); P.nz = w->take<double>(N);
+    P.hu = w->take<float>(N); P.hv = w->take<float>(N); P.hmat = w->take<uint32_t>(N);
+    P.tr = w->take<float>(N); P.tg = w->take<float>(N); P.tb = w->take<float>(N);
+    P.pixel = w->take<uint32_t>(N); P.path_id = w->take<uint64_t>(N); P.draw = w->take<uint32_t>(N); P.segment = w->take<uint32_t>(N);
+    P.alive = w->take<uint8_t>(N);
+    for (int q = 0; q < Q_COUNT; ++q) Q.q[q] = w->take<uint32_t>(N);
+    Q.counts = w->take<uint32_t>(16);
+    Q.dead = w->take<uint32_t>(1);
+    Q.next_path = w->take<unsigned long long>(1);
+    Q.stats = w->take<unsigned long long>(9);
+    if (w->used > w->cap) return cudaErrorMemoryAllocation;
+    if ((err = cudaMallocHost(&w->h_flag, 2 * sizeof(unsigned int))) != cudaSuccess) return err;
+    if ((err = cudaEventCreate(&w->ev_begin)) != cudaSuccess) return err;
+    if ((err = cudaEventCreate(&w->ev_end)) != cudaSuccess) return err;
+    if ((err = cudaEventCreateWithFlags(&w->ev_poll[0], cudaEventDisableTiming)) != cudaSuccess) return err;
+    if ((err = cudaEventCreateWithFlags(&w->ev_poll[1], cudaEventDisableTiming)) != cudaSuccess) return err;
+    w->n_slots = N;
+    return cudaSuccess;
+}
+
+template <bool MEDIA, bool COUNT>
+static void launch_extend(int occ, int blocks, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
+    // occ = resident 128-thread blocks per SM the kernel is compiled for (register budget 128 / 96 / 80)
+    if (occ >= 6) k_extend<MEDIA, COUNT, 6><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+    else if (occ == 5) k_extend<MEDIA, COUNT, 5><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+    else k_extend<MEDIA, COUNT, 4><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+}
 
 cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const RenderTuning& tune, int64_t* d_accum, cudaStream_t stream,
-                          rt_stats* stats) {
+                          rt_stats* stats, Workspace** wsp) {
     cudaError_t err = cudaSuccess;
     JobDev J;
     J.W = job.width; J.H = job.height; J.rows = job.rows; J.spp_total = job.spp_total;
@@ -349,98 +534,85 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
     N = (N + 127u) & ~127u;
     J.n_slots = N;
 
-    Arena A;
-    PathState P;
-    Queues Q;
-    unsigned int* h_flag = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ext_events;
     unsigned long long h_stats[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t iterations = 0, launches = 0;
     float ms_device = 0.f;
     double ms_extend = 0.0;
+    Workspace* w = nullptr;
 
     if (J.total_paths == 0) goto done;
+    CK(ensure_workspace(*wsp, N));
+    w = *wsp;
     {
-        const size_t per_slot = 7 * 8 + 3 * 8 + 2 * 4 + 4 + 3 * 4 + 4 + 8 + 4 + 4 + 1 + (2 + MAT_TYPE_COUNT) * 4;
-        A.cap = (size_t)N * per_slot + 64 * 256 + 4096;
-        CK(cudaMalloc(&A.base, A.cap));
-        P.ox = A.take<double>(N); P.oy = A.take<double>(N); P.oz = A.take<double>(N);
-        P.dx = A.take<double>(N); P.dy = A.take<double>(N); P.dz = A.take<double>(N); P.time = A.take<double>(N);
-        P.nx = A.take<double>(N); P.ny = A.take<double>(N); P.nz = A.take<double>(N);
-        P.hu = A.take<float>(N); P.hv = A.take<float>(N); P.hmat = A.take<uint32_t>(N);
-        P.tr = A.take<float>(N); P.tg = A.take<float>(N); P.tb = A.take<float>(N);
-        P.pixel = A.take<uint32_t>(N); P.path_id = A.take<uint64_t>(N); P.draw = A.take<uint32_t>(N); P.segment = A.take<uint32_t>(N);
-        P.alive = A.take<uint8_t>(N);
-        Q.newq[0] = A.take<uint32_t>(N); Q.newq[1] = A.take<uint32_t>(N);
-        for (int m = 0; m < MAT_TYPE_COUNT; ++m) Q.matq[m] = A.take<uint32_t>(N);
-        Q.counts = A.take<uint32_t>(C_NUM);
-        Q.next_path = A.take<unsigned long long>(1);
-        Q.stats = A.take<unsigned long long>(9);
-        if (A.used > A.cap) { err = cudaErrorMemoryAllocation; goto done; }
-    }
-    CK(cudaMallocHost(&h_flag, 2 * sizeof(unsigned int)));
-    CK(cudaEventCreate(&ev_begin));
-    CK(cudaEventCreate(&ev_end));
-    CK(cudaEventCreateWithFlags(&ev_poll[0], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ev_poll[1], cudaEventDisableTiming));
-    {
-        CK(cudaMemsetAsync(P.alive, 0, N, stream));
-        CK(cudaMemsetAsync(Q.counts, 0, C_NUM * sizeof(uint32_t), stream));
-        CK(cudaMemsetAsync(Q.next_path, 0, sizeof(unsigned long long), stream));
-        CK(cudaMemsetAsync(Q.stats, 0, 9 * sizeof(unsigned long long), stream));
+        PathState& P = w->P;
+        Queues& Q = w->Q;
         const int qblocks = (int)std::min<uint32_t>((N + 255) / 256, 148 * 8);
-        k_iota<<<qblocks, 256, 0, stream>>>(Q.newq[0], N);
+        const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, tune.extend_occ) * (uint32_t)std::max(1, tune.extend_waves));
+        const bool media = scene.n_media != 0;
+        CK(cudaEventRecord(w->ev_begin, stream));
+        if (tune.mode == RT_MODE_FUSED) {
+            k_mega_init<<<1, 32, 0, stream>>>(Q);
+            const int occ = std::max(2, std::min(4, tune.mega_occ));
+            const int mblocks = 148 * occ;
+            if (media) {
+                if (occ >= 4) k_mega<true, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (occ == 3) k_mega<true, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<true, 2><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else {
+                if (occ >= 4) k_mega<false, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (occ == 3) k_mega<false, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<false, 2><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+            }
+            CK(cudaGetLastError());
+            launches += 2;
+            iterations = 1;
+            CK(cudaEventRecord(w->ev_end, stream));
+            CK(cudaMemcpyAsync(h_stats, Q.stats, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            CK(cudaEventElapsedTime(&ms_device, w->ev_begin, w->ev_end));
+            goto done;
+        }
+        k_init<<<qblocks, 256, 0, stream>>>(P, Q, N);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(Q.counts + C_NEWQ0, &N, sizeof(uint32_t), cudaMemcpyHostToDevice, stream)); // pageable source: copied before return
-
-        const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148 * 16);
-        CK(cudaEventRecord(ev_begin, stream));
-        int cur = 0;
+        ++launches;
+        int parity = 0;   // counts buffer the next k_shade_all drains
         const int batch = 16; // iterations enqueued between completion checks
-        int pending = -1;     // index of the poll slot still in flight
+        int pending = -1;
         bool finished = false;
-        h_flag[0] = h_flag[1] = 0;
+        w->h_flag[0] = w->h_flag[1] = 0;
         for (uint64_t guard = 0; !finished && guard < (1ull << 40); ++guard) {
             const int slot = (int)(guard & 1);
             for (int it = 0; it < batch; ++it) {
-                k_generate<<<qblocks, 256, 0, stream>>>(scene, J, P, Q, cur);
+                k_shade_all<<<qblocks, 256, 0, stream>>>(scene, J, P, Q, d_accum, parity);
+                parity ^= 1;
+                cudaEvent_t ea = nullptr, eb = nullptr;
                 if (tune.timed_extend) {
-                    cudaEvent_t a, b;
-                    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-                    CK(cudaEventRecord(a, stream));
-                    k_extend<<<eblocks, 128, 0, stream>>>(scene, J, P, Q, d_accum, cur);
-                    CK(cudaEventRecord(b, stream));
-                    ext_events.push_back(a); ext_events.push_back(b);
-                } else {
-                    k_extend<<<eblocks, 128, 0, stream>>>(scene, J, P, Q, d_accum, cur);
+                    CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
+                    CK(cudaEventRecord(ea, stream));
                 }
-                k_shade<MAT_LAMBERTIAN><<<qblocks, 256, 0, stream>>>(scene, J, P, Q, d_accum, cur);
-                k_shade<MAT_METAL><<<qblocks, 256, 0, stream>>>(scene, J, P, Q, d_accum, cur);
-                k_shade<MAT_DIELECTRIC><<<qblocks, 256, 0, stream>>>(scene, J, P, Q, d_accum, cur);
-                k_shade<MAT_LIGHT><<<qblocks, 256, 0, stream>>>(scene, J, P, Q, d_accum, cur);
-                k_shade<MAT_ISOTROPIC><<<qblocks, 256, 0, stream>>>(scene, J, P, Q, d_accum, cur);
-                cur ^= 1;
+                if (media) { if (tune.count_events) launch_extend<true, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(tune.extend_occ, eblocks, stream, scene, J, P, Q, parity); }
+                else { if (tune.count_events) launch_extend<false, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<false, false>(tune.extend_occ, eblocks, stream, scene, J, P, Q, parity); }
+                if (tune.timed_extend) {
+                    CK(cudaEventRecord(eb, stream));
+                    ext_events.push_back(ea); ext_events.push_back(eb);
+                }
                 ++iterations;
-                launches += 7;
+                launches += 2;
             }
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(&h_flag[slot], Q.counts + C_DEAD, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
-            CK(cudaEventRecord(ev_poll[slot], stream));
+            CK(cudaMemcpyAsync(&w->h_flag[slot], Q.dead, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaEventRecord(w->ev_poll[slot], stream));
             if (pending >= 0) {
-                CK(cudaEventSynchronize(ev_poll[pending]));
-                if (h_flag[pending] >= N) finished = true;
+                CK(cudaEventSynchronize(w->ev_poll[pending]));
+                if (w->h_flag[pending] >= N) finished = true;
             }
             pending = slot;
         }
-        if (!finished) {
-            // drain: the last enqueued batch may have finished the job
-            CK(cudaEventSynchronize(ev_poll[pending]));
-        }
-        CK(cudaEventRecord(ev_end, stream));
+        CK(cudaEventRecord(w->ev_end, stream));
         CK(cudaMemcpyAsync(h_stats, Q.stats, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
-        CK(cudaEventElapsedTime(&ms_device, ev_begin, ev_end));
+        CK(cudaEventElapsedTime(&ms_device, w->ev_begin, w->ev_end));
         for (size_t i = 0; i + 1 < ext_events.size(); i += 2) {
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, ext_events[i], ext_events[i + 1]));
@@ -460,12 +632,6 @@ done:
         stats->ms_extend = ms_extend;
     }
     for (cudaEvent_t e : ext_events) cudaEventDestroy(e);
-    if (ev_begin) cudaEventDestroy(ev_begin);
-    if (ev_end) cudaEventDestroy(ev_end);
-    if (ev_poll[0]) cudaEventDestroy(ev_poll[0]);
-    if (ev_poll[1]) cudaEventDestroy(ev_poll[1]);
-    if (h_flag) cudaFreeHost(h_flag);
-    if (A.base) cudaFree(A.base);
     return err;
 }
 

@@ -16,16 +16,25 @@ struct RenderJob {
     uint64_t seed;
 };
 
+#define RT_MODE_WAVEFRONT 0 // k_extend + k_shade_all per iteration, per-material queues, path state in HBM
+#define RT_MODE_FUSED 1     // k_mega: persistent threads, path state in registers
+
 struct RenderTuning {
+    int mode = RT_MODE_WAVEFRONT;
+    int mega_occ = 3;               // k_mega variant: resident 128-thread blocks per SM (2 / 3 / 4)
     uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
     int timed_extend = 0;           // 1: bracket every extend launch with CUDA events (for the roofline)
     int count_events = 0;           // 1: count BVH node visits / primitive tests on the device
+    int extend_occ = 4;             // k_extend variant: resident 128-thread blocks per SM (4 / 5 / 6)
+    int extend_waves = 4;           // k_extend grid = 148 * extend_occ * extend_waves blocks (grid-stride over the slots)
 };
 
 // Wavefront render of one shard into a device-resident int64 fixed-point accumulator (W*H*3).
 // Returns cudaSuccess or the first CUDA error; fills stats.
+struct Workspace; // path state + queues, allocated on first use and reused by later renders of the scene
+void free_workspace(Workspace* w);
 cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const RenderTuning& tune, int64_t* d_accum, cudaStream_t stream,
-                          rt_stats* stats);
+                          rt_stats* stats, Workspace** workspace);
 
 // accum -> Screen-layout doubles (vec3.rs:89-107), rows >= rendered_rows stay 0
 cudaError_t launch_resolve(const int64_t* d_accum, double* d_screen, int32_t width, int32_t height, int32_t spp, int32_t rendered_rows,

@@ -120,35 +120,48 @@ RT_DEV void xform_ray(const XformOp* __restrict__ ops, uint32_t off, uint32_t le
 
 // ------------------------------------------------------------------ best-hit bookkeeping
 struct BestHit {
-    double t;        // closest_so_far
-    int32_t prim_id; // -1 = none; ties (equal t) go to the larger depth-first id = "later list element wins" (hit.rs:675-683)
-    uint32_t type, idx, side, inst;
+    double t;      // closest_so_far
+    uint32_t type; // PrimType, 0xffffffff = nothing found yet
+    uint32_t idx, side, inst;
 };
-
+#define RT_NONE 0xffffffffu
 #define RT_INF (__longlong_as_double(0x7ff0000000000000LL))
+RT_DEV void best_init(BestHit& b, double t_max) { b.t = t_max; b.type = RT_NONE; b.idx = 0; b.side = 0; b.inst = 0; }
 
+// Accepts t <= closest_so_far like the reference's list scan (hit.rs:675-683: the later element wins
+// an exact tie).  Ties are decided by the depth-first leaf id, fetched only when a tie happens.
 RT_DEV void consider(const DeviceScene& S, BestHit& best, double t, uint32_t type, uint32_t idx, uint32_t side, uint32_t inst) {
     if (!(t <= best.t) || !(t < RT_INF)) return; // NaN and +inf are rejected (documented divergence: the reference lets t = +inf through)
-    const int32_t pid = (int32_t)(__ldg(&S.meta[type][idx].prim_id) + side);
-    if (t < best.t || pid > best.prim_id) {
-        best.t = t; best.prim_id = pid; best.type = type; best.idx = idx; best.side = side; best.inst = inst;
+    if (t == best.t && best.type != RT_NONE) {
+        const uint32_t pid_new = __ldg(&S.meta[type][idx].prim_id) + side;
+        const uint32_t pid_old = __ldg(&S.meta[best.type][best.idx].prim_id) + best.side;
+        if (pid_new < pid_old) return;
     }
+    best.t = t; best.type = type; best.idx = idx; best.side = side; best.inst = inst;
 }
 
 // ------------------------------------------------------------------ primitive tests (f64)
-// Sphere / MovingSphere / GravitySphere::hit root selection (hit.rs:204-222, 282-300, 398-416)
-RT_DEV double sphere_root(const Ray& r, D3 c, double radius, double t_min, double t_max) {
+// Sphere / MovingSphere / GravitySphere::hit root selection (hit.rs:204-222, 282-300, 398-416).
+// a = d.d and 1/a depend only on the ray: computed once per ray per instance (RayPre).
+struct RayPre {
+    double a, inv_a;
+};
+RT_DEV RayPre make_raypre(const Ray& r) {
+    RayPre p;
+    p.a = length_squared(r.d);
+    p.inv_a = 1.0 / p.a;
+    return p;
+}
+RT_DEV double sphere_root(const Ray& r, const RayPre& pre, D3 c, double radius, double t_min, double t_max) {
     const D3 oc = r.o - c;
-    const double a = length_squared(r.d);
     const double half_b = dot(oc, r.d);
     const double cc = length_squared(oc) - radius * radius;
-    const double disc = half_b * half_b - a * cc;
+    const double disc = half_b * half_b - pre.a * cc;
     if (disc < 0.0) return RT_INF;
     const double sqrtd = sqrt(disc);
-    const double inv_a = 1.0 / a;
-    double root = (-half_b - sqrtd) * inv_a;
+    double root = (-half_b - sqrtd) * pre.inv_a;
     if (root < t_min || t_max < root) {
-        root = (-half_b + sqrtd) * inv_a;
+        root = (-half_b + sqrtd) * pre.inv_a;
         if (root < t_min || t_max < root) return RT_INF;
     }
     return root;
@@ -246,97 +259,89 @@ struct TraceCounters {
 };
 
 // Tests every primitive of one leaf against the object-space ray.
-RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t type, uint32_t first, uint32_t n, uint32_t inst) {
+RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, const RayPre& pre, double t_min, BestHit& best, uint32_t type, uint32_t first, uint32_t n,
+                      uint32_t inst) {
     for (uint32_t i = first; i < first + n; ++i) {
-        switch (type) {
-        case PRIM_SPHERE: {
-            const double4 s = *reinterpret_cast<const double4*>(&S.spheres[i]);
-            consider(S, best, sphere_root(r, mk3(s.x, s.y, s.z), s.w, t_min, best.t), type, i, 0, inst);
-        } break;
-        case PRIM_MOVING: {
-            const DMoving m = S.movings[i];
-            consider(S, best, sphere_root(r, moving_center(m, r.time), m.r, t_min, best.t), type, i, 0, inst);
-        } break;
-        case PRIM_GRAVITY: {
-            const DGravity g = S.gravities[i];
-            consider(S, best, sphere_root(r, gravity_center(S, g, r.time), g.r, t_min, best.t), type, i, 0, inst);
-        } break;
-        case PRIM_RECT: {
+        if (type <= PRIM_GRAVITY) { // the three sphere kinds share the root solve (hit.rs:204-222, 282-300, 398-416)
+            D3 c;
+            double rad;
+            if (type == PRIM_SPHERE) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(&S.spheres[i]));
+                const double2 b = __ldg(reinterpret_cast<const double2*>(&S.spheres[i]) + 1);
+                c = mk3(a.x, a.y, b.x); rad = b.y;
+            } else if (type == PRIM_MOVING) {
+                const DMoving m = S.movings[i];
+                c = moving_center(m, r.time); rad = m.r;
+            } else {
+                const DGravity g = S.gravities[i];
+                c = gravity_center(S, g, r.time); rad = g.r;
+            }
+            consider(S, best, sphere_root(r, pre, c, rad, t_min, best.t), type, i, 0, inst);
+        } else if (type == PRIM_RECT) {
             const DRect q = S.rects[i];
             consider(S, best, rect_t(r, q, t_min, best.t), type, i, 0, inst);
-        } break;
-        case PRIM_BOX: {
+        } else if (type == PRIM_BOX) {
             const DBox b = S.boxes[i];
             uint32_t side;
             const double t = box_t(r, b, t_min, best.t, side);
             consider(S, best, t, type, i, side, inst);
-        } break;
-        default: { // PRIM_TRI
+        } else { // PRIM_TRI
             consider(S, best, tri_t(r, &S.tris[i], t_min, best.t), type, i, 0, inst);
-        } break;
         }
     }
 }
 
 // Closest hit inside one instance; `r` is already in the instance's space.
+//
+// "while-while" traversal: each lane walks interior nodes until it holds a pending leaf (or is done);
+// only when every lane of the warp has left that inner loop are the leaves processed, so the expensive
+// f64 primitive tests run with as many lanes active as possible.  The instance root is stored as the
+// first node of a sibling pair whose second node is an empty leaf, so the root needs no special case.
 template <bool COUNT>
 RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r, double t_min, BestHit& best, TraceCounters* cnt) {
-    const Instance* ip = &S.instances[inst_idx];
     const RayF f = make_rayf(r);
+    const RayPre pre = make_raypre(r);
     const float tminf = f32_down(t_min);
+    float tmaxf = f32_up(best.t);
     const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
     uint32_t stack[RT_STACK];
     int sp = 0;
-    uint32_t cur = __ldg(&ip->root);
-    {   // root: its own box, then leaf or descend
-        const float4 lo = __ldg(nodes + 2 * cur), hi = __ldg(nodes + 2 * cur + 1);
-        float tn;
-        if (COUNT) cnt->nodes++;
-        if (!slab(lo, hi, f, tminf, f32_up(best.t), tn)) return;
-        const uint32_t count = __float_as_uint(hi.w);
-        if (count) {
-            if (COUNT) cnt->prims += count & 0xffffffu;
-            leaf_test(S, r, t_min, best, count >> 24, __float_as_uint(lo.w), count & 0xffffffu, inst_idx);
-            return;
-        }
-        cur = __float_as_uint(lo.w);
-    }
-    for (;;) {
-        // cur = index of the left child of an interior node: fetch both siblings (64 B)
-        const float4 lo0 = __ldg(nodes + 2 * cur), hi0 = __ldg(nodes + 2 * cur + 1);
-        const float4 lo1 = __ldg(nodes + 2 * cur + 2), hi1 = __ldg(nodes + 2 * cur + 3);
-        const float tmaxf = f32_up(best.t);
-        float tn0, tn1;
-        bool h0 = slab(lo0, hi0, f, tminf, tmaxf, tn0);
-        bool h1 = slab(lo1, hi1, f, tminf, tmaxf, tn1);
-        if (COUNT) cnt->nodes += 2;
-        const uint32_t c0 = __float_as_uint(hi0.w), c1 = __float_as_uint(hi1.w);
-        if (h0 && c0) {
-            if (COUNT) cnt->prims += c0 & 0xffffffu;
-            leaf_test(S, r, t_min, best, c0 >> 24, __float_as_uint(lo0.w), c0 & 0xffffffu, inst_idx);
-            h0 = false;
-        }
-        if (h1 && c1) {
-            // the first leaf may have shortened the ray
-            if (tn1 <= f32_up(best.t)) {
-                if (COUNT) cnt->prims += c1 & 0xffffffu;
-                leaf_test(S, r, t_min, best, c1 >> 24, __float_as_uint(lo1.w), c1 & 0xffffffu, inst_idx);
+    const uint32_t DONE = 0xffffffffu;
+    uint32_t cur = __ldg(&S.instances[inst_idx].root);
+    while (cur != DONE) {
+        uint32_t leaf_first0 = 0, leaf_cnt0 = 0, leaf_first1 = 0, leaf_cnt1 = 0; // cnt = (type << 24) | n, 0 = none
+        while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0) {
+            // cur = index of the left node of a sibling pair: one 64-byte fetch, two slab tests
+            const float4 lo0 = __ldg(nodes + 2 * cur), hi0 = __ldg(nodes + 2 * cur + 1);
+            const float4 lo1 = __ldg(nodes + 2 * cur + 2), hi1 = __ldg(nodes + 2 * cur + 3);
+            float tn0, tn1;
+            bool h0 = slab(lo0, hi0, f, tminf, tmaxf, tn0);
+            bool h1 = slab(lo1, hi1, f, tminf, tmaxf, tn1);
+            if (COUNT) cnt->nodes += 2;
+            const uint32_t c0 = __float_as_uint(hi0.w), c1 = __float_as_uint(hi1.w);
+            if (h0 && c0) { leaf_first0 = __float_as_uint(lo0.w); leaf_cnt0 = c0 & 0x7fffffffu; h0 = false; }
+            if (h1 && c1) { leaf_first1 = __float_as_uint(lo1.w); leaf_cnt1 = c1 & 0x7fffffffu; h1 = false; }
+            if (h0 && h1) {
+                const uint32_t n0 = __float_as_uint(lo0.w), n1 = __float_as_uint(lo1.w);
+                const bool first0 = tn0 <= tn1;
+                cur = first0 ? n0 : n1;
+                if (sp < RT_STACK) stack[sp++] = first0 ? n1 : n0;
+            } else if (h0) {
+                cur = __float_as_uint(lo0.w);
+            } else if (h1) {
+                cur = __float_as_uint(lo1.w);
+            } else {
+                cur = sp ? stack[--sp] : DONE;
             }
-            h1 = false;
         }
-        if (h0 && h1) {
-            const uint32_t n0 = __float_as_uint(lo0.w), n1 = __float_as_uint(lo1.w);
-            const bool first0 = tn0 <= tn1;
-            cur = first0 ? n0 : n1;
-            if (sp < RT_STACK) stack[sp++] = first0 ? n1 : n0;
-        } else if (h0) {
-            cur = __float_as_uint(lo0.w);
-        } else if (h1) {
-            cur = __float_as_uint(lo1.w);
-        } else {
-            if (sp == 0) return;
-            cur = stack[--sp];
+        for (int k = 0; k < 2; ++k) { // runtime loop: one copy of the primitive code
+            const uint32_t lc = k ? leaf_cnt1 : leaf_cnt0, lf = k ? leaf_first1 : leaf_first0;
+            if (lc & 0xffffffu) {
+                if (COUNT) cnt->prims += lc & 0xffffffu;
+                leaf_test(S, r, pre, t_min, best, lc >> 24, lf, lc & 0xffffffu, inst_idx);
+            }
         }
+        tmaxf = f32_up(best.t);
     }
 }
 
@@ -353,14 +358,9 @@ template <bool COUNT>
 RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, const Ray& world_ray, double t_min, BestHit& best, TraceCounters* cnt) {
     for (uint32_t i = i0; i < i1; ++i) {
         const Instance* ip = &S.instances[i];
-        const uint32_t len = __ldg(&ip->chain_len);
-        if (len == 0) {
-            trace_instance<COUNT>(S, i, world_ray, t_min, best, cnt);
-        } else {
-            Ray r = world_ray;
-            xform_ray(S.ops, __ldg(&ip->chain_off), len, r);
-            trace_instance<COUNT>(S, i, r, t_min, best, cnt);
-        }
+        Ray r = world_ray;
+        xform_ray(S.ops, __ldg(&ip->chain_off), __ldg(&ip->chain_len), r);
+        trace_instance<COUNT>(S, i, r, t_min, best, cnt);
     }
 }
 
@@ -464,12 +464,14 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
     const Medium md = S.media[mi];
     Ray r = world_ray;
     xform_ray(S.ops, md.chain_off, md.chain_len, r);
-    BestHit b1; b1.t = RT_INF; b1.prim_id = -1; b1.type = 0; b1.idx = 0; b1.side = 0; b1.inst = 0;
+    BestHit b1;
+    best_init(b1, RT_INF);
     trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, -RT_INF, b1, cnt);
-    if (b1.prim_id < 0) return;
-    BestHit b2; b2.t = RT_INF; b2.prim_id = -1; b2.type = 0; b2.idx = 0; b2.side = 0; b2.inst = 0;
+    if (b1.type == RT_NONE) return;
+    BestHit b2;
+    best_init(b2, RT_INF);
     trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, b1.t + 0.0001, b2, cnt);
-    if (b2.prim_id < 0) return;
+    if (b2.type == RT_NONE) return;
     double t1 = fmax(b1.t, t_min);
     const double t2 = fmin(b2.t, closest);
     if (t1 >= t2) return;
@@ -480,7 +482,6 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
     if (hit_distance > distance_inside_boundary) return;
     const double t = t1 + hit_distance / ray_length;
     if (!(t <= closest)) return;
-    if (t == closest && (int32_t)md.prim_id < winner) return;
     closest = t;
     winner = (int32_t)mi;
     // p = r.at(t) in the medium's space, brought back out through the medium's own chain
@@ -495,24 +496,27 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
 
 // world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
 // surface (order independent because medium draws are keyed).
-template <bool COUNT, bool WANT_UV>
+template <bool COUNT, bool WANT_UV, bool MEDIA>
 RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double t_max, bool media, uint64_t seed, uint64_t path_id, uint32_t segment,
                       HitRec& h, TraceCounters* cnt) {
-    BestHit best; best.t = t_max; best.prim_id = -1; best.type = 0; best.idx = 0; best.side = 0; best.inst = 0;
+    BestHit best;
+    best_init(best, t_max);
     trace_instances<COUNT>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
-    double closest = best.t;
-    int32_t mwin = -1;
-    D3 mp = mk3(0, 0, 0);
-    if (media) {
-        for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT>(S, mi, ray, t_min, closest, mwin, mp, seed, path_id, segment, cnt);
+    if (MEDIA) {
+        double closest = best.t;
+        int32_t mwin = -1;
+        D3 mp = mk3(0, 0, 0);
+        if (media) {
+            for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT>(S, mi, ray, t_min, closest, mwin, mp, seed, path_id, segment, cnt);
+        }
+        if (mwin >= 0) {
+            const Medium md = S.media[mwin];
+            h.p = mp; h.n = mk3(0, 0, 0); h.t = closest; h.u = 0.0; h.v = 0.0; h.front = true; // hit.rs:975-984
+            h.mat = md.mat_id; h.prim_id = md.prim_id;
+            return true;
+        }
     }
-    if (mwin >= 0) {
-        const Medium md = S.media[mwin];
-        h.p = mp; h.n = mk3(0, 0, 0); h.t = closest; h.u = 0.0; h.v = 0.0; h.front = true; // hit.rs:975-984
-        h.mat = md.mat_id; h.prim_id = md.prim_id;
-        return true;
-    }
-    if (best.prim_id < 0) return false;
+    if (best.type == RT_NONE) return false;
     h = finalize_hit<WANT_UV>(S, ray, best);
     return true;
 }

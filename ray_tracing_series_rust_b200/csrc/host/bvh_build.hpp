@@ -55,7 +55,13 @@ public:
         if (nodes_.size() & 1u) nodes_.push_back(BvhNode32{}); // keep sibling pairs 64 B aligned
         res.root = (uint32_t)nodes_.size();
         nodes_.push_back(BvhNode32{});
-        nodes_.push_back(BvhNode32{}); // pad so that the first pair is at an even index
+        {   // the root's sibling: an empty leaf with an inverted box (never hit, nothing to test)
+            BvhNode32 dummy{};
+            for (int a = 0; a < 3; ++a) { dummy.min[a] = 3.0e38f; dummy.max[a] = -3.0e38f; }
+            dummy.first = 0;
+            dummy.count = RT_LEAF_FLAG;
+            nodes_.push_back(dummy);
+        }
         struct Work { uint32_t node, lo, hi; int depth; };
         std::vector<Work> stack;
         stack.push_back({res.root, 0u, (uint32_t)prims.size(), 1});
@@ -160,7 +166,7 @@ public:
             if (make_leaf) {
                 const uint32_t type = prims[w.lo].type;
                 nd.first = type_cursor[type];
-                nd.count = (type << 24) | n;
+                nd.count = RT_LEAF_FLAG | (type << 24) | n;
                 type_cursor[type] += n;
                 for (uint32_t i = w.lo; i < w.hi; ++i) res.leaf_order.push_back(prims[i].src);
                 continue;

@@ -100,7 +100,8 @@ struct rt_scene {
     double domain_radius = 0.0;
     DeviceBuffers dev;
     RenderTuning tuning;
-    ~rt_scene() { dev.release(); }
+    Workspace* workspace = nullptr;
+    ~rt_scene() { dev.release(); free_workspace(workspace); }
 };
 
 #define CHECK_SCENE(s) \
@@ -394,6 +395,8 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF) {
     HF.pad = bo.pad;
     const char* env_leaf = std::getenv("RTB200_MAX_LEAF");
     if (env_leaf) bo.max_leaf = std::max(1, std::atoi(env_leaf));
+    const char* env_cp = std::getenv("RTB200_COST_PRIM");
+    if (env_cp) bo.cost_prim = std::atof(env_cp);
 
     std::vector<std::pair<uint32_t, uint32_t>> world_range(F.worlds.size());
     for (size_t wi = 0; wi < F.worlds.size(); ++wi) {
@@ -574,6 +577,10 @@ rt_scene* rt_scene_create(void) {
     rt_scene* s = new rt_scene();
     const char* e = std::getenv("RTB200_WAVE_SLOTS");
     if (e) s->tuning.wave_slots = (uint32_t)std::max(128L, std::atol(e));
+    if ((e = std::getenv("RTB200_EXTEND_OCC"))) s->tuning.extend_occ = std::atoi(e);
+    if ((e = std::getenv("RTB200_EXTEND_WAVES"))) s->tuning.extend_waves = std::atoi(e);
+    if ((e = std::getenv("RTB200_MODE"))) s->tuning.mode = std::atoi(e);
+    if ((e = std::getenv("RTB200_MEGA_OCC"))) s->tuning.mega_occ = std::atoi(e);
     return s;
 }
 void rt_scene_destroy(rt_scene* s) { delete s; }
@@ -870,7 +877,7 @@ int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg, int64_t* d_ac
     RenderTuning tune = s->tuning;
     tune.timed_extend = (cfg->flags & 1) ? 1 : 0;
     tune.count_events = (cfg->flags & 2) ? 1 : 0;
-    const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats);
+    const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats, &s->workspace);
     if (e != cudaSuccess) return fail_cuda(e, "render");
     if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return RT_OK;
@@ -996,7 +1003,7 @@ RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]) {
                 if (nd.min[a] < it.mn[a] || nd.max[a] > it.mx[a] || !(nd.min[a] <= nd.max[a])) ++violations;
             if (nd.count) {
                 ++leaves;
-                const uint32_t type = nd.count >> 24, n = nd.count & 0xffffffu;
+                const uint32_t type = (nd.count >> 24) & 0x7fu, n = nd.count & 0xffffffu;
                 for (uint32_t i = nd.first; i < nd.first + n; ++i) {
                     if (type >= PRIM_TYPE_COUNT || i >= counts[type]) { ++violations; continue; }
                     if (seen[type][i]++) ++violations;

@@ -20,6 +20,7 @@
 
 namespace rtb {
 
+#define RT_LEAF_FLAG 0x80000000u
 #define RT_BVH_MAX_DEPTH 60 // traversal stack is 64 entries (rt_device.cuh RT_STACK)
 
 enum PrimType : uint32_t {
@@ -31,13 +32,13 @@ enum TexType : uint32_t { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMA
 enum XformType : uint32_t { XF_TRANSLATE = 0, XF_ROTATE_Y = 1 };
 
 // 32-byte BVH node.  Interior: count == 0, first = index of the left child (right = first + 1).
-// Leaf: count > 0 primitives of one type, `first` = index into that type's buffer,
-// type stored in the top byte of count.
+// Leaf: count = 0x80000000 | type << 24 | n: n primitives of one type, `first` = index into that
+// type's buffer.  An instance root is the first node of a pair whose second node is an empty leaf.
 struct alignas(32) BvhNode32 {
     float min[3];
     uint32_t first;
     float max[3];
-    uint32_t count; // (type << 24) | n
+    uint32_t count; // 0 = interior, else RT_LEAF_FLAG | (type << 24) | n
 };
 
 struct alignas(16) DSphere { double cx, cy, cz, r; };                                  // hit.rs:180-184

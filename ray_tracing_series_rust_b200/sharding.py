@@ -1,0 +1,29 @@
+"""Multi-GPU sharding of one render: every (pixel, sample) is independent
+(src/world.rs:1208-1216 has no cross-iteration state but the per-pixel sum), so rank r of R renders the
+sample range [begin, end) of every pixel and the int64 fixed-point accumulators are summed with ONE
+reduce.  Philox streams are keyed by the global sample index, integer addition is associative: the
+reduced image does not depend on R.
+
+The reference's analogue is the row-band fan-out + mpsc gather of render_scene (world.rs:1198-1240).
+"""
+from __future__ import annotations
+
+
+def sample_range(spp: int, rank: int, world: int, scaling: str = "strong"):
+    """-> (spp_total, begin, end).  strong: the workload's spp is split across ranks (remainder spread
+    over the first ranks); weak: every rank renders `spp` samples of an image with spp * world samples."""
+    if world < 1 or not (0 <= rank < world) or spp < 1:
+        raise ValueError("bad shard request")
+    if scaling == "weak":
+        return spp * world, spp * rank, spp * (rank + 1)
+    if scaling != "strong":
+        raise ValueError("scaling must be 'weak' or 'strong'")
+    return spp, (spp * rank) // world, (spp * (rank + 1)) // world
+
+
+def reduce_accumulators(accum, dst: int = 0):
+    """Sum the per-rank int64 accumulators onto `dst` (NCCL on GPU tensors, gloo on CPU tensors)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
+    return accum

@@ -212,6 +212,22 @@ def test_determinism_wave_size_and_sharding(orc):
     assert not np.array_equal(a1, a4)
 
 
+@pytest.mark.parametrize("scene_id", [13, 5, 6])
+def test_fused_mode_is_bit_identical_to_wavefront(scene_id, monkeypatch):
+    # RT_MODE_FUSED (persistent k_mega) and the wavefront share device functions, Philox streams and the
+    # integer accumulator: same image bit for bit, same segment count
+    res = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("RTB200_MODE", mode)
+        g = rtb.new_scene()
+        g.world_build(scene_id, 3)
+        g.commit()
+        _, acc, st = g.render(capi.make_config(72, 1.0 if scene_id != 13 else 1.5, 6, 50, seed=4), want_accum=True)
+        res.append((acc, st["segments"], st["kernel_launches"]))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+    assert res[1][2] == 2 and res[0][2] > 2
+
+
 def test_compat_threads_black_rows_and_ppm(orc, tmp_path):
     # world.rs:1198-1202: rows >= threads * (H / threads) are never rendered (top rows of the PPM)
     g, o = pu.build_pair(orc, 13)

@@ -1,0 +1,83 @@
+"""N>1 host path on CPU: two gloo ranks render disjoint sample ranges (with the oracle standing in for
+the GPU renderer — same C-ABI, same rt_render_config sample_begin/sample_end contract), the int64
+accumulators are summed with one reduce, and rank 0's result equals the single-process render."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, scaling, out_path):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from ray_tracing_series_rust_b200 import capi, sharding
+    s = oracle.new_scene()
+    s.world_build(5, 0xB002)
+    s.commit()
+    spp = 6
+    total, b, e = sharding.sample_range(spp, rank, world, scaling)
+    cfg = capi.make_config(40, 1.0, total, 50, seed=3, sample_begin=b, sample_end=e, threads=2)
+    _, acc, st = s.render(cfg, want_accum=True)
+    t = torch.from_numpy(acc)
+    paths = torch.tensor([st["paths"]], dtype=torch.int64)
+    sharding.reduce_accumulators(t, dst=0)
+    dist.reduce(paths, dst=0, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        np.save(out_path, t.numpy())
+        np.save(out_path + ".paths.npy", paths.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scaling", ["strong", "weak"])
+def test_two_rank_sample_sharding_matches_single_process(orc, tmp_path, scaling):
+    from ray_tracing_series_rust_b200 import capi
+    world = 2
+    out = str(tmp_path / f"acc_{scaling}.npy")
+    mp.spawn(_worker, args=(world, _free_port(), scaling, out), nprocs=world, join=True)
+    got = np.load(out)
+    paths = int(np.load(out + ".paths.npy")[0])
+    total = 6 * world if scaling == "weak" else 6
+    s = orc.new_scene()
+    s.world_build(5, 0xB002)
+    s.commit()
+    _, ref, st = s.render(capi.make_config(40, 1.0, total, 50, seed=3, threads=2), want_accum=True)
+    assert paths == st["paths"] == 40 * 40 * total
+    # the oracle rounds each shard's f64 sum to fixed point once, so shards differ from the whole by at most one unit per rank
+    assert np.abs(got - ref).max() <= world
+
+
+def test_sample_range_partition():
+    from ray_tracing_series_rust_b200 import sharding
+    for spp in (1, 7, 500, 10000):
+        for world in (1, 2, 3, 4, 8):
+            cover = []
+            for r in range(world):
+                tot, b, e = sharding.sample_range(spp, r, world, "strong")
+                assert tot == spp and 0 <= b <= e <= spp
+                cover += list(range(b, e))
+            assert cover == list(range(spp))
+            tot, b, e = sharding.sample_range(spp, world - 1, world, "weak")
+            assert (tot, e - b, e) == (spp * world, spp, spp * world)
+    with pytest.raises(ValueError):
+        sharding.sample_range(10, 2, 2)

@@ -36,3 +36,37 @@ if __name__ == "__main__":
     elif what == "slots":
         for s in (1 << 16, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22):
             run(13, 800, 1.5, 100, slots=s, label="slots")
+    elif what == "modes":
+        run(13, 800, 1.5, 50, label="warm")
+        for mode, occ in ((0, 0), (1, 4), (1, 3), (1, 2)):
+            os.environ["RTB200_MODE"] = str(mode); os.environ["RTB200_MEGA_OCC"] = str(occ); os.environ["RTB200_EXTEND_OCC"] = "5"
+            tag = f"mode{mode} occ{occ}"
+            run(13, 800, 1.5, 500, label=f"book1 {tag}")
+            run(99, 800, 1.5, 200, label=f"book1b {tag}")
+            run(5, 600, 1.0, 200, label=f"smoke {tag}")
+            run(6, 1000, 1.0, 40, label=f"book2 {tag}")
+            run(14, 1000, 1.0, 10, param=660, label=f"mesh871k {tag}")
+    elif what == "sah":
+        run(13, 800, 1.5, 50, label="warm")
+        os.environ["RTB200_EXTEND_OCC"] = "5"
+        for leaf, cp in ((4, 2), (1, 2), (2, 2), (2, 4), (4, 4), (4, 8), (8, 1), (8, 2), (3, 3)):
+            os.environ["RTB200_MAX_LEAF"] = str(leaf); os.environ["RTB200_COST_PRIM"] = str(cp)
+            tag = f"leaf{leaf} cp{cp}"
+            run(13, 800, 1.5, 100, flags=2, label=f"book1 {tag} COUNT")
+            run(13, 800, 1.5, 200, label=f"book1 {tag}")
+            run(6, 1000, 1.0, 20, label=f"book2 {tag}")
+            run(14, 1000, 1.0, 8, param=660, label=f"mesh871k {tag}")
+    elif what == "sweep":
+        run(13, 800, 1.5, 50, label="warm")
+        for occ in (4, 5, 6):
+            for waves in (1, 4, 16):
+                os.environ["RTB200_EXTEND_OCC"] = str(occ); os.environ["RTB200_EXTEND_WAVES"] = str(waves)
+                run(13, 800, 1.5, 100, label=f"book1 occ{occ} w{waves}")
+        os.environ["RTB200_EXTEND_WAVES"] = "4"
+        for occ in (4, 5, 6):
+            os.environ["RTB200_EXTEND_OCC"] = str(occ)
+            for s in (1 << 18, 1 << 19, 1 << 20, 1 << 21):
+                run(13, 800, 1.5, 100, slots=s, label=f"book1 occ{occ} slots{s}")
+            run(5, 600, 1.0, 50, label=f"smoke occ{occ}")
+            run(6, 1000, 1.0, 10, label=f"book2 occ{occ}")
+            run(14, 1000, 1.0, 5, param=200, label=f"mesh80k occ{occ}")
