@@ -20,8 +20,8 @@
 #include <cstdio>
 #include <vector>
 
-#ifndef RT_EXTEND_MIN_BLOCKS
-#define RT_EXTEND_MIN_BLOCKS 4
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 3
 #endif
 
 #include "rt_device.cuh"
@@ -29,16 +29,17 @@
 namespace rtb {
 
 // ------------------------------------------------------------------ path state (SoA, one entry per slot)
+// Four 32-byte chunks per slot, each in its own array: every access moves whole 32 B sectors with two
+// 128-bit loads/stores, also when the slot indices come scattered out of a material queue.
+struct alignas(32) SlotA { double ox, oy, oz, time; };                                   // ray origin (after a hit: HitRecord.p) + time
+struct alignas(32) SlotB { double dx, dy, dz; uint32_t pad0, pad1; };                     // ray direction; for uv-reading materials (dx,dy) := (u,v) after the hit
+struct alignas(32) SlotC { double nx, ny, nz; uint32_t hmat, pad; };                      // HitRecord.normal, material id | front_face << 31
+struct alignas(32) SlotD { float tr, tg, tb; uint32_t draw; uint64_t path_id; uint32_t segment, pixel; }; // throughput, Philox stream + counter, ray_color iteration, pixel
 struct PathState {
-    double *ox, *oy, *oz, *dx, *dy, *dz, *time; // current ray; after a hit (ox,oy,oz) holds HitRecord.p
-    double *nx, *ny, *nz;                       // HitRecord.normal
-    float *hu, *hv;                             // HitRecord.u, v
-    uint32_t* hmat;                             // material id | front_face << 31
-    float *tr, *tg, *tb;                        // `product` of ray_color (throughput)
-    uint32_t* pixel;                            // j * W + i
-    uint64_t* path_id;                          // (j*W + i) * spp_total + sample: the Philox stream id
-    uint32_t* draw;                             // Philox draw counter
-    uint32_t* segment;                          // ray_color loop iteration
+    SlotA* A;
+    SlotB* B;
+    SlotC* C;
+    SlotD* D;
     uint8_t* alive;
 };
 
@@ -96,13 +97,24 @@ RT_DEV void accumulate(int64_t* __restrict__ accum, uint32_t pixel, float r, flo
 __global__ void k_init(PathState P, Queues Q, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Q.q[Q_MISS][i] = i;
-        P.tr[i] = 0.f; P.tg[i] = 0.f; P.tb[i] = 0.f;
-        P.pixel[i] = 0;
+        SlotD d;
+        d.tr = 0.f; d.tg = 0.f; d.tb = 0.f; d.draw = 0; d.path_id = 0; d.segment = 0; d.pixel = 0;
+        P.D[i] = d;
         P.alive[i] = 1;
     }
     if (blockIdx.x == 0 && threadIdx.x < 16) Q.counts[threadIdx.x] = (threadIdx.x == Q_MISS) ? n : 0u;
     if (blockIdx.x == 0 && threadIdx.x == 0) { *Q.dead = 0; *Q.next_path = 0ull; }
     if (blockIdx.x == 0 && threadIdx.x < 9) Q.stats[threadIdx.x] = 0ull;
+}
+
+// L -> (sample, pixel) without 64-bit integer division: quotient estimate in f64 (exact for L < 2^53) + one correction step
+RT_DEV void split_path_index(unsigned long long L, uint32_t npix, uint32_t& s_local, uint32_t& pix) {
+    uint32_t q = (uint32_t)__double2uint_rz(__ull2double_rz(L) / (double)npix);
+    long long r = (long long)L - (long long)q * (long long)npix;
+    if (r < 0) { --q; r += npix; }
+    else if (r >= (long long)npix) { ++q; r -= npix; }
+    s_local = q;
+    pix = (uint32_t)r;
 }
 
 // New camera path into `slot` (pixel jitter world.rs:1212-1213 + Camera::get_ray), or retire the slot.
@@ -119,23 +131,21 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
         return;
     }
     // sample-major order: consecutive path indices are neighbouring pixels of one sample => coherent primary rays
-    const uint32_t s_local = (uint32_t)(L / J.npix_rendered);
-    const uint32_t pix = (uint32_t)(L % J.npix_rendered);
-    const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix % (uint32_t)J.W);
+    uint32_t s_local, pix;
+    split_path_index(L, J.npix_rendered, s_local, pix);
+    const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix - (uint32_t)j * (uint32_t)J.W);
     const uint64_t path_id = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
     PathRng g;
     g.init(J.seed, path_id, 0);
     const double u = ((double)ii + g.gen()) / (double)(J.W - 1); // world.rs:1212
     const double v = ((double)j + g.gen()) / (double)(J.H - 1);  // world.rs:1213
     const Ray r = camera_get_ray(S.cam, u, v, g);
-    P.ox[slot] = r.o.x; P.oy[slot] = r.o.y; P.oz[slot] = r.o.z;
-    P.dx[slot] = r.d.x; P.dy[slot] = r.d.y; P.dz[slot] = r.d.z;
-    P.time[slot] = r.time;
-    P.tr[slot] = 1.f; P.tg[slot] = 1.f; P.tb[slot] = 1.f;
-    P.pixel[slot] = pix;
-    P.path_id[slot] = path_id;
-    P.draw[slot] = g.draw;
-    P.segment[slot] = 0;
+    SlotA a; a.ox = r.o.x; a.oy = r.o.y; a.oz = r.o.z; a.time = r.time;
+    SlotB b; b.dx = r.d.x; b.dy = r.d.y; b.dz = r.d.z; b.pad0 = 0; b.pad1 = 0;
+    SlotD d; d.tr = 1.f; d.tg = 1.f; d.tb = 1.f; d.draw = g.draw; d.path_id = path_id; d.segment = 0; d.pixel = pix;
+    P.A[slot] = a;
+    P.B[slot] = b;
+    P.D[slot] = d;
 }
 
 // ------------------------------------------------------------------ k_extend: world.hit(ray, 0.001, inf) for every live slot
@@ -146,23 +156,30 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
     TraceCounters tc; tc.nodes = 0; tc.prims = 0;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < J.n_slots; slot += gridDim.x * blockDim.x) {
         if (!P.alive[slot]) continue;
+        const SlotA a = P.A[slot];
+        const SlotB b = P.B[slot];
         Ray r;
-        r.o = mk3(P.ox[slot], P.oy[slot], P.oz[slot]);
-        r.d = mk3(P.dx[slot], P.dy[slot], P.dz[slot]);
-        r.time = P.time[slot];
+        r.o = mk3(a.ox, a.oy, a.oz);
+        r.d = mk3(b.dx, b.dy, b.dz);
+        r.time = a.time;
         uint64_t path_id = 0;
         uint32_t segment = 0;
-        if (MEDIA) { path_id = P.path_id[slot]; segment = P.segment[slot]; }
+        if (MEDIA) { const SlotD d = P.D[slot]; path_id = d.path_id; segment = d.segment; }
         HitRec h;
         const bool hit = world_hit<COUNT, false, MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
         ++my_segments;
         uint32_t qi = Q_MISS;
         if (hit) {
-            P.ox[slot] = h.p.x; P.oy[slot] = h.p.y; P.oz[slot] = h.p.z;
-            P.nx[slot] = h.n.x; P.ny[slot] = h.n.y; P.nz[slot] = h.n.z;
-            P.hu[slot] = (float)h.u; P.hv[slot] = (float)h.v;
-            P.hmat[slot] = h.mat | (h.front ? 0x80000000u : 0u);
-            qi = __ldg(&S.materials[h.mat].type);
+            SlotA na; na.ox = h.p.x; na.oy = h.p.y; na.oz = h.p.z; na.time = a.time;
+            SlotC nc; nc.nx = h.n.x; nc.ny = h.n.y; nc.nz = h.n.z; nc.hmat = h.mat | (h.front ? 0x80000000u : 0u); nc.pad = 0;
+            P.A[slot] = na;
+            P.C[slot] = nc;
+            const DMaterial* mp = &S.materials[h.mat];
+            qi = __ldg(&mp->type);
+            if (__ldg(&mp->flags) & 1u) { // the texture chain reads (u,v): such materials never read the incoming direction
+                double2 uv = make_double2(h.u, h.v);
+                *reinterpret_cast<double2*>(&P.B[slot]) = uv;
+            }
         }
         Q.q[qi][agg_reserve(counts, qi)] = slot;
     }
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
 // warp only ever holds entries of ONE queue (material-coherent warps without one launch per material).
 // Paths that end here (miss, light, absorbed, depth exhausted) add their radiance to the pixel and the
 // slot is refilled in place with the next camera path.
-__global__ void __launch_bounds__(256) k_shade_all(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q,
+__global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q,
                                                    int64_t* __restrict__ accum, int parity) {
     const uint32_t* counts = Q.counts + 8 * parity;
     uint32_t start[Q_COUNT + 1];
@@ -202,42 +219,56 @@ __global__ void __launch_bounds__(256) k_shade_all(const __grid_constant__ Devic
         const uint32_t i = f - start[q];
         if (i >= counts[q]) continue; // padding lane
         const uint32_t slot = Q.q[q][i];
+        SlotD sd = P.D[slot];
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
         if (q == Q_MISS) {
             // world.rs:86-89: output += product * background
-            contrib = mkf3(P.tr[slot] * S.background[0], P.tg[slot] * S.background[1], P.tb[slot] * S.background[2]);
+            contrib = mkf3(sd.tr * S.background[0], sd.tg * S.background[1], sd.tb * S.background[2]);
         } else {
-            const uint32_t hm = P.hmat[slot];
+            const SlotA sa = P.A[slot];
+            const SlotC sc = P.C[slot];
+            const uint32_t hm = sc.hmat;
             const DMaterial m = S.materials[hm & 0x7fffffffu];
-            const D3 p = mk3(P.ox[slot], P.oy[slot], P.oz[slot]);
+            const D3 p = mk3(sa.ox, sa.oy, sa.oz);
+            double hu = 0.0, hv = 0.0;
+            D3 d_in = mk3(0, 0, 0);
+            if (q == MAT_METAL || q == MAT_DIELECTRIC) {
+                const SlotB sb = P.B[slot];
+                d_in = mk3(sb.dx, sb.dy, sb.dz);
+            } else if (m.flags & 1u) {
+                const double2 uv = *reinterpret_cast<const double2*>(&P.B[slot]);
+                hu = uv.x; hv = uv.y;
+            }
             if (q == MAT_LIGHT) {
-                const F3 e = tex_value(S, m.tex, (double)P.hu[slot], (double)P.hv[slot], p); // hit.rs:1146-1151, world.rs:78-84
-                contrib = mkf3(P.tr[slot] * e.x, P.tg[slot] * e.y, P.tb[slot] * e.z);
+                const F3 e = tex_value(S, m.tex, hu, hv, p); // hit.rs:1146-1151, world.rs:78-84
+                contrib = mkf3(sd.tr * e.x, sd.tg * e.y, sd.tb * e.z);
             } else {
                 PathRng g;
-                g.init(J.seed, P.path_id[slot], P.draw[slot]);
-                const D3 n3 = mk3(P.nx[slot], P.ny[slot], P.nz[slot]);
+                g.init(J.seed, sd.path_id, sd.draw);
+                const D3 n3 = mk3(sc.nx, sc.ny, sc.nz);
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
                 bool scattered;
-                if (q == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, p, n3, (double)P.hu[slot], (double)P.hv[slot], g, dir, att);
-                else if (q == MAT_METAL) scattered = scatter_metal(m, mk3(P.dx[slot], P.dy[slot], P.dz[slot]), n3, g, dir, att);
-                else if (q == MAT_DIELECTRIC) scattered = scatter_dielectric(m, mk3(P.dx[slot], P.dy[slot], P.dz[slot]), n3, (hm >> 31) != 0, g, dir, att);
-                else scattered = scatter_isotropic(S, m, p, (double)P.hu[slot], (double)P.hv[slot], g, dir, att);
-                const uint32_t seg = P.segment[slot] + 1;
+                if (q == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, p, n3, hu, hv, g, dir, att);
+                else if (q == MAT_METAL) scattered = scatter_metal(m, d_in, n3, g, dir, att);
+                else if (q == MAT_DIELECTRIC) scattered = scatter_dielectric(m, d_in, n3, (hm >> 31) != 0, g, dir, att);
+                else scattered = scatter_isotropic(S, m, p, hu, hv, g, dir, att);
+                const uint32_t seg = sd.segment + 1;
                 if (scattered && (int32_t)seg < J.max_depth) { // world.rs:64-67: at most max_depth hit queries per path
-                    P.tr[slot] *= att.x; P.tg[slot] *= att.y; P.tb[slot] *= att.z; // world.rs:75
-                    P.dx[slot] = dir.x; P.dy[slot] = dir.y; P.dz[slot] = dir.z;     // the origin already is rec.p
-                    P.draw[slot] = g.draw;
-                    P.segment[slot] = seg;
+                    sd.tr *= att.x; sd.tg *= att.y; sd.tb *= att.z; // world.rs:75
+                    sd.draw = g.draw;
+                    sd.segment = seg;
+                    SlotB nb; nb.dx = dir.x; nb.dy = dir.y; nb.dz = dir.z; nb.pad0 = 0; nb.pad1 = 0; // the origin already is rec.p
+                    P.B[slot] = nb;
+                    P.D[slot] = sd;
                     ended = false;
                 }
                 // absorbed (Metal) or depth exhausted: the path keeps what it has (nothing: emitters do not scatter)
             }
         }
         if (ended) {
-            accumulate(accum, P.pixel[slot], contrib.x, contrib.y, contrib.z);
+            accumulate(accum, sd.pixel, contrib.x, contrib.y, contrib.z);
             regenerate(S, J, P, Q, slot);
         }
     }
@@ -281,9 +312,9 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                 if (L >= J.total_paths) {
                     exhausted = true;
                 } else {
-                    const uint32_t s_local = (uint32_t)(L / J.npix_rendered);
-                    pixel = (uint32_t)(L % J.npix_rendered);
-                    const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel % (uint32_t)J.W);
+                    uint32_t s_local;
+                    split_path_index(L, J.npix_rendered, s_local, pixel);
+                    const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
                     path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
                     PathRng g;
                     g.init(J.seed, path_id, 0);
@@ -484,17 +515,12 @@ static cudaError_t ensure_workspace(Workspace*& w, uint32_t N) {
     free_workspace(w);
     w = new Workspace();
     cudaError_t err = cudaSuccess;
-    const size_t per_slot = 7 * 8 + 3 * 8 + 2 * 4 + 4 + 3 * 4 + 4 + 8 + 4 + 4 + 1 + Q_COUNT * 4;
+    const size_t per_slot = 4 * 32 + 1 + Q_COUNT * 4;
     w->cap = (size_t)N * per_slot + 64 * 256 + 4096;
     if ((err = cudaMalloc(&w->base, w->cap)) != cudaSuccess) return err;
     PathState& P = w->P;
     Queues& Q = w->Q;
-    P.ox = w->take<double>(N); P.oy = w->take<double>(N); P.oz = w->take<double>(N);
-    P.dx = w->take<double>(N); P.dy = w->take<double>(N); P.dz = w->take<double>(N); P.time = w->take<double>(N);
-    P.nx = w->take<double>(N); P.ny = w->take<double>(N); P.nz = w->take<double>(N);
-    P.hu = w->take<float>(N); P.hv = w->take<float>(N); P.hmat = w->take<uint32_t>(N);
-    P.tr = w->take<float>(N); P.tg = w->take<float>(N); P.tb = w->take<float>(N);
-    P.pixel = w->take<uint32_t>(N); P.path_id = w->take<uint64_t>(N); P.draw = w->take<uint32_t>(N); P.segment = w->take<uint32_t>(N);
+    P.A = w->take<SlotA>(N); P.B = w->take<SlotB>(N); P.C = w->take<SlotC>(N); P.D = w->take<SlotD>(N);
     P.alive = w->take<uint8_t>(N);
     for (int q = 0; q < Q_COUNT; ++q) Q.q[q] = w->take<uint32_t>(N);
     Q.counts = w->take<uint32_t>(16);
@@ -548,8 +574,9 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         PathState& P = w->P;
         Queues& Q = w->Q;
         const int qblocks = (int)std::min<uint32_t>((N + 255) / 256, 148 * 8);
-        const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, tune.extend_occ) * (uint32_t)std::max(1, tune.extend_waves));
         const bool media = scene.n_media != 0;
+        const int ext_occ = tune.extend_occ > 0 ? tune.extend_occ : (media ? 4 : 5);
+        const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, ext_occ) * (uint32_t)std::max(1, tune.extend_waves));
         CK(cudaEventRecord(w->ev_begin, stream));
         if (tune.mode == RT_MODE_FUSED) {
             k_mega_init<<<1, 32, 0, stream>>>(Q);
@@ -591,8 +618,8 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                     CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
                     CK(cudaEventRecord(ea, stream));
                 }
-                if (media) { if (tune.count_events) launch_extend<true, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(tune.extend_occ, eblocks, stream, scene, J, P, Q, parity); }
-                else { if (tune.count_events) launch_extend<false, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<false, false>(tune.extend_occ, eblocks, stream, scene, J, P, Q, parity); }
+                if (media) { if (tune.count_events) launch_extend<true, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(ext_occ, eblocks, stream, scene, J, P, Q, parity); }
+                else { if (tune.count_events) launch_extend<false, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<false, false>(ext_occ, eblocks, stream, scene, J, P, Q, parity); }
                 if (tune.timed_extend) {
                     CK(cudaEventRecord(eb, stream));
                     ext_events.push_back(ea); ext_events.push_back(eb);

@@ -25,7 +25,7 @@ struct RenderTuning {
     uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
     int timed_extend = 0;           // 1: bracket every extend launch with CUDA events (for the roofline)
     int count_events = 0;           // 1: count BVH node visits / primitive tests on the device
-    int extend_occ = 4;             // k_extend variant: resident 128-thread blocks per SM (4 / 5 / 6)
+    int extend_occ = 0;             // k_extend variant: resident 128-thread blocks per SM (4 / 5 / 6); 0 = auto (5, or 4 with media)
     int extend_waves = 4;           // k_extend grid = 148 * extend_occ * extend_waves blocks (grid-stride over the slots)
 };
 

@@ -145,11 +145,14 @@ RT_DEV void consider(const DeviceScene& S, BestHit& best, double t, uint32_t typ
 // a = d.d and 1/a depend only on the ray: computed once per ray per instance (RayPre).
 struct RayPre {
     double a, inv_a;
+    D3 inv_d; // 1 / direction per axis, for the axis-aligned plane tests (rects, box sides)
 };
-RT_DEV RayPre make_raypre(const Ray& r) {
+RT_DEV RayPre make_raypre(const Ray& r, bool planar) {
     RayPre p;
     p.a = length_squared(r.d);
     p.inv_a = 1.0 / p.a;
+    p.inv_d = mk3(0, 0, 0);
+    if (planar) p.inv_d = mk3(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
     return p;
 }
 RT_DEV double sphere_root(const Ray& r, const RayPre& pre, D3 c, double radius, double t_min, double t_max) {
@@ -177,34 +180,40 @@ RT_DEV D3 gravity_center(const DeviceScene& S, const DGravity& g, double time) {
     i = i < 0 ? 0 : (i >= g.n ? g.n - 1 : i); // window uploaded for the camera shutter; clamped
     return mk3(g.x, __ldg(&S.gravity_table[g.table_off + (int32_t)i]), g.z);
 }
-// XyRect / XzRect / YzRect::hit (hit.rs:476-485, 541-550, 606-615): returns t or +inf
-RT_DEV double rect_t(const Ray& r, const DRect& q, double t_min, double t_max) {
+// XyRect / XzRect / YzRect::hit (hit.rs:476-485, 541-550, 606-615): returns t or +inf.
+// t = (k - o) / d is evaluated as (k - o) * (1/d) with the per-ray reciprocal (<= 1 ulp from the division).
+RT_DEV double rect_t(const Ray& r, const RayPre& pre, const DRect& q, double t_min, double t_max) {
     const int ax = q.axis;
     const int ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
-    const double t = (q.k - axis_of(r.o, ax)) / axis_of(r.d, ax);
+    const double t = (q.k - axis_of(r.o, ax)) * axis_of(pre.inv_d, ax);
     if (t < t_min || t > t_max) return RT_INF;
     const double x = axis_of(r.o, ia) + t * axis_of(r.d, ia);
     const double y = axis_of(r.o, ib) + t * axis_of(r.d, ib);
     if (x < q.a0 || x > q.a1 || y < q.b0 || y > q.b1) return RT_INF;
     return t;
 }
+// One side of a RectPrism (hit.rs:722-769): s = 0..5 -> +z(p1.z), -z(p0.z), +y, -y, +x, -x.  Returns t or +inf.
+RT_DEV double box_side_t(const Ray& r, const RayPre& pre, const DBox& b, int s) {
+    const int ax = s < 2 ? 2 : (s < 4 ? 1 : 0);
+    const int ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+    const double k = (s & 1) ? b.p0[ax] : b.p1[ax];
+    const double t = (k - axis_of(r.o, ax)) * axis_of(pre.inv_d, ax);
+    if (!(t < RT_INF) || !(t > -RT_INF)) return RT_INF;
+    const double x = axis_of(r.o, ia) + t * axis_of(r.d, ia);
+    const double y = axis_of(r.o, ib) + t * axis_of(r.d, ib);
+    if (x < b.p0[ia] || x > b.p1[ia] || y < b.p0[ib] || y > b.p1[ib]) return RT_INF;
+    return t;
+}
 // RectPrism = HittableList of six rects scanned in order with a shrinking closest_so_far
-// (hit.rs:722-769, 660-690): +z(p1.z), -z(p0.z), +y, -y, +x, -x.  Returns t and the winning side.
-RT_DEV double box_t(const Ray& r, const DBox& b, double t_min, double t_max, uint32_t& side_out) {
+// (hit.rs:660-690).  Returns t and the winning side (later side wins an exact tie).
+RT_DEV double box_t(const Ray& r, const RayPre& pre, const DBox& b, double t_min, double t_max, uint32_t& side_out) {
     double closest = t_max;
     bool any = false;
     uint32_t side = 0;
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
-        const int ax = s < 2 ? 2 : (s < 4 ? 1 : 0);
-        const int ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
-        const double k = (s & 1) ? b.p0[ax] : b.p1[ax];
-        const double t = (k - axis_of(r.o, ax)) / axis_of(r.d, ax);
+        const double t = box_side_t(r, pre, b, s);
         if (t < t_min || t > closest || !(t < RT_INF)) continue;
-        const double x = axis_of(r.o, ia) + t * axis_of(r.d, ia);
-        const double y = axis_of(r.o, ib) + t * axis_of(r.d, ib);
-        if (x < b.p0[ia] || x > b.p1[ia] || y < b.p0[ib] || y > b.p1[ib]) continue;
-        if (t != t) continue;
         closest = t; any = true; side = (uint32_t)s;
     }
     side_out = side;
@@ -279,11 +288,11 @@ RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, const RayPre& pre, dou
             consider(S, best, sphere_root(r, pre, c, rad, t_min, best.t), type, i, 0, inst);
         } else if (type == PRIM_RECT) {
             const DRect q = S.rects[i];
-            consider(S, best, rect_t(r, q, t_min, best.t), type, i, 0, inst);
+            consider(S, best, rect_t(r, pre, q, t_min, best.t), type, i, 0, inst);
         } else if (type == PRIM_BOX) {
             const DBox b = S.boxes[i];
             uint32_t side;
-            const double t = box_t(r, b, t_min, best.t, side);
+            const double t = box_t(r, pre, b, t_min, best.t, side);
             consider(S, best, t, type, i, side, inst);
         } else { // PRIM_TRI
             consider(S, best, tri_t(r, &S.tris[i], t_min, best.t), type, i, 0, inst);
@@ -300,7 +309,7 @@ RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, const RayPre& pre, dou
 template <bool COUNT>
 RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r, double t_min, BestHit& best, TraceCounters* cnt) {
     const RayF f = make_rayf(r);
-    const RayPre pre = make_raypre(r);
+    const RayPre pre = make_raypre(r, (S.flags & 1u) != 0);
     const float tminf = f32_down(t_min);
     float tmaxf = f32_up(best.t);
     const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
@@ -464,16 +473,51 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
     const Medium md = S.media[mi];
     Ray r = world_ray;
     xform_ray(S.ops, md.chain_off, md.chain_len, r);
-    BestHit b1;
-    best_init(b1, RT_INF);
-    trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, -RT_INF, b1, cnt);
-    if (b1.type == RT_NONE) return;
-    BestHit b2;
-    best_init(b2, RT_INF);
-    trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, b1.t + 0.0001, b2, cnt);
-    if (b2.type == RT_NONE) return;
-    double t1 = fmax(b1.t, t_min);
-    const double t2 = fmin(b2.t, closest);
+    // boundary.hit(r, -inf, +inf) then boundary.hit(r, rec1.t + 0.0001, +inf) (hit.rs:956-957)
+    double ta, tb;
+    if (md.fast_type != 0) {
+        // the boundary is a single sphere or a single box (optionally under Translate/RotateY): both
+        // crossings from one solve instead of two traversals
+        Ray rb = r;
+        xform_ray(S.ops, md.fast_chain_off, md.fast_chain_len, rb);
+        if (COUNT) cnt->prims += 2;
+        if (md.fast_type == 1) {
+            const DSphere sp = S.spheres[md.fast_idx];
+            const D3 oc = rb.o - mk3(sp.cx, sp.cy, sp.cz);
+            const double a = length_squared(rb.d), half_b = dot(oc, rb.d);
+            const double disc = half_b * half_b - a * (length_squared(oc) - sp.r * sp.r);
+            if (disc < 0.0) return;
+            const double sq = sqrt(disc), inv_a = 1.0 / a;
+            ta = (-half_b - sq) * inv_a;
+            tb = (-half_b + sq) * inv_a;
+            if (!(ta < RT_INF) || !(ta > -RT_INF)) return;
+            if (tb < ta + 0.0001 || !(tb < RT_INF)) return;
+        } else {
+            const DBox bx = S.boxes[md.fast_idx];
+            const RayPre pre = make_raypre(rb, true);
+            double ts[6];
+            ta = RT_INF;
+#pragma unroll
+            for (int sd = 0; sd < 6; ++sd) { ts[sd] = box_side_t(rb, pre, bx, sd); ta = fmin(ta, ts[sd]); }
+            if (!(ta < RT_INF)) return;
+            tb = RT_INF;
+#pragma unroll
+            for (int sd = 0; sd < 6; ++sd) if (ts[sd] >= ta + 0.0001) tb = fmin(tb, ts[sd]);
+            if (!(tb < RT_INF)) return;
+        }
+    } else {
+        BestHit b1;
+        best_init(b1, RT_INF);
+        trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, -RT_INF, b1, cnt);
+        if (b1.type == RT_NONE) return;
+        BestHit b2;
+        best_init(b2, RT_INF);
+        trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, b1.t + 0.0001, b2, cnt);
+        if (b2.type == RT_NONE) return;
+        ta = b1.t; tb = b2.t;
+    }
+    double t1 = fmax(ta, t_min);
+    const double t2 = fmin(tb, closest);
     if (t1 >= t2) return;
     if (t1 < 0.0) t1 = 0.0;
     const double ray_length = sqrt(length_squared(r.d));

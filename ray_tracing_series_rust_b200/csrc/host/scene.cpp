@@ -485,6 +485,18 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF) {
         m.mat_id = (uint32_t)n.mat;
         m.prim_id = (uint32_t)n.prim_base;
         m.neg_inv_density = -1.0 / n.d[0]; // hit.rs:949
+        m.fast_type = 0; m.fast_idx = 0; m.fast_chain_off = 0; m.fast_chain_len = 0;
+        if (m.inst_end - m.inst_begin == 1) {
+            const Instance& bi = instances[m.inst_begin];
+            const BvhNode32& rn = nodes[bi.root];
+            const uint32_t lt = (rn.count >> 24) & 0x7fu, ln = rn.count & 0xffffffu;
+            if ((rn.count & RT_LEAF_FLAG) && ln == 1 && (lt == PRIM_SPHERE || lt == PRIM_BOX)) {
+                m.fast_type = lt == PRIM_SPHERE ? 1u : 2u;
+                m.fast_idx = rn.first;
+                m.fast_chain_off = bi.chain_off;
+                m.fast_chain_len = bi.chain_len;
+            }
+        }
         media.push_back(m);
     }
 
@@ -562,6 +574,7 @@ int32_t do_commit(rt_scene* s) {
     D.n_main_instances = HF.n_main_instances;
     D.n_media = (uint32_t)media.size();
     D.n_prims = (uint32_t)s->n_prims;
+    D.flags = (!rects.empty() || !boxes.empty()) ? 1u : 0u;
     if (s->camera.set) D.cam = s->camera.cam;
     for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
     s->dev.valid = true;

@@ -69,6 +69,8 @@ struct Medium { // hit.rs:938-951
     uint32_t chain_off, chain_len; // wrappers around the ConstantMedium itself (usually 0)
     uint32_t mat_id, prim_id;
     double neg_inv_density;
+    // fast path: the boundary is ONE sphere (1) or ONE box (2) reached through one wrapper chain
+    uint32_t fast_type, fast_idx, fast_chain_off, fast_chain_len;
 };
 
 struct DMaterial {
@@ -121,7 +123,7 @@ struct DeviceScene {
     uint32_t n_main_instances;
     uint32_t n_media;
     uint32_t n_prims;
-    uint32_t pad_;
+    uint32_t flags; // bit 0: the scene has axis rects / boxes (per-ray inverse directions are needed)
     DCamera cam;
     float background[3];
     float pad2_;

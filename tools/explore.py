@@ -56,6 +56,16 @@ if __name__ == "__main__":
             run(13, 800, 1.5, 200, label=f"book1 {tag}")
             run(6, 1000, 1.0, 20, label=f"book2 {tag}")
             run(14, 1000, 1.0, 8, param=660, label=f"mesh871k {tag}")
+    elif what == "all":
+        run(13, 800, 1.5, 50, label="warm")
+        run(13, 800, 1.5, 500, label="book1 final")
+        run(99, 800, 1.5, 500, label="book1 shipped")
+        run(5, 600, 1.0, 300, label="cornell smoke")
+        run(6, 1000, 1.0, 100, label="book2 final")
+        run(14, 1000, 1.0, 20, param=660, label="mesh 871k")
+        run(5, 600, 1.0, 30, flags=3, label="cornell smoke COUNT")
+        run(6, 1000, 1.0, 10, flags=3, label="book2 COUNT")
+        run(14, 1000, 1.0, 4, param=660, flags=3, label="mesh COUNT")
     elif what == "sweep":
         run(13, 800, 1.5, 50, label="warm")
         for occ in (4, 5, 6):
