@@ -21,7 +21,7 @@
 #include <vector>
 
 #ifndef RT_SHADE_MIN_BLOCKS
-#define RT_SHADE_MIN_BLOCKS 3
+#define RT_SHADE_MIN_BLOCKS 4
 #endif
 
 #include "rt_device.cuh"
@@ -51,6 +51,7 @@ struct Queues {
     uint32_t* q[Q_COUNT];
     uint32_t* counts;            // [2][8]
     uint32_t* dead;              // slots that found no more work
+    uint32_t* ext_cursor;        // k_extend_p: next slot to hand out (reset by k_shade_all)
     unsigned long long* next_path;
     unsigned long long* stats;   // [0] segments, [1] nodes, [2] prims, [3] medium queries, [4..8] scatters by material
 };
@@ -103,7 +104,7 @@ __global__ void k_init(PathState P, Queues Q, uint32_t n) {
         P.alive[i] = 1;
     }
     if (blockIdx.x == 0 && threadIdx.x < 16) Q.counts[threadIdx.x] = (threadIdx.x == Q_MISS) ? n : 0u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *Q.dead = 0; *Q.next_path = 0ull; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *Q.dead = 0; *Q.next_path = 0ull; *Q.ext_cursor = 0; }
     if (blockIdx.x == 0 && threadIdx.x < 9) Q.stats[threadIdx.x] = 0ull;
 }
 
@@ -137,6 +138,7 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
     const uint64_t path_id = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
     PathRng g;
     g.init(J.seed, path_id, 0);
+    g.prefetch2(); // jitter (2) + lens disk (2 per try) + time (1): two blocks cover 2 disk tries
     const double u = ((double)ii + g.gen()) / (double)(J.W - 1); // world.rs:1212
     const double v = ((double)j + g.gen()) / (double)(J.H - 1);  // world.rs:1213
     const Ray r = camera_get_ray(S.cam, u, v, g);
@@ -195,6 +197,182 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
     }
 }
 
+// ------------------------------------------------------------------ k_extend_p: persistent, warp-scheduled world.hit
+// Every lane owns one ray and is in one of three states; each turn the warp runs the phase that serves
+// the most lanes per unit of cost (greedy), so lanes neither wait for the slowest lane's leaf search
+// (while-while) nor for the longest ray of the warp (one ray per thread):
+//   TRAV  one sibling-pair step of the BVH walk (64 B fetch, two f32 slab tests)
+//   LEAF  the f64 primitive tests of the lane's pending leaves
+//   ADV   traversal of the current instance finished: next instance, or media + HitRecord + queue push,
+//         then fetch the next live slot (warp-aggregated claim of consecutive slots) and set it up
+#ifndef RT_TRAV_STEPS
+#define RT_TRAV_STEPS 3
+#endif
+#define RT_ST_TRAV 0
+#define RT_ST_LEAF 1
+#define RT_ST_ADV 2
+#define RT_ST_EXIT 3
+template <bool MEDIA, bool COUNT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_extend_p(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q,
+                                                         int parity) {
+    uint32_t* counts = Q.counts + 8 * parity;
+    const unsigned full = 0xffffffffu;
+    const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
+    const bool planar = (S.flags & 1u) != 0;
+    uint32_t stack[RT_STACK];
+    int sp = 0;
+    int state = RT_ST_ADV;
+    bool have_ray = false;
+    uint32_t slot = 0, inst_i = 0, cur = 0xffffffffu;
+    uint32_t leaf_first0 = 0, leaf_cnt0 = 0, leaf_first1 = 0, leaf_cnt1 = 0;
+    Ray r; // ray in the current instance's space
+    r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.time = 0.0;
+    RayF f; f.idx = f.idy = f.idz = f.oodx = f.oody = f.oodz = 0.f;
+    RayPre pre; pre.a = 1.0; pre.inv_a = 1.0; pre.inv_d = mk3(0, 0, 0);
+    float tminf = 0.f, tmaxf = 0.f;
+    BestHit best;
+    best_init(best, RT_INF);
+    uint32_t my_segments = 0;
+    TraceCounters tc; tc.nodes = 0; tc.prims = 0;
+    const uint32_t DONE = 0xffffffffu;
+    const double t_min = 0.001;
+
+    for (;;) {
+        const unsigned mT = __ballot_sync(full, state == RT_ST_TRAV);
+        const unsigned mL = __ballot_sync(full, state == RT_ST_LEAF);
+        const unsigned mA = __ballot_sync(full, state == RT_ST_ADV);
+        if (!(mT | mL | mA)) break;
+        // greedy phase choice: lanes served per unit cost (pair step 1, leaf tests ~2.5, advance ~4)
+        const int sT = __popc(mT) * 20, sL = __popc(mL) * 8, sA = __popc(mA) * 5;
+        if (sT >= sL && sT >= sA) {
+            // up to RT_TRAV_STEPS pair steps per scheduling decision (amortises the ballots)
+            for (int step = 0; step < RT_TRAV_STEPS && state == RT_ST_TRAV; ++step) {
+                const float4 lo0 = __ldg(nodes + 2 * cur), hi0 = __ldg(nodes + 2 * cur + 1);
+                const float4 lo1 = __ldg(nodes + 2 * cur + 2), hi1 = __ldg(nodes + 2 * cur + 3);
+                float tn0, tn1;
+                bool h0 = slab(lo0, hi0, f, tminf, tmaxf, tn0);
+                bool h1 = slab(lo1, hi1, f, tminf, tmaxf, tn1);
+                if (COUNT) tc.nodes += 2;
+                const uint32_t c0 = __float_as_uint(hi0.w), c1 = __float_as_uint(hi1.w);
+                if (h0 && c0) { leaf_first0 = __float_as_uint(lo0.w); leaf_cnt0 = c0 & 0x7fffffffu; h0 = false; }
+                if (h1 && c1) { leaf_first1 = __float_as_uint(lo1.w); leaf_cnt1 = c1 & 0x7fffffffu; h1 = false; }
+                if (h0 && h1) {
+                    const uint32_t n0 = __float_as_uint(lo0.w), n1 = __float_as_uint(lo1.w);
+                    const bool first0 = tn0 <= tn1;
+                    cur = first0 ? n0 : n1;
+                    if (sp < RT_STACK) stack[sp++] = first0 ? n1 : n0;
+                } else if (h0) {
+                    cur = __float_as_uint(lo0.w);
+                } else if (h1) {
+                    cur = __float_as_uint(lo1.w);
+                } else {
+                    cur = sp ? stack[--sp] : DONE;
+                }
+                if ((leaf_cnt0 | leaf_cnt1) & 0xffffffu) state = RT_ST_LEAF;
+                else { leaf_cnt0 = 0; leaf_cnt1 = 0; if (cur == DONE) state = RT_ST_ADV; }
+            }
+        } else if (sL >= sA) {
+            if (state == RT_ST_LEAF) {
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t lc = k ? leaf_cnt1 : leaf_cnt0, lf = k ? leaf_first1 : leaf_first0;
+                    if (lc & 0xffffffu) {
+                        if (COUNT) tc.prims += lc & 0xffffffu;
+                        leaf_test(S, r, pre, t_min, best, lc >> 24, lf, lc & 0xffffffu, inst_i);
+                    }
+                }
+                leaf_cnt0 = 0; leaf_cnt1 = 0;
+                tmaxf = f32_up(best.t);
+                state = (cur == DONE) ? RT_ST_ADV : RT_ST_TRAV;
+            }
+        } else {
+            if (state == RT_ST_ADV) {
+                bool need_setup = false;
+                if (have_ray) {
+                    ++inst_i;
+                    if (inst_i < S.n_main_instances) {
+                        need_setup = true;
+                    } else {
+                        // world.hit is complete for this ray: media, HitRecord, queue push
+                        const SlotA a = P.A[slot];
+                        const SlotB b = P.B[slot];
+                        Ray wr;
+                        wr.o = mk3(a.ox, a.oy, a.oz); wr.d = mk3(b.dx, b.dy, b.dz); wr.time = a.time;
+                        HitRec h;
+                        bool hit = false;
+                        if (MEDIA) {
+                            const SlotD d = P.D[slot];
+                            double closest = best.t;
+                            int32_t mwin = -1;
+                            D3 mp = mk3(0, 0, 0);
+                            for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT, false>(S, mi, wr, t_min, closest, mwin, mp, J.seed, d.path_id, d.segment, &tc);
+                            if (mwin >= 0) {
+                                const Medium md = S.media[mwin];
+                                h.p = mp; h.n = mk3(0, 0, 0); h.t = closest; h.u = 0.0; h.v = 0.0; h.front = true; // hit.rs:975-984
+                                h.mat = md.mat_id; h.prim_id = md.prim_id;
+                                hit = true;
+                            }
+                        }
+                        if (!hit && best.type != RT_NONE) { h = finalize_hit<false>(S, wr, best); hit = true; }
+                        uint32_t qi = Q_MISS;
+                        if (hit) {
+                            SlotA na; na.ox = h.p.x; na.oy = h.p.y; na.oz = h.p.z; na.time = a.time;
+                            SlotC nc; nc.nx = h.n.x; nc.ny = h.n.y; nc.nz = h.n.z; nc.hmat = h.mat | (h.front ? 0x80000000u : 0u); nc.pad = 0;
+                            P.A[slot] = na;
+                            P.C[slot] = nc;
+                            const DMaterial* mp2 = &S.materials[h.mat];
+                            qi = __ldg(&mp2->type);
+                            if (__ldg(&mp2->flags) & 1u) *reinterpret_cast<double2*>(&P.B[slot]) = make_double2(h.u, h.v);
+                        }
+                        Q.q[qi][agg_reserve(counts, qi)] = slot;
+                        have_ray = false;
+                    }
+                }
+                if (!have_ray) {
+                    // claim the next slot (consecutive slots for the lanes fetching together => coalesced state loads)
+                    const unsigned act = __activemask();
+                    const int leader = __ffs(act) - 1;
+                    uint32_t base = 0;
+                    if ((int)lane_id() == leader) base = atomicAdd(Q.ext_cursor, (uint32_t)__popc(act));
+                    base = __shfl_sync(act, base, leader);
+                    slot = base + __popc(act & ((1u << lane_id()) - 1u));
+                    if (slot >= J.n_slots) {
+                        state = RT_ST_EXIT;
+                    } else if (P.alive[slot]) {
+                        have_ray = true;
+                        inst_i = 0;
+                        best_init(best, RT_INF);
+                        ++my_segments;
+                        need_setup = true;
+                    } // dead slot: stay in ADV and fetch again
+                }
+                if (need_setup) {
+                    const SlotA a = P.A[slot];
+                    const SlotB b = P.B[slot];
+                    r.o = mk3(a.ox, a.oy, a.oz); r.d = mk3(b.dx, b.dy, b.dz); r.time = a.time;
+                    const Instance* ip = &S.instances[inst_i];
+                    xform_ray(S.ops, __ldg(&ip->chain_off), __ldg(&ip->chain_len), r);
+                    f = make_rayf(r);
+                    pre = make_raypre(r, planar);
+                    tminf = f32_down(t_min);
+                    tmaxf = f32_up(best.t);
+                    cur = __ldg(&ip->root);
+                    sp = 0;
+                    leaf_cnt0 = 0; leaf_cnt1 = 0;
+                    state = RT_ST_TRAV;
+                }
+            }
+        }
+    }
+    uint32_t segs = my_segments;
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(full, segs, o);
+    if (lane_id() == 0 && segs) atomicAdd(&Q.stats[0], (unsigned long long)segs);
+    if (COUNT) {
+        uint32_t a = tc.nodes, b = tc.prims;
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(full, a, o); b += __shfl_xor_sync(full, b, o); }
+        if (lane_id() == 0) { atomicAdd(&Q.stats[1], (unsigned long long)a); atomicAdd(&Q.stats[2], (unsigned long long)b); }
+    }
+}
+
 // ------------------------------------------------------------------ k_shade_all: one launch drains every material queue and the miss queue.
 // The flat work index space is the concatenation of the queues, each padded to a multiple of 32, so a
 // warp only ever holds entries of ONE queue (material-coherent warps without one launch per material).
@@ -210,6 +388,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
     const uint32_t total = start[Q_COUNT];
     if (blockIdx.x == 0 && threadIdx.x < 8) {
         Q.counts[8 * (parity ^ 1) + threadIdx.x] = 0; // next k_extend fills the other buffer
+        if (threadIdx.x == 0) *Q.ext_cursor = 0;
         if (threadIdx.x < MAT_TYPE_COUNT && counts[threadIdx.x]) atomicAdd(&Q.stats[4 + threadIdx.x], (unsigned long long)counts[threadIdx.x]);
     }
     for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < total; f += gridDim.x * blockDim.x) {
@@ -246,6 +425,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
             } else {
                 PathRng g;
                 g.init(J.seed, sd.path_id, sd.draw);
+                g.prefetch2();
                 const D3 n3 = mk3(sc.nx, sc.ny, sc.nz);
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
@@ -525,6 +705,7 @@ static cudaError_t ensure_workspace(Workspace*& w, uint32_t N) {
     for (int q = 0; q < Q_COUNT; ++q) Q.q[q] = w->take<uint32_t>(N);
     Q.counts = w->take<uint32_t>(16);
     Q.dead = w->take<uint32_t>(1);
+    Q.ext_cursor = w->take<uint32_t>(1);
     Q.next_path = w->take<unsigned long long>(1);
     Q.stats = w->take<unsigned long long>(9);
     if (w->used > w->cap) return cudaErrorMemoryAllocation;
@@ -535,6 +716,14 @@ static cudaError_t ensure_workspace(Workspace*& w, uint32_t N) {
     if ((err = cudaEventCreateWithFlags(&w->ev_poll[1], cudaEventDisableTiming)) != cudaSuccess) return err;
     w->n_slots = N;
     return cudaSuccess;
+}
+
+template <bool MEDIA, bool COUNT>
+static void launch_extend_p(int occ, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
+    // persistent: exactly the resident number of CTAs (148 SMs x occ)
+    if (occ >= 5) k_extend_p<MEDIA, COUNT, 5><<<148 * 5, 128, 0, st>>>(scene, J, P, Q, parity);
+    else if (occ == 4) k_extend_p<MEDIA, COUNT, 4><<<148 * 4, 128, 0, st>>>(scene, J, P, Q, parity);
+    else k_extend_p<MEDIA, COUNT, 3><<<148 * 3, 128, 0, st>>>(scene, J, P, Q, parity);
 }
 
 template <bool MEDIA, bool COUNT>
@@ -576,6 +765,9 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         const int qblocks = (int)std::min<uint32_t>((N + 255) / 256, 148 * 8);
         const bool media = scene.n_media != 0;
         const int ext_occ = tune.extend_occ > 0 ? tune.extend_occ : (media ? 4 : 5);
+        // measured (profiles/): the warp-scheduled persistent kernel wins on deep triangle BVHs (+22 % on the 871k mesh),
+        // the one-ray-per-thread kernel on small scenes and on scenes with media
+        const int ext_kind = tune.extend_kind >= 0 ? tune.extend_kind : ((!media && (scene.flags & 4u)) ? 1 : 0);
         const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, ext_occ) * (uint32_t)std::max(1, tune.extend_waves));
         CK(cudaEventRecord(w->ev_begin, stream));
         if (tune.mode == RT_MODE_FUSED) {
@@ -618,7 +810,11 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                     CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
                     CK(cudaEventRecord(ea, stream));
                 }
-                if (media) { if (tune.count_events) launch_extend<true, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(ext_occ, eblocks, stream, scene, J, P, Q, parity); }
+                if (ext_kind == 1 && (!media || (scene.flags & 2u))) {
+                    const int pocc = tune.extend_occ > 0 ? tune.extend_occ : 4;
+                    if (media) { if (tune.count_events) launch_extend_p<true, true>(pocc, stream, scene, J, P, Q, parity); else launch_extend_p<true, false>(pocc, stream, scene, J, P, Q, parity); }
+                    else { if (tune.count_events) launch_extend_p<false, true>(pocc, stream, scene, J, P, Q, parity); else launch_extend_p<false, false>(pocc, stream, scene, J, P, Q, parity); }
+                } else if (media) { if (tune.count_events) launch_extend<true, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(ext_occ, eblocks, stream, scene, J, P, Q, parity); }
                 else { if (tune.count_events) launch_extend<false, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<false, false>(ext_occ, eblocks, stream, scene, J, P, Q, parity); }
                 if (tune.timed_extend) {
                     CK(cudaEventRecord(eb, stream));

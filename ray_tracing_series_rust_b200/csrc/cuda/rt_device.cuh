@@ -68,18 +68,30 @@ RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
 // xi = u32 * 2^-32 (identical in oracle/rt_oracle.hpp PathCtx).
 struct PathRng {
     uint2 key, path;
-    uint32_t draw, cached;
-    uint4 blk;
+    uint32_t draw, cached; // cached = index of the block held in blk; blk2 holds block cached + 1 when have2
+    uint4 blk, blk2;
+    bool have2;
     RT_DEV void init(uint64_t seed, uint64_t path_id, uint32_t draw0) {
         key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
         path = make_uint2((uint32_t)path_id, (uint32_t)(path_id >> 32));
         draw = draw0;
         cached = 0xffffffffu;
+        have2 = false;
+    }
+    // Compute the next two blocks now, while the warp is converged: the rejection loops that consume
+    // them diverge, and a Philox block generated inside them runs with a handful of active lanes.
+    RT_DEV void prefetch2() {
+        const uint32_t b = draw >> 2;
+        blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
+        blk2 = philox4x32_10(make_uint4(path.x, path.y, b + 1u, 0u), key);
+        cached = b;
+        have2 = true;
     }
     RT_DEV uint32_t next_u32() {
         const uint32_t b = draw >> 2;
         if (b != cached) {
-            blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
+            if (have2 && b == cached + 1u) { blk = blk2; have2 = false; }
+            else blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
             cached = b;
         }
         const uint32_t w = draw & 3u;
@@ -467,7 +479,10 @@ RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const Bes
 }
 
 // ------------------------------------------------------------------ ConstantMedium::hit (hit.rs:955-986)
-template <bool COUNT>
+// GENERAL = false compiles out the two-traversal path for arbitrary boundaries (it costs the hot
+// kernels registers and a second traversal stack); the host only picks such kernels when every medium
+// of the scene has the single-sphere / single-box fast path (DeviceScene.flags bit 1).
+template <bool COUNT, bool GENERAL>
 RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray, double t_min, double& closest, int32_t& winner, D3& p_out,
                          uint64_t seed, uint64_t path_id, uint32_t segment, TraceCounters* cnt) {
     const Medium md = S.media[mi];
@@ -505,7 +520,7 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
             for (int sd = 0; sd < 6; ++sd) if (ts[sd] >= ta + 0.0001) tb = fmin(tb, ts[sd]);
             if (!(tb < RT_INF)) return;
         }
-    } else {
+    } else if (GENERAL) {
         BestHit b1;
         best_init(b1, RT_INF);
         trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, -RT_INF, b1, cnt);
@@ -515,6 +530,8 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
         trace_instances<COUNT>(S, md.inst_begin, md.inst_end, r, b1.t + 0.0001, b2, cnt);
         if (b2.type == RT_NONE) return;
         ta = b1.t; tb = b2.t;
+    } else {
+        return; // kernels compiled without the general path are only launched when every medium has the fast path
     }
     double t1 = fmax(ta, t_min);
     const double t2 = fmin(tb, closest);
@@ -551,7 +568,7 @@ RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double
         int32_t mwin = -1;
         D3 mp = mk3(0, 0, 0);
         if (media) {
-            for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT>(S, mi, ray, t_min, closest, mwin, mp, seed, path_id, segment, cnt);
+            for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT, true>(S, mi, ray, t_min, closest, mwin, mp, seed, path_id, segment, cnt);
         }
         if (mwin >= 0) {
             const Medium md = S.media[mwin];

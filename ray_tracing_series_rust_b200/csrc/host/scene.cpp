@@ -575,6 +575,12 @@ int32_t do_commit(rt_scene* s) {
     D.n_media = (uint32_t)media.size();
     D.n_prims = (uint32_t)s->n_prims;
     D.flags = (!rects.empty() || !boxes.empty()) ? 1u : 0u;
+    {
+        bool all_fast = true;
+        for (const Medium& m : media) all_fast = all_fast && m.fast_type != 0;
+        if (all_fast) D.flags |= 2u;
+    }
+    if (tris.size() >= 4096) D.flags |= 4u; // deep triangle BVH: prefer the persistent warp-scheduled extend kernel
     if (s->camera.set) D.cam = s->camera.cam;
     for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
     s->dev.valid = true;
@@ -593,6 +599,7 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_EXTEND_OCC"))) s->tuning.extend_occ = std::atoi(e);
     if ((e = std::getenv("RTB200_EXTEND_WAVES"))) s->tuning.extend_waves = std::atoi(e);
     if ((e = std::getenv("RTB200_MODE"))) s->tuning.mode = std::atoi(e);
+    if ((e = std::getenv("RTB200_EXTEND_KIND"))) s->tuning.extend_kind = std::atoi(e);
     if ((e = std::getenv("RTB200_MEGA_OCC"))) s->tuning.mega_occ = std::atoi(e);
     return s;
 }

@@ -56,6 +56,16 @@ if __name__ == "__main__":
             run(13, 800, 1.5, 200, label=f"book1 {tag}")
             run(6, 1000, 1.0, 20, label=f"book2 {tag}")
             run(14, 1000, 1.0, 8, param=660, label=f"mesh871k {tag}")
+    elif what == "kinds":
+        run(13, 800, 1.5, 50, label="warm")
+        for kind, occ in ((0, 0), (1, 4), (1, 3), (1, 5)):
+            os.environ["RTB200_EXTEND_KIND"] = str(kind); os.environ["RTB200_EXTEND_OCC"] = str(occ)
+            tag = f"kind{kind} occ{occ}"
+            run(13, 800, 1.5, 300, label=f"book1 {tag}")
+            run(99, 800, 1.5, 100, label=f"book1b {tag}")
+            run(5, 600, 1.0, 200, label=f"smoke {tag}")
+            run(6, 1000, 1.0, 50, label=f"book2 {tag}")
+            run(14, 1000, 1.0, 10, param=660, label=f"mesh871k {tag}")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
