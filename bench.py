@@ -280,6 +280,7 @@ def main():
         barrier()
         t0 = time.time()
         scene.commit()
+        t_commit = time.time()
         cfg = capi.make_config(W, aspect, spp_total, depth, seed=100 + k, sample_begin=s_begin, sample_end=s_end)
         accum.zero_()
         st = capi.Stats()
@@ -291,6 +292,8 @@ def main():
         barrier()
         if k > 0:
             e2e_ms.append(1e3 * (time.time() - t0))
+        if rank == 0 and os.environ.get("RTB200_BENCH_DEBUG"):
+            print(f"[e2e] step {k}: {1e3 * (time.time() - t0):.1f} ms (commit {1e3 * (t_commit - t0):.1f}, render {st.ms_total:.1f} / device {st.ms_device:.1f})", file=sys.stderr)
     e2e_local = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_local, op=dist.ReduceOp.MAX)
@@ -298,7 +301,7 @@ def main():
     out_hc = (C.c_int64 * 16)()
     api.lib.rt_scene_host_check.restype = C.c_int32
     api.lib.rt_scene_host_check(C.c_void_p(scene.h), out_hc)
-    scene_bytes = int(out_hc[0]) * 32 + int(out_hc[5]) * 40 + int(out_hc[6]) * 88 + int(out_hc[7]) * 48 + int(out_hc[8]) * 56 + int(out_hc[9]) * 56 + int(out_hc[10]) * 56
+    scene_bytes = int(out_hc[14])
 
     if rank != 0:
         if world > 1:

@@ -273,7 +273,7 @@ RTB_EXPORT int32_t rt_unit_op(rt_scene* s, int32_t op, uint32_t ia, uint32_t ib,
 RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots);
 /* Host-only self check of the flattener and BVH builder (needs no GPU): out[0] nodes, [1] max depth,
  * [2] main instances, [3] instances, [4] media, [5..10] primitives per rt_prim_type, [11] leaves,
- * [12] invariant violations (0 = valid), [13] numbered prims. */
+ * [12] invariant violations (0 = valid), [13] numbered prims, [14] bytes the last commit uploaded. */
 RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]);
 #endif
 

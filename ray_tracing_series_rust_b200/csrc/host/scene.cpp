@@ -74,13 +74,18 @@ struct CameraDesc {
     DCamera cam;
 };
 
-struct DeviceBuffers {
-    std::vector<void*> allocs;
+struct DeviceBuffers { // one grow-only device arena + one pinned staging buffer: a commit is ONE H2D copy
+    char* arena = nullptr;
+    size_t capacity = 0;
+    char* staging = nullptr;
+    size_t staging_capacity = 0;
     DeviceScene scene;
     bool valid = false;
+    size_t bytes = 0; // bytes uploaded by the last commit
     void release() {
-        for (void* p : allocs) cudaFree(p);
-        allocs.clear();
+        if (arena) cudaFree(arena);
+        if (staging) cudaFreeHost(staging);
+        arena = nullptr; staging = nullptr; capacity = 0; staging_capacity = 0;
         valid = false;
     }
 };
@@ -309,21 +314,43 @@ struct Flattener {
     }
 };
 
-template <class T>
-cudaError_t upload(DeviceBuffers& dev, const std::vector<T>& v, const T*& out) {
-    out = nullptr;
-    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return e;
-    dev.allocs.push_back(p);
-    if (!v.empty()) {
-        e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) return e;
+struct UploadPlan { // collects the flattened arrays, lays them out 256-byte aligned, uploads them in one copy
+    struct Piece { const void* src; size_t bytes; size_t offset; const void** dst; };
+    std::vector<Piece> pieces;
+    size_t total = 0;
+    template <class T> void add(const std::vector<T>& v, const T*& field) {
+        total = (total + 255) & ~(size_t)255;
+        Piece p;
+        p.src = v.data(); p.bytes = v.size() * sizeof(T); p.offset = total;
+        p.dst = reinterpret_cast<const void**>(&field);
+        pieces.push_back(p);
+        total += std::max<size_t>(p.bytes, 16);
     }
-    out = reinterpret_cast<const T*>(p);
-    return cudaSuccess;
-}
+    cudaError_t run(DeviceBuffers& dev) {
+        cudaError_t e;
+        if (total > dev.capacity) {
+            if (dev.arena) cudaFree(dev.arena);
+            dev.arena = nullptr; dev.capacity = 0;
+            const size_t cap = total + total / 4 + 4096;
+            if ((e = cudaMalloc(&dev.arena, cap)) != cudaSuccess) return e;
+            dev.capacity = cap;
+        }
+        if (total > dev.staging_capacity) {
+            if (dev.staging) cudaFreeHost(dev.staging);
+            dev.staging = nullptr; dev.staging_capacity = 0;
+            const size_t cap = total + total / 4 + 4096;
+            if ((e = cudaMallocHost(&dev.staging, cap)) != cudaSuccess) return e;
+            dev.staging_capacity = cap;
+        }
+        for (const Piece& p : pieces) {
+            if (p.bytes) std::memcpy(dev.staging + p.offset, p.src, p.bytes);
+            *p.dst = dev.arena + p.offset;
+        }
+        if ((e = cudaMemcpy(dev.arena, dev.staging, total, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        dev.bytes = total;
+        return cudaSuccess;
+    }
+};
 
 bool tex_reads_uv(const rt_scene* s, int32_t t, int depth = 0) {
     if (depth > 64) return false;
@@ -558,19 +585,16 @@ int32_t do_commit(rt_scene* s) {
     std::vector<PerlinTable>& perlin = HF.perlin;
     std::vector<float4>& texels = HF.texels;
 
-    s->dev.release();
+    s->dev.valid = false;
     DeviceScene& D = s->dev.scene;
     std::memset(&D, 0, sizeof D);
-#define UP(vec, field)                                              \
-    if ((ce = upload(s->dev, vec, D.field)) != cudaSuccess) {       \
-        s->dev.release();                                           \
-        return fail_cuda(ce, "scene upload");                       \
-    }
-    UP(nodes, nodes) UP(spheres, spheres) UP(movings, movings) UP(gravities, gravities) UP(gtable, gravity_table)
-    UP(rects, rects) UP(boxes, boxes) UP(tris, tris)
-    for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) { UP(meta[t], meta[t]) }
-    UP(instances, instances) UP(ops, ops) UP(media, media) UP(dmats, materials) UP(dtex, textures) UP(perlin, perlin) UP(texels, texels)
-#undef UP
+    UploadPlan up;
+    up.add(nodes, D.nodes); up.add(spheres, D.spheres); up.add(movings, D.movings); up.add(gravities, D.gravities); up.add(gtable, D.gravity_table);
+    up.add(rects, D.rects); up.add(boxes, D.boxes); up.add(tris, D.tris);
+    for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) up.add(meta[t], D.meta[t]);
+    up.add(instances, D.instances); up.add(ops, D.ops); up.add(media, D.media); up.add(dmats, D.materials); up.add(dtex, D.textures);
+    up.add(perlin, D.perlin); up.add(texels, D.texels);
+    if ((ce = up.run(s->dev)) != cudaSuccess) return fail_cuda(ce, "scene upload");
     D.n_main_instances = HF.n_main_instances;
     D.n_media = (uint32_t)media.size();
     D.n_prims = (uint32_t)s->n_prims;
@@ -1054,6 +1078,7 @@ RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]) {
         for (uint8_t v : seen[(size_t)t])
             if (v != 1) ++violations;
     out[11] = leaves; out[12] = violations; out[13] = s->n_prims;
+    out[14] = (int64_t)s->dev.bytes; // bytes uploaded host->device by the last rt_scene_commit
     return RT_OK;
 }
 
