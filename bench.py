@@ -228,11 +228,13 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     host_screen = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
 
-    def one_step(step, timed_extend=False, count=False):
+    def one_step(step, timed_extend=False, count=False, local_only=False):
         cfg = capi.make_config(W, aspect, spp_total, depth, seed=1 + step, sample_begin=s_begin, sample_end=s_end, flags=(1 if timed_extend else 0) | (2 if count else 0))
         accum.zero_()
         st = capi.Stats()
         api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
+        if local_only:  # rank-0-only diagnostics after the other ranks have left: no collective
+            return st.as_dict()
         sharding.reduce_accumulators(accum, dst=0)
         if rank == 0:
             api.check(api.resolve_device(C.c_void_p(accum.data_ptr()), C.c_void_p(screen.data_ptr()), W, H, spp_total, H, C.c_void_p(stream.cuda_stream)))
@@ -303,14 +305,16 @@ def main():
     api.lib.rt_scene_host_check(C.c_void_p(scene.h), out_hc)
     scene_bytes = int(out_hc[14])
 
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()  # every collective is done; rank 0 continues alone (roofline, CPU baseline)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (k_extend), rank 0: device events around every extend launch
-    st_t = one_step(1000, timed_extend=True)
-    st_c = one_step(1000, count=True)
+    st_t = one_step(1000, timed_extend=True, local_only=True)
+    st_c = one_step(1000, count=True, local_only=True)
     n_ext = max(1, st_t["iterations"])
     ext_ms_avg = st_t["ms_extend"] / n_ext
     hbm, hbm_src = peaks()
@@ -373,8 +377,6 @@ def main():
     if not args.no_extra and world == 1 and args.workload == "book1_final" and not args.spp:
         line["also"] = extra_workloads(api, rtb, capi, stream)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
