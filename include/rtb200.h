@@ -233,6 +233,18 @@ RTB_EXPORT int32_t rt_resolve_device(const int64_t* d_accum, double* d_screen, i
                                      int32_t rendered_rows, void* cuda_stream);
 #endif
 
+/* render_scene_with_time(t0, t1, path, world): the per-frame animation entry.  cfg == NULL uses the
+ * reference's hard-coded frame settings: 500x500 (aspect 1.0), 500 spp, depth 50, camera
+ * (13,2,3)->(0,0,0), vfov 20, aperture 0.1, focus 10, background (0.7,0.8,1), THREADS = 11 row bands
+ * (so rows 495..499 stay black).  With cfg != NULL the image size / spp / depth / compat_threads / seed
+ * come from cfg and the camera aspect is cfg->aspect_ratio.  The shutter [t0, t1) is set on the scene's
+ * camera, the scene is re-committed (moving bounds and GravitySphere windows follow the shutter), rendered
+ * and written as P3 to `path` (path NULL: no file).  out_screen may be NULL.
+ *                                   [ref: src/world.rs:1249-1330] */
+RTB_EXPORT int32_t RTB_FN(render_scene_with_time)(rt_scene* s, double t0, double t1, const char* path,
+                                                  const rt_render_config* cfg, double* out_screen,
+                                                  rt_stats* stats);
+
 /* Screen::write_to_ppm (path NULL => stdout) / write_to_ppm_file: byte-identical P3
  *                                   [ref: src/screen.rs:40-59] */
 RTB_EXPORT int32_t RTB_FN(write_ppm)(const char* path_or_null, const double* screen,

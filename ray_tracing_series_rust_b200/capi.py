@@ -106,6 +106,7 @@ SIGNATURES = {
     "render": (C.c_int32, [_P, C.POINTER(RenderConfig), c_d3, C.POINTER(C.c_int64), C.POINTER(Stats)]),
     "image_height": (C.c_int32, [C.POINTER(RenderConfig)]),
     "write_ppm": (C.c_int32, [C.c_char_p, c_d3, C.c_int32, C.c_int32]),
+    "render_scene_with_time": (C.c_int32, [_P, C.c_double, C.c_double, C.c_char_p, C.POINTER(RenderConfig), c_d3, C.POINTER(Stats)]),
     "trace_batch": (C.c_int32, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_uint64, _P]),
 }
 # product-only entry points (device-resident accumulators for the multi-GPU path)
@@ -309,6 +310,16 @@ class Scene:
         self._c(self.api.render(self.h, C.byref(cfg), screen.ctypes.data_as(c_d3),
                                 accum.ctypes.data_as(C.POINTER(C.c_int64)) if want_accum else None, C.byref(st)))
         return screen, accum, st.as_dict()
+
+    def render_scene_with_time(self, t0, t1, path=None, cfg: RenderConfig = None):
+        """render_scene_with_time(t0, t1, path, world)  [ref: world.rs:1249]; cfg None = the reference's 500x500x500spp frame"""
+        probe = cfg if cfg is not None else make_config(500, 1.0, 500, 50)
+        H, W = self.image_height(probe), probe.image_width
+        screen = np.zeros((H, W, 3), dtype=np.float64)
+        st = Stats()
+        self._c(self.api.render_scene_with_time(self.h, float(t0), float(t1), str(path).encode() if path is not None else None,
+                                                C.byref(cfg) if cfg is not None else None, screen.ctypes.data_as(c_d3), C.byref(st)))
+        return screen, st.as_dict()
 
     def trace_batch(self, rays: np.ndarray, t_min=0.001, t_max=float("inf"), flags=RT_TRACE_SKIP_MEDIA, seed=0):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

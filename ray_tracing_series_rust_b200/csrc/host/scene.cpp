@@ -973,6 +973,35 @@ int32_t rt_write_ppm(const char* path, const double* screen, int32_t width, int3
     return RT_OK;
 }
 
+#define PFX(name) rt_##name
+// render_scene_with_time (world.rs:1249-1330)
+int32_t PFX(render_scene_with_time)(rt_scene* s, double t0, double t1, const char* path, const rt_render_config* cfg_in, double* out_screen, rt_stats* stats) {
+    CHECK_SCENE(s);
+    rt_render_config cfg;
+    if (cfg_in) {
+        cfg = *cfg_in;
+    } else {
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.image_width = 500; cfg.aspect_ratio = 1.0; cfg.samples_per_pixel = 500; cfg.max_depth = 50; // world.rs:1253-1257
+        cfg.compat_threads = 11;                                                                          // world.rs:18, 1281
+        cfg.seed = 1;
+    }
+    const double lookfrom[3] = {13, 2, 3}, lookat[3] = {0, 0, 0}, vup[3] = {0, 1, 0}, bg[3] = {0.7, 0.8, 1.0}; // world.rs:1252, 1259-1263
+    int32_t rc = PFX(scene_set_camera)(s, lookfrom, lookat, vup, 20.0, cfg.aspect_ratio, 0.1, 10.0, t0, t1);
+    if (rc != RT_OK) return rc;
+    if ((rc = PFX(scene_set_background)(s, bg)) != RT_OK) return rc;
+    if ((rc = PFX(scene_commit)(s)) != RT_OK) return rc;
+    const int32_t H = PFX(image_height)(&cfg);
+    if (H <= 0) return fail(RT_ERR_INVALID, "image height <= 0");
+    std::vector<double> local;
+    double* screen = out_screen;
+    if (!screen) { local.resize((size_t)cfg.image_width * H * 3); screen = local.data(); }
+    if ((rc = PFX(render)(s, &cfg, screen, nullptr, stats)) != RT_OK) return rc;
+    if (path) return PFX(write_ppm)(path, screen, cfg.image_width, H);
+    return RT_OK;
+}
+#undef PFX
+
 // ---------------------------------------------------------------- parity hook
 int32_t rt_trace_batch(rt_scene* s, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t flags, uint64_t seed, rt_hit* out) {
     CHECK_SCENE(s);

@@ -27,3 +27,11 @@ def reduce_accumulators(accum, dst: int = 0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
     return accum
+
+
+def frames_for_rank(n_frames: int, rank: int, world: int):
+    """Animation sharding: frame f goes to rank f mod world; no collective, each frame is
+    committed (shutter window) and rendered on one GPU.  [ref: render_scene_with_time, src/world.rs:1249]"""
+    if world < 1 or not (0 <= rank < world) or n_frames < 0:
+        raise ValueError("bad shard request")
+    return list(range(rank, n_frames, world))

@@ -262,6 +262,25 @@ def test_camera_shutter_recommit_gravity(orc):
         g.trace_batch(pu.primary_rays(camf, 4, 4, time=5.0))  # outside the committed shutter
 
 
+def test_render_scene_with_time_frames(orc, tmp_path):
+    # world.rs:1249-1330 on the GPU: frames of the bouncing animation, sample-exact against the oracle
+    g, o = rtb.new_scene(), orc.new_scene()
+    for s in (g, o):
+        s.world_build(8, 0xB005)
+    for frame in (0, 57):
+        cfg = capi.make_config(72, 1.5, 4, 50, seed=5 + frame, threads=4)
+        sg, stg = g.render_scene_with_time(0.4 * frame, 0.4 * frame + 0.4, tmp_path / f"g{frame}.ppm", cfg)
+        so, sto = o.render_scene_with_time(0.4 * frame, 0.4 * frame + 0.4, tmp_path / f"o{frame}.ppm", cfg)
+        assert stg["paths"] == sto["paths"] and abs(stg["segments"] - sto["segments"]) <= 0.005 * sto["segments"]
+        assert (np.abs(sg - so) > 1).any(axis=2).mean() < 0.02
+        assert (tmp_path / f"g{frame}.ppm").read_text().split("\n")[1] == "72 48"
+    # the reference's hard-coded frame: 500x500, 500 spp, THREADS = 11 => rows 495..499 never rendered
+    scr, st = g.render_scene_with_time(2.0, 2.4, tmp_path / "full.ppm", None)
+    assert scr.shape == (500, 500, 3) and st["paths"] == 495 * 500 * 500
+    assert np.all(scr[495:] == 0) and scr[:495].min() > 0  # every rendered pixel sees sky, ground or a sphere
+    assert (tmp_path / "full.ppm").read_text().startswith("P3\n500 500\n255\n0 0 0\n")
+
+
 def test_full_size_book1_properties(orc):
     """BASELINE.json configs[0] at full size (800x533, 500 spp, depth 50): size-independent checks —
     shard linearity, path count, and 48 random pixels recomputed path-by-path by the oracle."""

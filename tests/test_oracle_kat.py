@@ -382,3 +382,23 @@ def test_sampler_distributions(orc):
     assert np.abs(out.mean(0)).max() < 0.02
     orc.api().kat_sampler(2, 3, 2, n, out.ctypes.data_as(capi.c_d3))
     assert ((out[:, :2] ** 2).sum(1)).max() < 1.0 and np.all(out[:, 2] == 0)
+
+
+def test_render_scene_with_time_oracle(orc, tmp_path):
+    # world.rs:1249-1330: per-frame entry; an explicit config keeps the CPU test small
+    s = orc.new_scene()
+    s.world_build(8, 0xB005)
+    cfg = capi.make_config(44, 1.0, 2, 8, seed=5, compat_threads=11, threads=2)
+    path = tmp_path / "frame.ppm"
+    scr, st = s.render_scene_with_time(1.2, 1.6, path, cfg)
+    assert scr.shape == (44, 44, 3) and st["paths"] == 44 * 44 * 2
+    lines = path.read_text().split("\n")
+    assert lines[:3] == ["P3", "44 44", "255"] and len(lines) == 3 + 44 * 44 + 1
+    assert scr.max() > 0
+    # the shutter was applied to the camera: time1/time2 of the camera block
+    out = (C.c_double * 24)()
+    orc.api().check(orc.api().kat_camera(s.h, out))
+    assert (out[22], out[23]) == (1.2, 1.6)
+    cfg2 = capi.make_config(45, 1.0, 1, 4, seed=5, compat_threads=11, threads=2)  # 45 rows, 11 bands of 4 -> row 44 black
+    scr2, _ = s.render_scene_with_time(0.0, 0.4, None, cfg2)
+    assert np.all(scr2[44] == 0) and scr2[:44].max() > 0

@@ -81,3 +81,12 @@ def test_sample_range_partition():
             assert (tot, e - b, e) == (spp * world, spp, spp * world)
     with pytest.raises(ValueError):
         sharding.sample_range(10, 2, 2)
+
+
+def test_frames_for_rank_partition():
+    from ray_tracing_series_rust_b200 import sharding
+    for n in (0, 1, 7, 240):
+        for world in (1, 2, 4, 8):
+            got = sorted(f for r in range(world) for f in sharding.frames_for_rank(n, r, world))
+            assert got == list(range(n))
+    assert sharding.frames_for_rank(240, 3, 8)[:3] == [3, 11, 19]
