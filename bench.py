@@ -318,11 +318,22 @@ def main():
     if rank != 0:
         return 0
 
-    # ---- roofline of the dominant kernel (k_extend), rank 0: device events around every extend launch
-    st_t = one_step(1000, timed_extend=True, local_only=True)
-    st_c = one_step(1000, count=True, local_only=True)
-    n_ext = max(1, st_t["iterations"])
-    ext_ms_avg = st_t["ms_extend"] / n_ext
+    # ---- roofline of the dominant kernel, rank 0.  RT_MODE_AUTO picks the fused persistent kernel (k_mega: one launch
+    # per render, path state in registers) or the wavefront (k_extend dominant: CUDA events around every launch).
+    st_n = one_step(1000, local_only=True)
+    fused = st_n["iterations"] == 1
+    st_c = one_step(1000, count=True, local_only=True)  # device event counters (runs the wavefront; same rays, same BVH work)
+    if fused:
+        n_ext = 1
+        ext_ms_avg = st_n["ms_device"]
+        seg_per_launch = float(st_n["segments"])
+        ext_share = 1.0
+    else:
+        st_t = one_step(1000, timed_extend=True, local_only=True)
+        n_ext = max(1, st_t["iterations"])
+        ext_ms_avg = st_t["ms_extend"] / n_ext
+        seg_per_launch = st_t["segments"] / n_ext
+        ext_share = st_t["ms_extend"] / max(st_t["ms_device"], 1e-9)
     hbm, hbm_src = peaks()
 
     cpu = None
@@ -339,26 +350,28 @@ def main():
     # reference-count variant is reported next to it as `reference_counts`.
     own_seg = max(st_c["segments"], 1)
     prim_b = B_PRIM[{13: 0, 99: 1, 5: 4, 6: 4, 14: 5}.get(sid, 0)]
-    own_bps = B_NODE * st_c["box_tests"] / own_seg + prim_b * st_c["prim_tests"][0] / own_seg + B_STATE
-    seg_per_launch = st_t["segments"] / n_ext
+    state_b = 0 if fused else B_STATE  # the fused kernel keeps the path state in registers: no state traffic to count
+    own_bps = B_NODE * st_c["box_tests"] / own_seg + prim_b * st_c["prim_tests"][0] / own_seg + state_b
     achieved = own_bps * seg_per_launch / (ext_ms_avg * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+        "bound": "hbm", "kernel": "k_mega (fused persistent: generate + world.hit + scatter)" if fused else "k_extend",
+        "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
         "peak_source": hbm_src,
-        "bytes_per_segment": own_bps, "bytes_per_segment_source": "device event counters (nodes tested x 32 B + primitive tests + 160 B state)",
+        "bytes_per_segment": own_bps,
+        "bytes_per_segment_source": "device event counters: BVH boxes tested x 32 B + primitive tests x B_type" + ("" if fused else " + 160 B wavefront state"),
         "nodes_per_segment": st_c["box_tests"] / own_seg, "prim_tests_per_segment": st_c["prim_tests"][0] / own_seg,
         "segments_per_launch": seg_per_launch, "launch_ms_avg": ext_ms_avg, "launches_timed": n_ext,
-        "extend_share_of_step": st_t["ms_extend"] / max(st_t["ms_device"], 1e-9),
+        "kernel_share_of_step": ext_share,
         "note": "the scene (<64 KB) is L1/L2 resident, so DRAM traffic is far below the algorithmic bytes; the kernel is issue/latency bound, see profiles/",
     }
     if algo:
-        ref_ach = algo["bytes_per_segment"] * seg_per_launch / (ext_ms_avg * 1e-3) / 1e9
-        roofline["reference_counts"] = {"bytes_per_segment": algo["bytes_per_segment"], "box_tests_per_segment": algo["box_tests_per_segment"],
+        ref_ach = (algo["bytes_per_segment"] - (B_STATE if fused else 0)) * seg_per_launch / (ext_ms_avg * 1e-3) / 1e9
+        roofline["reference_counts"] = {"bytes_per_segment": algo["bytes_per_segment"] - (B_STATE if fused else 0), "box_tests_per_segment": algo["box_tests_per_segment"],
                                         "prim_tests_per_segment": algo["prim_tests_per_segment"], "achieved": ref_ach, "frac": ref_ach / hbm}
     prof = os.path.join(ROOT, "profiles", "extend_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(prof)).get(args.workload, {}).get("fused" if fused else "wavefront", {}).get("dram_bytes_per_launch")
         except Exception:
             pass
 
@@ -370,6 +383,7 @@ def main():
         "config": {"workload": args.workload, "description": desc, "image": [W, H], "spp_per_gpu": s_end - s_begin, "spp_total": spp_total, "max_depth": depth,
                    "paths_per_step": paths_all, "segments_per_path": segments / max(1, (s_end - s_begin) * W * H * args.steps),
                    "sharding": "sample ranges + one NCCL int64 reduce to rank 0" if world > 1 else "single GPU",
+                   "render_mode": "fused persistent kernel (RT_MODE_AUTO)" if fused else "wavefront (RT_MODE_AUTO)",
                    "l2": "flushed between timed steps (256 MiB memset, untimed); path state > L2",
                    "vs_baseline_note": "README.md:23 146.440 s on 10 threads of an unspecified CPU => 1.456e6 paths/s (derived)",
                    "render_wall_s": ms_per_step * 1e-3, "commit_s": commit_s, "wall_s_timed_region": t_wall},

@@ -186,6 +186,11 @@ typedef struct rt_render_config {
 } rt_render_config;
 
 #define RT_RENDER_DEFAULT 0
+/* diagnostics / mode selection (GPU library; the oracle ignores them) */
+#define RT_RENDER_TIMED_EXTEND 1    /* bracket every k_extend launch with CUDA events -> rt_stats.ms_extend */
+#define RT_RENDER_COUNT_EVENTS 2    /* count BVH boxes tested / primitive tests on the device -> rt_stats */
+#define RT_RENDER_FORCE_WAVEFRONT 4 /* wavefront mode: k_extend + k_shade_all per iteration, per-material queues */
+#define RT_RENDER_FORCE_FUSED 8     /* fused mode: one persistent kernel, path state in registers */
 /* fixed-point scale of the radiance accumulator: sum of samples * 2^32 in an int64 per channel */
 #define RT_ACCUM_SCALE_LOG2 32
 

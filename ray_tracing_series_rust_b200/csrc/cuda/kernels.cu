@@ -65,6 +65,23 @@ struct JobDev {
     int32_t count_events;
 };
 
+// Path-state chunks are streamed (read once / written once per kernel): evict-first hints keep them from
+// pushing the BVH nodes and primitives out of L1 / L2.
+template <class T> RT_DEV T ld_stream(const T* p) {
+    static_assert(sizeof(T) == 32, "32-byte chunk");
+    union { T t; uint4 q[2]; } u;
+    u.q[0] = __ldcs(reinterpret_cast<const uint4*>(p));
+    u.q[1] = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
+    return u.t;
+}
+template <class T> RT_DEV void st_stream(T* p, const T& v) {
+    static_assert(sizeof(T) == 32, "32-byte chunk");
+    union { T t; uint4 q[2]; } u;
+    u.t = v;
+    __stcs(reinterpret_cast<uint4*>(p), u.q[0]);
+    __stcs(reinterpret_cast<uint4*>(p) + 1, u.q[1]);
+}
+
 RT_DEV uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // warp-aggregated queue push: lanes of the warp that push to the same counter share one atomic
@@ -158,15 +175,15 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
     TraceCounters tc; tc.nodes = 0; tc.prims = 0;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < J.n_slots; slot += gridDim.x * blockDim.x) {
         if (!P.alive[slot]) continue;
-        const SlotA a = P.A[slot];
-        const SlotB b = P.B[slot];
+        const SlotA a = ld_stream(&P.A[slot]);
+        const SlotB b = ld_stream(&P.B[slot]);
         Ray r;
         r.o = mk3(a.ox, a.oy, a.oz);
         r.d = mk3(b.dx, b.dy, b.dz);
         r.time = a.time;
         uint64_t path_id = 0;
         uint32_t segment = 0;
-        if (MEDIA) { const SlotD d = P.D[slot]; path_id = d.path_id; segment = d.segment; }
+        if (MEDIA) { const SlotD d = ld_stream(&P.D[slot]); path_id = d.path_id; segment = d.segment; }
         HitRec h;
         const bool hit = world_hit<COUNT, false, MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
         ++my_segments;
@@ -174,8 +191,8 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
         if (hit) {
             SlotA na; na.ox = h.p.x; na.oy = h.p.y; na.oz = h.p.z; na.time = a.time;
             SlotC nc; nc.nx = h.n.x; nc.ny = h.n.y; nc.nz = h.n.z; nc.hmat = h.mat | (h.front ? 0x80000000u : 0u); nc.pad = 0;
-            P.A[slot] = na;
-            P.C[slot] = nc;
+            st_stream(&P.A[slot], na);
+            st_stream(&P.C[slot], nc);
             const DMaterial* mp = &S.materials[h.mat];
             qi = __ldg(&mp->type);
             if (__ldg(&mp->flags) & 1u) { // the texture chain reads (u,v): such materials never read the incoming direction
@@ -770,18 +787,22 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         const int ext_kind = tune.extend_kind >= 0 ? tune.extend_kind : ((!media && (scene.flags & 4u)) ? 1 : 0);
         const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, ext_occ) * (uint32_t)std::max(1, tune.extend_waves));
         CK(cudaEventRecord(w->ev_begin, stream));
-        if (tune.mode == RT_MODE_FUSED) {
+        // RT_MODE_AUTO (measured on B200, profiles/README.md): the fused persistent kernel wins where shading is cheap
+        // (book-1 scenes +20 %, mesh room +7 %); the wavefront wins with media / Perlin textures (Cornell smoke +8 %, book-2 final +56 %)
+        const int mode = tune.mode != RT_MODE_AUTO ? tune.mode : ((scene.n_media == 0 && !(scene.flags & 8u)) ? RT_MODE_FUSED : RT_MODE_WAVEFRONT);
+        if (mode == RT_MODE_FUSED) {
             k_mega_init<<<1, 32, 0, stream>>>(Q);
-            const int occ = std::max(2, std::min(4, tune.mega_occ));
+            const int occ = std::max(3, std::min(6, tune.mega_occ));
             const int mblocks = 148 * occ;
             if (media) {
-                if (occ >= 4) k_mega<true, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else if (occ == 3) k_mega<true, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<true, 2><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                if (occ >= 5) k_mega<true, 5><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (occ == 4) k_mega<true, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<true, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else {
-                if (occ >= 4) k_mega<false, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else if (occ == 3) k_mega<false, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<false, 2><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                if (occ >= 6) k_mega<false, 6><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (occ == 5) k_mega<false, 5><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (occ == 4) k_mega<false, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<false, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
             }
             CK(cudaGetLastError());
             launches += 2;

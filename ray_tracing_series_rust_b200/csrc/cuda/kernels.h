@@ -18,10 +18,11 @@ struct RenderJob {
 
 #define RT_MODE_WAVEFRONT 0 // k_extend + k_shade_all per iteration, per-material queues, path state in HBM
 #define RT_MODE_FUSED 1     // k_mega: persistent threads, path state in registers
+#define RT_MODE_AUTO (-1)    // measured rule: fused for scenes without media and without noise textures, else wavefront
 
 struct RenderTuning {
-    int mode = RT_MODE_WAVEFRONT;
-    int mega_occ = 3;               // k_mega variant: resident 128-thread blocks per SM (2 / 3 / 4)
+    int mode = RT_MODE_AUTO;
+    int mega_occ = 4;               // k_mega variant: resident 128-thread blocks per SM (3 .. 6); 4 = 128 registers, no spills
     uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
     int timed_extend = 0;           // 1: bracket every extend launch with CUDA events (for the roofline)
     int count_events = 0;           // 1: count BVH node visits / primitive tests on the device

@@ -604,6 +604,7 @@ int32_t do_commit(rt_scene* s) {
         for (const Medium& m : media) all_fast = all_fast && m.fast_type != 0;
         if (all_fast) D.flags |= 2u;
     }
+    if (!perlin.empty()) D.flags |= 8u;     // Perlin-noise textures: expensive, divergent shading
     if (tris.size() >= 4096) D.flags |= 4u; // deep triangle BVH: prefer the persistent warp-scheduled extend kernel
     if (s->camera.set) D.cam = s->camera.cam;
     for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
@@ -919,8 +920,11 @@ int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg, int64_t* d_ac
     if (stats) std::memset(stats, 0, sizeof *stats);
     const auto t0 = std::chrono::steady_clock::now();
     RenderTuning tune = s->tuning;
-    tune.timed_extend = (cfg->flags & 1) ? 1 : 0;
-    tune.count_events = (cfg->flags & 2) ? 1 : 0;
+    tune.timed_extend = (cfg->flags & RT_RENDER_TIMED_EXTEND) ? 1 : 0;
+    tune.count_events = (cfg->flags & RT_RENDER_COUNT_EVENTS) ? 1 : 0;
+    if (cfg->flags & RT_RENDER_FORCE_WAVEFRONT) tune.mode = RT_MODE_WAVEFRONT;
+    if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
+    if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
     const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats, &s->workspace);
     if (e != cudaSuccess) return fail_cuda(e, "render");
     if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -213,18 +213,18 @@ def test_determinism_wave_size_and_sharding(orc):
 
 
 @pytest.mark.parametrize("scene_id", [13, 5, 6])
-def test_fused_mode_is_bit_identical_to_wavefront(scene_id, monkeypatch):
-    # RT_MODE_FUSED (persistent k_mega) and the wavefront share device functions, Philox streams and the
-    # integer accumulator: same image bit for bit, same segment count
+def test_fused_mode_is_bit_identical_to_wavefront(scene_id):
+    # RT_RENDER_FORCE_FUSED (persistent k_mega) and RT_RENDER_FORCE_WAVEFRONT share device functions, Philox
+    # streams and the integer accumulator: same image bit for bit, same segment count
+    g = rtb.new_scene()
+    g.world_build(scene_id, 3)
+    g.commit()
     res = []
-    for mode in ("0", "1"):
-        monkeypatch.setenv("RTB200_MODE", mode)
-        g = rtb.new_scene()
-        g.world_build(scene_id, 3)
-        g.commit()
-        _, acc, st = g.render(capi.make_config(72, 1.0 if scene_id != 13 else 1.5, 6, 50, seed=4), want_accum=True)
+    for flags in (4, 8, 0):
+        _, acc, st = g.render(capi.make_config(72, 1.0 if scene_id != 13 else 1.5, 6, 50, seed=4, flags=flags), want_accum=True)
         res.append((acc, st["segments"], st["kernel_launches"]))
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
+    assert np.array_equal(res[0][0], res[2][0])  # and so is whatever RT_MODE_AUTO picks
     assert res[1][2] == 2 and res[0][2] > 2
 
 
