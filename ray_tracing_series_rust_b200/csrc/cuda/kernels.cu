@@ -168,7 +168,7 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
 }
 
 // ------------------------------------------------------------------ k_extend: world.hit(ray, 0.001, inf) for every live slot
-template <bool MEDIA, bool COUNT, int MINB>
+template <bool MEDIA, bool COUNT, int MINB, bool GENERAL_MEDIA>
 __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q, int parity) {
     uint32_t* counts = Q.counts + 8 * parity;
     uint32_t my_segments = 0;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
         uint32_t segment = 0;
         if (MEDIA) { const SlotD d = ld_stream(&P.D[slot]); path_id = d.path_id; segment = d.segment; }
         HitRec h;
-        const bool hit = world_hit<COUNT, false, MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
+        const bool hit = world_hit<COUNT, false, MEDIA, GENERAL_MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
         ++my_segments;
         uint32_t qi = Q_MISS;
         if (hit) {
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
 // two modes produce bit-identical images.
 #define RT_MEGA_CHUNK 512u
-template <bool MEDIA, int MINB>
+template <bool MEDIA, int MINB, bool GENERAL_MEDIA = true>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         if (!alive) continue;
         // ---- one ray_color iteration (world.rs:63-91)
         HitRec h;
-        const bool hit = world_hit<false, false, MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        const bool hit = world_hit<false, false, MEDIA, GENERAL_MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
         ++my_segments;
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
@@ -745,10 +745,16 @@ static void launch_extend_p(int occ, cudaStream_t st, const DeviceScene& scene, 
 
 template <bool MEDIA, bool COUNT>
 static void launch_extend(int occ, int blocks, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
-    // occ = resident 128-thread blocks per SM the kernel is compiled for (register budget 128 / 96 / 80)
-    if (occ >= 6) k_extend<MEDIA, COUNT, 6><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-    else if (occ == 5) k_extend<MEDIA, COUNT, 5><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-    else k_extend<MEDIA, COUNT, 4><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+    // occ = resident 128-thread blocks per SM the kernel is compiled for (register budget 128 / 96 / 80).
+    // Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without the general two-traversal path.
+    const bool general = MEDIA && !(scene.flags & 2u);
+    if (general) {
+        k_extend<MEDIA, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+    } else {
+        if (occ >= 6) k_extend<MEDIA, COUNT, 6, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        else if (occ == 5) k_extend<MEDIA, COUNT, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        else k_extend<MEDIA, COUNT, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+    }
 }
 
 cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const RenderTuning& tune, int64_t* d_accum, cudaStream_t stream,
@@ -794,10 +800,11 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             k_mega_init<<<1, 32, 0, stream>>>(Q);
             const int occ = std::max(3, std::min(6, tune.mega_occ));
             const int mblocks = 148 * occ;
-            if (media) {
-                if (occ >= 5) k_mega<true, 5><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else if (occ == 4) k_mega<true, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<true, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+            if (media && !(scene.flags & 2u)) {
+                k_mega<true, 3, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (media) {
+                if (occ >= 4) k_mega<true, 4, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<true, 3, false><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else {
                 if (occ >= 6) k_mega<false, 6><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else if (occ == 5) k_mega<false, 5><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);

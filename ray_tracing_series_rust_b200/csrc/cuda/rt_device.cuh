@@ -557,7 +557,7 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
 
 // world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
 // surface (order independent because medium draws are keyed).
-template <bool COUNT, bool WANT_UV, bool MEDIA>
+template <bool COUNT, bool WANT_UV, bool MEDIA, bool GENERAL_MEDIA = true>
 RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double t_max, bool media, uint64_t seed, uint64_t path_id, uint32_t segment,
                       HitRec& h, TraceCounters* cnt) {
     BestHit best;
@@ -568,7 +568,7 @@ RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double
         int32_t mwin = -1;
         D3 mp = mk3(0, 0, 0);
         if (media) {
-            for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT, true>(S, mi, ray, t_min, closest, mwin, mp, seed, path_id, segment, cnt);
+            for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<COUNT, GENERAL_MEDIA>(S, mi, ray, t_min, closest, mwin, mp, seed, path_id, segment, cnt);
         }
         if (mwin >= 0) {
             const Medium md = S.media[mwin];

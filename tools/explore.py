@@ -38,7 +38,7 @@ if __name__ == "__main__":
             run(13, 800, 1.5, 100, slots=s, label="slots")
     elif what == "modes":
         run(13, 800, 1.5, 50, label="warm")
-        for mode, occ in ((1, 4), (1, 5), (1, 6)):
+        for mode, occ in ((0, 0), (1, 4)):
             os.environ["RTB200_MODE"] = str(mode); os.environ["RTB200_MEGA_OCC"] = str(occ); os.environ["RTB200_EXTEND_OCC"] = "5"
             tag = f"mode{mode} occ{occ}"
             run(13, 800, 1.5, 500, label=f"book1 {tag}")
