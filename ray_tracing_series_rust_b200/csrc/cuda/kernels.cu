@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
         uint32_t segment = 0;
         if (MEDIA) { const SlotD d = ld_stream(&P.D[slot]); path_id = d.path_id; segment = d.segment; }
         HitRec h;
-        const bool hit = world_hit<COUNT, false, MEDIA, GENERAL_MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
+        const bool hit = world_hit<COUNT, 2, MEDIA, GENERAL_MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
         ++my_segments;
         uint32_t qi = Q_MISS;
         if (hit) {
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend_p(const __grid_constant__ 
                                 hit = true;
                             }
                         }
-                        if (!hit && best.type != RT_NONE) { h = finalize_hit<false>(S, wr, best); hit = true; }
+                        if (!hit && best.type != RT_NONE) { h = finalize_hit<2>(S, wr, best); hit = true; }
                         uint32_t qi = Q_MISS;
                         if (hit) {
                             SlotA na; na.ox = h.p.x; na.oy = h.p.y; na.oz = h.p.z; na.time = a.time;
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
 // two modes produce bit-identical images.
 #define RT_MEGA_CHUNK 512u
-template <bool MEDIA, int MINB, bool GENERAL_MEDIA = true>
+template <bool MEDIA, int MINB, bool GENERAL_MEDIA, bool FULLTEX>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         if (!alive) continue;
         // ---- one ray_color iteration (world.rs:63-91)
         HitRec h;
-        const bool hit = world_hit<false, false, MEDIA, GENERAL_MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        const bool hit = world_hit<false, FULLTEX ? 2 : 0, MEDIA, GENERAL_MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
         ++my_segments;
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         } else {
             const DMaterial m = S.materials[h.mat];
             if (m.type == MAT_LIGHT) {
-                const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
+                const F3 e = tex_value<FULLTEX>(S, m.tex, h.u, h.v, h.p);
                 contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
             } else {
                 PathRng g;
@@ -548,10 +548,10 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
                 bool scattered;
-                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian<FULLTEX>(S, m, h.p, h.n, h.u, h.v, g, dir, att);
                 else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
                 else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
-                else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                else scattered = scatter_isotropic<FULLTEX>(S, m, h.p, h.u, h.v, g, dir, att);
                 if (scattered && (int32_t)(segment + 1) < J.max_depth) {
                     tr *= att.x; tg *= att.y; tb *= att.z;
                     r.o = h.p; r.d = dir;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Dev
         r.d = mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
         r.time = rays[i].time;
         HitRec h;
-        const bool hit = world_hit<false, true, true>(S, r, t_min, t_max, (flags & RT_TRACE_SEEDED_MEDIA) != 0, seed, (uint64_t)i, 0u, h, nullptr);
+        const bool hit = world_hit<false, 1, true>(S, r, t_min, t_max, (flags & RT_TRACE_SEEDED_MEDIA) != 0, seed, (uint64_t)i, 0u, h, nullptr);
         rt_hit o;
         if (hit) {
             o.prim_id = (int32_t)h.prim_id; o.mat_id = (int32_t)h.mat; o.t = h.t;
@@ -800,16 +800,22 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             k_mega_init<<<1, 32, 0, stream>>>(Q);
             const int occ = std::max(3, std::min(6, tune.mega_occ));
             const int mblocks = 148 * occ;
+            // Measured (tools/explore.py ab RTB200_FULLTEX 0,1): the variant WITHOUT the Noise/Image texture code is 15 % slower on
+            // the book-1 scene (154.5 vs 134.4 ms; same 128 registers, no spills - a code-layout effect), so the full variant is the default.
+            const bool fulltex = tune.force_fulltex != 0 || (scene.flags & (8u | 16u)) != 0;
             if (media && !(scene.flags & 2u)) {
-                k_mega<true, 3, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+                k_mega<true, 3, true, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (media) {
-                if (occ >= 4) k_mega<true, 4, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<true, 3, false><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+                if (occ >= 4) k_mega<true, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<true, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (fulltex) {
+                if (occ >= 4) k_mega<false, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<false, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else {
-                if (occ >= 6) k_mega<false, 6><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else if (occ == 5) k_mega<false, 5><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else if (occ == 4) k_mega<false, 4><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<false, 3><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                if (occ >= 6) k_mega<false, 6, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (occ == 5) k_mega<false, 5, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (occ == 4) k_mega<false, 4, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<false, 3, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
             }
             CK(cudaGetLastError());
             launches += 2;

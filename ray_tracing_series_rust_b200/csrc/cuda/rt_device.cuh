@@ -407,7 +407,9 @@ RT_DEV void sphere_uv(D3 p, double& u, double& v) { // hit.rs:195-200
 // Rebuild the full HitRecord of the winning primitive, then undo the wrapper chain from the inside
 // out exactly as Translate::hit / RotateY::hit do (hit.rs:808-820, 909-930), including their
 // re-face-forwarding quirks.
-template <bool WANT_UV>
+// UVMODE: 0 = never compute sphere (u,v) (the scene has no image texture), 1 = always (parity hook),
+// 2 = when the hit material's texture chain reads them
+template <int UVMODE>
 RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const BestHit& b) {
     HitRec h;
     const Instance* ip = &S.instances[b.inst];
@@ -425,9 +427,11 @@ RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const Bes
     case PRIM_SPHERE: {
         const DSphere s = S.spheres[b.idx];
         outward = (h.p - mk3(s.cx, s.cy, s.cz)) * (1.0 / s.r);
-        bool need_uv = WANT_UV;
-        if (!WANT_UV) need_uv = (__ldg(&S.materials[m.mat_id].flags) & 1u) != 0;
-        if (need_uv) sphere_uv(outward, h.u, h.v);
+        if (UVMODE != 0) {
+            bool need_uv = UVMODE == 1;
+            if (UVMODE == 2) need_uv = (__ldg(&S.materials[m.mat_id].flags) & 1u) != 0;
+            if (need_uv) sphere_uv(outward, h.u, h.v);
+        }
     } break;
     case PRIM_MOVING: {
         const DMoving s = S.movings[b.idx];
@@ -557,7 +561,7 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
 
 // world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
 // surface (order independent because medium draws are keyed).
-template <bool COUNT, bool WANT_UV, bool MEDIA, bool GENERAL_MEDIA = true>
+template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true>
 RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double t_max, bool media, uint64_t seed, uint64_t path_id, uint32_t segment,
                       HitRec& h, TraceCounters* cnt) {
     BestHit best;
@@ -578,7 +582,7 @@ RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double
         }
     }
     if (best.type == RT_NONE) return false;
-    h = finalize_hit<WANT_UV>(S, ray, best);
+    h = finalize_hit<UVMODE>(S, ray, best);
     return true;
 }
 
@@ -616,6 +620,9 @@ RT_DEV double perlin_turbulence(const PerlinTable* __restrict__ pt, D3 p, int de
     return fabs(accum);
 }
 
+// FULL = false compiles only SolidColor and Checker (kernels picked for scenes without Noise / Image
+// textures: the Perlin and image code would only cost instruction-cache space)
+template <bool FULL = true>
 RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p) { // texture.rs:7-9
     for (int guard = 0; guard < 64; ++guard) {
         const DTexture* t = &S.textures[tex];
@@ -626,6 +633,7 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
             tex = sines < 0.0f ? __ldg(&t->b) : __ldg(&t->a);
             continue;
         }
+        if (!FULL) break;
         if (type == TEX_NOISE) { // texture.rs:80-88
             const double s = 0.5 * (1.0 + sin(t->scale * p.z + 10.0 * perlin_turbulence(&S.perlin[t->a], p, 7)));
             return mkf3((float)s, (float)s, (float)s);
@@ -646,11 +654,12 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
 
 // ------------------------------------------------------------------ Material::scatter (hit.rs:1004-1152)
 // Returns true when the path continues; `dir` = scattered direction, `att` = attenuation.
+template <bool FULLTEX = true>
 RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, PathRng& g, D3& dir, F3& att) {
     D3 sd = n + random_unit_vector(g);
     if (near_zero(sd)) sd = n;
     dir = sd;
-    att = tex_value(S, m.tex, u, v, p);
+    att = tex_value<FULLTEX>(S, m.tex, u, v, p);
     return true;
 }
 RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, PathRng& g, D3& dir, F3& att) {
@@ -676,9 +685,10 @@ RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D3 n, bool front, Pa
     else dir = refract(ud, n, ratio);
     return true;
 }
+template <bool FULLTEX = true>
 RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, PathRng& g, D3& dir, F3& att) {
     dir = random_in_unit_sphere(g); // not normalised (hit.rs:1007)
-    att = tex_value(S, m.tex, u, v, p);
+    att = tex_value<FULLTEX>(S, m.tex, u, v, p);
     return true;
 }
 

@@ -605,6 +605,7 @@ int32_t do_commit(rt_scene* s) {
         if (all_fast) D.flags |= 2u;
     }
     if (!perlin.empty()) D.flags |= 8u;     // Perlin-noise textures: expensive, divergent shading
+    if (!texels.empty()) D.flags |= 16u;    // image textures (sphere uv needed)
     if (tris.size() >= 4096) D.flags |= 4u; // deep triangle BVH: prefer the persistent warp-scheduled extend kernel
     if (s->camera.set) D.cam = s->camera.cam;
     for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
@@ -625,6 +626,7 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_EXTEND_WAVES"))) s->tuning.extend_waves = std::atoi(e);
     if ((e = std::getenv("RTB200_MODE"))) s->tuning.mode = std::atoi(e);
     if ((e = std::getenv("RTB200_EXTEND_KIND"))) s->tuning.extend_kind = std::atoi(e);
+    if ((e = std::getenv("RTB200_FULLTEX"))) s->tuning.force_fulltex = std::atoi(e);
     if ((e = std::getenv("RTB200_MEGA_OCC"))) s->tuning.mega_occ = std::atoi(e);
     return s;
 }

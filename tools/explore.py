@@ -66,6 +66,16 @@ if __name__ == "__main__":
             run(5, 600, 1.0, 200, label=f"smoke {tag}")
             run(6, 1000, 1.0, 50, label=f"book2 {tag}")
             run(14, 1000, 1.0, 10, param=660, label=f"mesh871k {tag}")
+    elif what == "ab":
+        # A/B inside one process (same GPU, same clocks): env var name, values, scenes
+        var = sys.argv[2]; vals = sys.argv[3].split(",")
+        run(13, 800, 1.5, 50, label="warm")
+        for rep in range(2):
+            for v in vals:
+                os.environ[var] = v
+                run(13, 800, 1.5, 500, label=f"book1 {var}={v} #{rep}")
+                run(99, 800, 1.5, 200, label=f"book1b {var}={v} #{rep}")
+                run(14, 1000, 1.0, 10, param=660, label=f"mesh {var}={v} #{rep}")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")

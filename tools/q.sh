@@ -1,6 +1,6 @@
 #!/bin/bash
 # prints one compact line per explore.py result
-python tools/explore.py ${1:-all} 2>&1 | python -c "
+python tools/explore.py ${1:-all} ${2:-} ${3:-} 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     try: d=json.loads(l)
