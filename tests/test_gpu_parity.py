@@ -81,6 +81,95 @@ def test_E1_interval_ends_and_ties(orc):
         assert hg["prim_id"][0] == ho["prim_id"][0]
 
 
+def test_E1_shared_objects_and_nested_chains(orc):
+    # Arc sharing (one object reached through several wrappers), wrapper chains of depth 3, a rotated
+    # instance that is NOT wrapped in a Translate (so RotateY's object-space face-forwarding quirk,
+    # hit.rs:921, is visible in the normal), a BVH of transformed children and a general medium boundary.
+    def build(s):
+        m = s.lambertian((0.5, 0.5, 0.5))
+        glass = s.dielectric(1.5)
+        sph = s.sphere((0, 0, 0), 1.0, glass)
+        box = s.box((-1, -1, -1), (1, 2, 1.5), m)
+        tri = s.triangle((0, 0, 0), (2, 0, 0.5), (0, 2, 1), m)
+        group = s.list([sph, s.translate((3, 0, 0), box)])
+        a = s.translate((-6, 0, 0), s.rotate_y(30, s.translate((0, 1, 0), group)))
+        b = s.rotate_y(-50, s.list([box, tri]))                        # bare RotateY
+        c = s.translate((6, 0, 2), group)                              # the same group again (shared)
+        d = s.bvh([s.translate((0, 5, 0), sph), s.translate((0, -5, 0), box), s.sphere((0, 0, 8), 2.0, m)], 0, 1)
+        med = s.constant_medium((1, 1, 1), 0.3, s.list([s.sphere((0, 0, -8), 2.0, m), s.sphere((1, 0, -8), 2.0, m)]))  # general boundary
+        s.set_root(s.list([a, b, c, d, med]))
+        s.set_camera((0, 3, 25), (0, 0, 0), (0, 1, 0), 40, 1.5, 0.0, 10, 0, 1)
+        s.commit()
+    g, o = rtb.new_scene(), orc.new_scene()
+    build(g); build(o)
+    assert g.num_prims() == o.num_prims() == 1 + 6 + 1 + 1 + 1 + 2
+    cam = pu.camera_fields(orc, o)
+    for rays in (pu.primary_rays(cam, 200, 130), pu.random_rays(80000, -12.0, 12.0, seed=21)):
+        hg, ho = g.trace_batch(rays), o.trace_batch(rays)
+        r = pu.assert_parity(hg, ho, "shared/nested")
+        assert r["hits"] > 3000
+        assert len(set(np.unique(ho["prim_id"])) - {-1}) >= 6
+        hg = g.trace_batch(rays, flags=capi.RT_TRACE_SEEDED_MEDIA, seed=5)
+        ho = o.trace_batch(rays, flags=capi.RT_TRACE_SEEDED_MEDIA, seed=5)
+        pu.assert_parity(hg, ho, "shared/nested + general medium")
+        assert (ho["prim_id"] == 9).sum() > 10  # the medium itself produced records
+    # and the render goes through the general-medium kernels (wavefront and fused) identically
+    cfg = capi.make_config(60, 1.5, 6, 20, seed=8)
+    sg, ag, stg = g.render(cfg, want_accum=True)
+    so, ao, sto = o.render(cfg, want_accum=True)
+    assert (np.abs(ag - ao) > 1e-5 * np.maximum(np.abs(ao), 2.0 ** 22)).any(axis=2).mean() < 0.02
+    _, af, _ = g.render(capi.make_config(60, 1.5, 6, 20, seed=8, flags=8), want_accum=True)
+    assert np.array_equal(ag, af)
+
+
+def test_documented_divergence_rotate_y_bbox_inside_bvh(orc):
+    # DESIGN.md divergence 4: RotateY::new computes the rotated corner bounds and then stores the UN-rotated
+    # box (hit.rs:886), so inside a reference BvhNode the corners of a rotated object that stick out of
+    # its un-rotated box are culled away.  The GPU path bounds the rotated object correctly: wherever the
+    # two disagree (beyond edge ties), the GPU sees the box and the reference sees through it.
+    def build(s):
+        m = s.lambertian((0.5, 0.5, 0.5))
+        s.set_root(s.bvh([s.rotate_y(45, s.box((-2, -1, -2), (2, 1, 2), m))], 0, 1))  # single-object node: bbox = the un-rotated box
+        s.set_camera((1, 4, 12), (0, 0, 0), (0, 1, 0), 40, 1.5, 0.0, 10, 0, 1)
+        s.commit()
+    g, o = rtb.new_scene(), orc.new_scene()
+    build(g); build(o)
+    rays = pu.primary_rays(pu.camera_fields(orc, o), 300, 200)
+    hg, ho = g.trace_batch(rays), o.trace_batch(rays)
+    diff = hg["prim_id"] != ho["prim_id"]
+    assert 50 < diff.sum() < 0.1 * rays.shape[0]
+    assert np.all(hg["prim_id"][diff] >= 0) and np.all(hg["prim_id"][diff] < 6)  # the GPU hits a side of the box ...
+    assert np.all(ho["prim_id"][diff] == -1)                                      # ... the reference sees through its corners
+    px = hg["p"][diff]
+    assert np.all(np.maximum(np.abs(px[:, 0]), np.abs(px[:, 2])) > 2.0 - 1e-9)     # only outside the un-rotated box
+    same = ~diff & (ho["prim_id"] >= 0)
+    assert same.sum() > 1000 and np.allclose(hg["t"][same], ho["t"][same], rtol=1e-12)
+
+
+def test_empty_world_and_edge_configs(orc):
+    # an empty HittableList never hits (hit.rs:660-690): every pixel is the background
+    g = rtb.new_scene()
+    g.set_root(g.list([]))
+    g.set_camera((0, 0, 5), (0, 0, 0), (0, 1, 0), 40, 1.0, 0.0, 10, 0, 1)
+    g.set_background((0.25, 0.5, 1.0))
+    g.commit()
+    scr, acc, st = g.render(capi.make_config(16, 1.0, 3, 5, seed=1), want_accum=True)
+    assert st["segments"] == st["paths"] == 16 * 16 * 3
+    assert np.all(scr == np.floor(255.9 * np.sqrt([0.25, 0.5, 1.0])))
+    h = g.trace_batch(capi.make_rays([(0, 0, 0)], [(0, 0, 1)]))
+    assert h["prim_id"][0] == -1
+    assert g.trace_batch(np.zeros(0, dtype=capi.RAY_DTYPE)).shape == (0,)
+    # Config::new asserts (world.rs:36-40) and bad sample ranges surface as errors, not crashes
+    for bad in (capi.make_config(0, 1.0, 1, 1), capi.make_config(8, 1.0, 0, 1), capi.make_config(8, 1.0, 1, 0),
+                capi.make_config(8, 1.0, 4, 5, sample_begin=3, sample_end=2), capi.make_config(8, 1.0, 4, 5, sample_end=9)):
+        with pytest.raises(capi.RtError):
+            g.render(bad)
+    # 1 spp, depth 1, odd sizes: exact path count, background only where nothing is hit
+    g2, o2 = pu.build_pair(orc, 4)
+    sg, ag, stg, so, ao, sto = render_pair(g2, o2, 37, 1.0, 1, 1)
+    assert stg["paths"] == sto["paths"] == 37 * 37 and np.array_equal(sg, so)
+
+
 @pytest.mark.parametrize("scene_id", [5, 6])
 def test_seeded_media_parity(orc, scene_id):
     g, o = pu.build_pair(orc, scene_id)
