@@ -72,6 +72,7 @@ enum MatType { MT_LAMBERTIAN = 0, MT_METAL = 1, MT_DIELECTRIC = 2, MT_LIGHT = 3,
 // ------------------------------------------------------------------ per-path RNG context
 // Stands in for every `thread_rng()` call site of the reference.  Draw k of a path is word k&3
 // of Philox block (path_lo, path_hi, k>>2, 0) under key (seed_lo, seed_hi); xi = u32 * 2^-32.
+// Each Material::scatter starts on a block boundary (begin_event).
 // ConstantMedium draws come from the order-independent sub-stream
 // (path_lo, path_hi, medium prim id, 0x80000000 | segment).
 struct PathCtx {
@@ -98,6 +99,10 @@ struct PathCtx {
         }
         return blk[draw++ & 3u];
     }
+    // Every Material::scatter call starts at the next multiple-of-4 draw index, i.e. on a fresh Philox
+    // block (part of the RNG contract shared with the GPU path: the block a scatter needs first is known
+    // before its rejection loop starts; at most 3 words per bounce are skipped).
+    void begin_event() { draw = (draw + 3u) & ~3u; }
     // rng.gen::<f64>()  -> uniform [0,1)
     double gen() { return (double)next_u32() * (1.0 / 4294967296.0); }
     // rng.gen_range(a..b) on f64
@@ -717,6 +722,7 @@ struct Isotropic : Material {
     explicit Isotropic(TexturePtr a) : albedo(a) {}
     bool scatter(const Ray& r_in, const HitRecord& rec, Ray& scattered, Color& attenuation) const override { // hit.rs:1004-1011
         ctx().cnt.scatters[MT_ISOTROPIC]++;
+        ctx().begin_event();
         scattered = Ray(rec.p, random_in_unit_sphere(), r_in.time);
         attenuation = albedo->value(rec.u, rec.v, rec.p);
         return true;
@@ -727,6 +733,7 @@ struct Lambertian : Material {
     explicit Lambertian(TexturePtr a) : albedo(a) {}
     bool scatter(const Ray& r_in, const HitRecord& rec, Ray& scattered, Color& attenuation) const override { // hit.rs:1039-1051
         ctx().cnt.scatters[MT_LAMBERTIAN]++;
+        ctx().begin_event();
         Vec3 scatter_direction = rec.normal + random_unit_vector();
         if (scatter_direction.near_zero()) scatter_direction = rec.normal;
         scattered = Ray(rec.p, scatter_direction, r_in.time);
@@ -740,6 +747,7 @@ struct Metal : Material {
     Metal(const Color& a, double f) : albedo(a), fuzz(f < 1.0 ? f : 1.0) {} // hit.rs:1060-1065
     bool scatter(const Ray& r_in, const HitRecord& rec, Ray& scattered, Color& attenuation) const override { // hit.rs:1069-1083
         ctx().cnt.scatters[MT_METAL]++;
+        ctx().begin_event();
         const Vec3 reflected = r_in.direction.unit().reflect(rec.normal);
         scattered = Ray(rec.p, reflected + fuzz * random_in_unit_sphere(), r_in.time);
         if (scattered.direction.dot(rec.normal) > 0.0) {
@@ -760,6 +768,7 @@ struct Dielectric : Material {
     }
     bool scatter(const Ray& r_in, const HitRecord& rec, Ray& scattered, Color& attenuation) const override { // hit.rs:1103-1126
         ctx().cnt.scatters[MT_DIELECTRIC]++;
+        ctx().begin_event();
         attenuation = Vec3(1, 1, 1);
         const double refraction_ratio = rec.front_face ? 1.0 / ir : ir;
         const Vec3 unit_direction = r_in.direction.unit();

@@ -442,7 +442,6 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
             } else {
                 PathRng g;
                 g.init(J.seed, sd.path_id, sd.draw);
-                g.prefetch2();
                 const D3 n3 = mk3(sc.nx, sc.ny, sc.nz);
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);

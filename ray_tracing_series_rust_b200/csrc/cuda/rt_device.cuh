@@ -65,7 +65,7 @@ RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 
 // Draw k of a path = word (k & 3) of block (path_lo, path_hi, k >> 2, 0) under key (seed_lo, seed_hi);
-// xi = u32 * 2^-32 (identical in oracle/rt_oracle.hpp PathCtx).
+// xi = u32 * 2^-32 (identical in oracle/rt_oracle.hpp PathCtx); scatters start on block boundaries.
 struct PathRng {
     uint2 key, path;
     uint32_t draw, cached; // cached = index of the block held in blk; blk2 holds block cached + 1 when have2
@@ -76,6 +76,16 @@ struct PathRng {
         path = make_uint2((uint32_t)path_id, (uint32_t)(path_id >> 32));
         draw = draw0;
         cached = 0xffffffffu;
+        have2 = false;
+    }
+    // RNG contract: every Material::scatter starts at the next multiple-of-4 draw index (as PathCtx::begin_event
+    // in the oracle).  The first block of the event is generated right here, while all lanes of the material
+    // branch are still together, instead of inside the diverged rejection loop.
+    RT_DEV void begin_event() {
+        draw = (draw + 3u) & ~3u;
+        const uint32_t b = draw >> 2;
+        blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
+        cached = b;
         have2 = false;
     }
     // Compute the next two blocks now, while the warp is converged: the rejection loops that consume
@@ -656,6 +666,7 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
 // Returns true when the path continues; `dir` = scattered direction, `att` = attenuation.
 template <bool FULLTEX = true>
 RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, PathRng& g, D3& dir, F3& att) {
+    g.begin_event();
     D3 sd = n + random_unit_vector(g);
     if (near_zero(sd)) sd = n;
     dir = sd;
@@ -663,6 +674,7 @@ RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D
     return true;
 }
 RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, PathRng& g, D3& dir, F3& att) {
+    g.begin_event();
     const D3 reflected = reflect(unit(d_in), n);
     dir = reflected + m.fuzz_or_ir * random_in_unit_sphere(g); // the draw happens even when fuzz == 0
     att = mkf3(m.albedo[0], m.albedo[1], m.albedo[2]);
@@ -675,6 +687,7 @@ RT_DEV double reflectance(double cosine, double ref_idx) { // hit.rs:1095-1099
     return r0 + (1.0 - r0) * (x * x * x * x * x);
 }
 RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D3 n, bool front, PathRng& g, D3& dir, F3& att) {
+    g.begin_event();
     att = mkf3(1.f, 1.f, 1.f);
     const double ratio = front ? 1.0 / m.fuzz_or_ir : m.fuzz_or_ir;
     const D3 ud = unit(d_in);
@@ -687,6 +700,7 @@ RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D3 n, bool front, Pa
 }
 template <bool FULLTEX = true>
 RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, PathRng& g, D3& dir, F3& att) {
+    g.begin_event();
     dir = random_in_unit_sphere(g); // not normalised (hit.rs:1007)
     att = tex_value<FULLTEX>(S, m.tex, u, v, p);
     return true;

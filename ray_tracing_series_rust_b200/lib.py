@@ -9,7 +9,7 @@ from . import capi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+LIB_PATH = os.environ.get("RTB200_LIB") or os.path.join(_HERE, "librtb200.so")  # RTB200_LIB: A/B another build of the same library
 
 _api = None
 
