@@ -301,12 +301,12 @@ def test_determinism_wave_size_and_sharding(orc):
     assert not np.array_equal(a1, a4)
 
 
-@pytest.mark.parametrize("scene_id", [13, 5, 6])
+@pytest.mark.parametrize("scene_id", [13, 5, 6, 14])
 def test_fused_mode_is_bit_identical_to_wavefront(scene_id):
     # RT_RENDER_FORCE_FUSED (persistent k_mega) and RT_RENDER_FORCE_WAVEFRONT share device functions, Philox
     # streams and the integer accumulator: same image bit for bit, same segment count
     g = rtb.new_scene()
-    g.world_build(scene_id, 3)
+    g.world_build(scene_id, 3, 48 if scene_id == 14 else 0)  # 14: 4608 triangles => the wavefront uses the warp-scheduled k_extend_p
     g.commit()
     res = []
     for flags in (4, 8, 0):
