@@ -289,18 +289,23 @@ struct TraceCounters {
     uint32_t nodes, prims;
 };
 
+// PM = compile-time mask of the primitive types the scene can contain (bit = PrimType): kernels specialised
+// for "spheres only" etc. drop the other tests from the hot loop.
+#define RT_PM_ALL 0x3fu
+#define RT_PM_HAS(PM, T) (((PM) >> (T)) & 1u)
 // Tests every primitive of one leaf against the object-space ray.
+template <uint32_t PM = RT_PM_ALL>
 RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, const RayPre& pre, double t_min, BestHit& best, uint32_t type, uint32_t first, uint32_t n,
                       uint32_t inst) {
     for (uint32_t i = first; i < first + n; ++i) {
-        if (type <= PRIM_GRAVITY) { // the three sphere kinds share the root solve (hit.rs:204-222, 282-300, 398-416)
+        if ((PM & 7u) && ((PM & ~7u) == 0 || type <= PRIM_GRAVITY)) { // the three sphere kinds share the root solve (hit.rs:204-222, 282-300, 398-416)
             D3 c;
             double rad;
-            if (type == PRIM_SPHERE) {
+            if (RT_PM_HAS(PM, PRIM_SPHERE) && ((PM & 6u) == 0 || type == PRIM_SPHERE)) {
                 const double2 a = __ldg(reinterpret_cast<const double2*>(&S.spheres[i]));
                 const double2 b = __ldg(reinterpret_cast<const double2*>(&S.spheres[i]) + 1);
                 c = mk3(a.x, a.y, b.x); rad = b.y;
-            } else if (type == PRIM_MOVING) {
+            } else if (RT_PM_HAS(PM, PRIM_MOVING) && (!RT_PM_HAS(PM, PRIM_GRAVITY) || type == PRIM_MOVING)) {
                 const DMoving m = S.movings[i];
                 c = moving_center(m, r.time); rad = m.r;
             } else {
@@ -308,15 +313,15 @@ RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, const RayPre& pre, dou
                 c = gravity_center(S, g, r.time); rad = g.r;
             }
             consider(S, best, sphere_root(r, pre, c, rad, t_min, best.t), type, i, 0, inst);
-        } else if (type == PRIM_RECT) {
+        } else if (RT_PM_HAS(PM, PRIM_RECT) && type == PRIM_RECT) {
             const DRect q = S.rects[i];
             consider(S, best, rect_t(r, pre, q, t_min, best.t), type, i, 0, inst);
-        } else if (type == PRIM_BOX) {
+        } else if (RT_PM_HAS(PM, PRIM_BOX) && type == PRIM_BOX) {
             const DBox b = S.boxes[i];
             uint32_t side;
             const double t = box_t(r, pre, b, t_min, best.t, side);
             consider(S, best, t, type, i, side, inst);
-        } else { // PRIM_TRI
+        } else if (RT_PM_HAS(PM, PRIM_TRI)) { // PRIM_TRI
             consider(S, best, tri_t(r, &S.tris[i], t_min, best.t), type, i, 0, inst);
         }
     }
@@ -328,10 +333,10 @@ RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, const RayPre& pre, dou
 // only when every lane of the warp has left that inner loop are the leaves processed, so the expensive
 // f64 primitive tests run with as many lanes active as possible.  The instance root is stored as the
 // first node of a sibling pair whose second node is an empty leaf, so the root needs no special case.
-template <bool COUNT>
+template <bool COUNT, uint32_t PM = RT_PM_ALL>
 RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r, double t_min, BestHit& best, TraceCounters* cnt) {
     const RayF f = make_rayf(r);
-    const RayPre pre = make_raypre(r, (S.flags & 1u) != 0);
+    const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
     const float tminf = f32_down(t_min);
     float tmaxf = f32_up(best.t);
     const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
@@ -369,7 +374,7 @@ RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r
             const uint32_t lc = k ? leaf_cnt1 : leaf_cnt0, lf = k ? leaf_first1 : leaf_first0;
             if (lc & 0xffffffu) {
                 if (COUNT) cnt->prims += lc & 0xffffffu;
-                leaf_test(S, r, pre, t_min, best, lc >> 24, lf, lc & 0xffffffu, inst_idx);
+                leaf_test<PM>(S, r, pre, t_min, best, lc >> 24, lf, lc & 0xffffffu, inst_idx);
             }
         }
         tmaxf = f32_up(best.t);
@@ -385,13 +390,13 @@ RT_DEV bool inst_box_hit(const Instance* ip, const Ray& r, double t_min, double 
 }
 
 // world.hit restricted to the instances [i0, i1): the main world or one medium's boundary.
-template <bool COUNT>
+template <bool COUNT, uint32_t PM = RT_PM_ALL>
 RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, const Ray& world_ray, double t_min, BestHit& best, TraceCounters* cnt) {
     for (uint32_t i = i0; i < i1; ++i) {
         const Instance* ip = &S.instances[i];
         Ray r = world_ray;
         xform_ray(S.ops, __ldg(&ip->chain_off), __ldg(&ip->chain_len), r);
-        trace_instance<COUNT>(S, i, r, t_min, best, cnt);
+        trace_instance<COUNT, PM>(S, i, r, t_min, best, cnt);
     }
 }
 
@@ -419,7 +424,7 @@ RT_DEV void sphere_uv(D3 p, double& u, double& v) { // hit.rs:195-200
 // re-face-forwarding quirks.
 // UVMODE: 0 = never compute sphere (u,v) (the scene has no image texture), 1 = always (parity hook),
 // 2 = when the hit material's texture chain reads them
-template <int UVMODE>
+template <int UVMODE, uint32_t PM = RT_PM_ALL>
 RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const BestHit& b) {
     HitRec h;
     const Instance* ip = &S.instances[b.inst];
@@ -432,9 +437,9 @@ RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const Bes
     h.t = b.t;
     h.p = ray_at(r, b.t);
     h.u = 0.0; h.v = 0.0;
-    D3 outward;
-    switch (b.type) {
-    case PRIM_SPHERE: {
+    D3 outward = mk3(0, 1, 0);
+    const uint32_t ty = b.type;
+    if (RT_PM_HAS(PM, PRIM_SPHERE) && ((PM & ~1u) == 0 || ty == PRIM_SPHERE)) {
         const DSphere s = S.spheres[b.idx];
         outward = (h.p - mk3(s.cx, s.cy, s.cz)) * (1.0 / s.r);
         if (UVMODE != 0) {
@@ -442,36 +447,30 @@ RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const Bes
             if (UVMODE == 2) need_uv = (__ldg(&S.materials[m.mat_id].flags) & 1u) != 0;
             if (need_uv) sphere_uv(outward, h.u, h.v);
         }
-    } break;
-    case PRIM_MOVING: {
+    } else if (RT_PM_HAS(PM, PRIM_MOVING) && ty == PRIM_MOVING) {
         const DMoving s = S.movings[b.idx];
         outward = (h.p - moving_center(s, r.time)) * (1.0 / s.r); // u = v = 0 (hit.rs:310-311)
-    } break;
-    case PRIM_GRAVITY: {
+    } else if (RT_PM_HAS(PM, PRIM_GRAVITY) && ty == PRIM_GRAVITY) {
         const DGravity s = S.gravities[b.idx];
         outward = (h.p - gravity_center(S, s, r.time)) * (1.0 / s.r);
-    } break;
-    case PRIM_RECT: {
+    } else if (RT_PM_HAS(PM, PRIM_RECT) && ty == PRIM_RECT) {
         const DRect q = S.rects[b.idx];
         const int ax = q.axis, ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
         h.u = (axis_of(h.p, ia) - q.a0) / (q.a1 - q.a0); // hit.rs:486-487 (x, y recomputed as o + t*d = p)
         h.v = (axis_of(h.p, ib) - q.b0) / (q.b1 - q.b0);
         outward = mk3(ax == 0 ? 1.0 : 0.0, ax == 1 ? 1.0 : 0.0, ax == 2 ? 1.0 : 0.0);
-    } break;
-    case PRIM_BOX: {
+    } else if (RT_PM_HAS(PM, PRIM_BOX) && ty == PRIM_BOX) {
         const DBox q = S.boxes[b.idx];
         const int s = (int)b.side;
         const int ax = s < 2 ? 2 : (s < 4 ? 1 : 0), ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
         h.u = (axis_of(h.p, ia) - q.p0[ia]) / (q.p1[ia] - q.p0[ia]);
         h.v = (axis_of(h.p, ib) - q.p0[ib]) / (q.p1[ib] - q.p0[ib]);
         outward = mk3(ax == 0 ? 1.0 : 0.0, ax == 1 ? 1.0 : 0.0, ax == 2 ? 1.0 : 0.0);
-    } break;
-    default: { // PRIM_TRI: u = v = 1 (hit.rs:157-158)
+    } else if (RT_PM_HAS(PM, PRIM_TRI)) { // PRIM_TRI: u = v = 1 (hit.rs:157-158)
         const DTri* tp = &S.tris[b.idx];
         const float4 q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
         outward = mk3(q2.y, q2.z, q2.w);
         h.u = 1.0; h.v = 1.0;
-    } break;
     }
     face_forward(r.d, outward, h.n, h.front);
     // unwind the chain: r currently holds the innermost ray
@@ -571,12 +570,12 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
 
 // world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
 // surface (order independent because medium draws are keyed).
-template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true>
+template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true, uint32_t PM = RT_PM_ALL>
 RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double t_max, bool media, uint64_t seed, uint64_t path_id, uint32_t segment,
                       HitRec& h, TraceCounters* cnt) {
     BestHit best;
     best_init(best, t_max);
-    trace_instances<COUNT>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
+    trace_instances<COUNT, PM>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
     if (MEDIA) {
         double closest = best.t;
         int32_t mwin = -1;
@@ -592,7 +591,7 @@ RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double
         }
     }
     if (best.type == RT_NONE) return false;
-    h = finalize_hit<UVMODE>(S, ray, best);
+    h = finalize_hit<UVMODE, PM>(S, ray, best);
     return true;
 }
 

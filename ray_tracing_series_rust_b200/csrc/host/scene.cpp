@@ -598,6 +598,8 @@ int32_t do_commit(rt_scene* s) {
     D.n_main_instances = HF.n_main_instances;
     D.n_media = (uint32_t)media.size();
     D.n_prims = (uint32_t)s->n_prims;
+    D.prim_mask = (spheres.empty() ? 0u : 1u) | (movings.empty() ? 0u : 2u) | (gravities.empty() ? 0u : 4u) | (rects.empty() ? 0u : 8u) |
+                  (boxes.empty() ? 0u : 16u) | (tris.empty() ? 0u : 32u);
     D.flags = (!rects.empty() || !boxes.empty()) ? 1u : 0u;
     {
         bool all_fast = true;
@@ -627,6 +629,7 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_MODE"))) s->tuning.mode = std::atoi(e);
     if ((e = std::getenv("RTB200_EXTEND_KIND"))) s->tuning.extend_kind = std::atoi(e);
     if ((e = std::getenv("RTB200_FULLTEX"))) s->tuning.force_fulltex = std::atoi(e);
+    if ((e = std::getenv("RTB200_PRIM_SPECIALISE"))) s->tuning.prim_specialise = std::atoi(e);
     if ((e = std::getenv("RTB200_MEGA_OCC"))) s->tuning.mega_occ = std::atoi(e);
     return s;
 }

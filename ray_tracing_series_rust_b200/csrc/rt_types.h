@@ -120,6 +120,8 @@ struct DeviceScene {
     const DTexture* textures;
     const PerlinTable* perlin;
     const float4* texels; // rgba f32, row 0 = top of file
+    uint32_t prim_mask; // bit t set: primitives of PrimType t exist
+    uint32_t pad0_;
     uint32_t n_main_instances;
     uint32_t n_media;
     uint32_t n_prims;
