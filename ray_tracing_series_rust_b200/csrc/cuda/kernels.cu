@@ -168,7 +168,7 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
 }
 
 // ------------------------------------------------------------------ k_extend: world.hit(ray, 0.001, inf) for every live slot
-template <bool MEDIA, bool COUNT, int MINB, bool GENERAL_MEDIA>
+template <bool MEDIA, bool COUNT, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL>
 __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q, int parity) {
     uint32_t* counts = Q.counts + 8 * parity;
     uint32_t my_segments = 0;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
         uint32_t segment = 0;
         if (MEDIA) { const SlotD d = ld_stream(&P.D[slot]); path_id = d.path_id; segment = d.segment; }
         HitRec h;
-        const bool hit = world_hit<COUNT, 2, MEDIA, GENERAL_MEDIA>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
+        const bool hit = world_hit<COUNT, 2, MEDIA, GENERAL_MEDIA, PM>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
         ++my_segments;
         uint32_t qi = Q_MISS;
         if (hit) {
@@ -734,6 +734,8 @@ static cudaError_t ensure_workspace(Workspace*& w, uint32_t N) {
     return cudaSuccess;
 }
 
+static int g_prim_specialise = 1;
+
 template <bool MEDIA, bool COUNT>
 static void launch_extend_p(int occ, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
     // persistent: exactly the resident number of CTAs (148 SMs x occ)
@@ -749,6 +751,10 @@ static void launch_extend(int occ, int blocks, cudaStream_t st, const DeviceScen
     const bool general = MEDIA && !(scene.flags & 2u);
     if (general) {
         k_extend<MEDIA, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+    } else if (MEDIA && !COUNT && g_prim_specialise && (scene.prim_mask & ~0x18u) == 0) {
+        k_extend<MEDIA, COUNT, 4, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
+    } else if (MEDIA && !COUNT && g_prim_specialise && (scene.prim_mask & ~0x1bu) == 0) {
+        k_extend<MEDIA, COUNT, 4, false, 0x1bu><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // spheres, moving spheres, rects, boxes (book-2 final)
     } else {
         if (occ >= 6) k_extend<MEDIA, COUNT, 6, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
         else if (occ == 5) k_extend<MEDIA, COUNT, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
@@ -786,6 +792,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         Queues& Q = w->Q;
         const int qblocks = (int)std::min<uint32_t>((N + 255) / 256, 148 * 8);
         const bool media = scene.n_media != 0;
+        g_prim_specialise = tune.prim_specialise;
         const int ext_occ = tune.extend_occ > 0 ? tune.extend_occ : (media ? 4 : 5);
         // measured (profiles/): the warp-scheduled persistent kernel wins on deep triangle BVHs (+22 % on the 871k mesh),
         // the one-ray-per-thread kernel on small scenes and on scenes with media
@@ -811,6 +818,8 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 k_mega<false, 4, false, true, 0x1u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres only (book-1 classic)
             } else if (fulltex && tune.prim_specialise && (scene.prim_mask & ~0x3u) == 0 && occ >= 4) {
                 k_mega<false, 4, false, true, 0x3u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres + moving spheres (book-1 as shipped)
+            } else if (fulltex && tune.prim_specialise && (scene.prim_mask & ~0x28u) == 0 && occ >= 4) {
+                k_mega<false, 4, false, true, 0x28u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);  // axis rects + triangles (mesh room)
             } else if (fulltex) {
                 if (occ >= 4) k_mega<false, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega<false, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);

@@ -76,6 +76,8 @@ if __name__ == "__main__":
                 run(13, 800, 1.5, 500, label=f"book1 {var}={v} #{rep}")
                 run(99, 800, 1.5, 200, label=f"book1b {var}={v} #{rep}")
                 run(14, 1000, 1.0, 10, param=660, label=f"mesh {var}={v} #{rep}")
+                run(5, 600, 1.0, 200, label=f"smoke {var}={v} #{rep}")
+                run(6, 1000, 1.0, 50, label=f"book2 {var}={v} #{rep}")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
