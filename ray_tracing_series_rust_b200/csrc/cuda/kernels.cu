@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
 // two modes produce bit-identical images.
 #define RT_MEGA_CHUNK 512u
-template <bool MEDIA, int MINB, bool GENERAL_MEDIA, bool FULLTEX, uint32_t PM = RT_PM_ALL>
+template <bool MEDIA, int MINB, bool GENERAL_MEDIA, bool FULLTEX, uint32_t PM = RT_PM_ALL, bool XF = true>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         if (!alive) continue;
         // ---- one ray_color iteration (world.rs:63-91)
         HitRec h;
-        const bool hit = world_hit<false, FULLTEX ? 2 : 0, MEDIA, GENERAL_MEDIA, PM>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        const bool hit = world_hit<false, FULLTEX ? 2 : 0, MEDIA, GENERAL_MEDIA, PM, XF>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
         ++my_segments;
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
@@ -814,6 +814,12 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             } else if (media) {
                 if (occ >= 4) k_mega<true, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega<true, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && scene.prim_mask == 0x1u && occ >= 4) {
+                k_mega<false, 4, false, true, 0x1u, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres only, no wrappers
+            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x3u) == 0 && occ >= 4) {
+                k_mega<false, 4, false, true, 0x3u, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x28u) == 0 && occ >= 4) {
+                k_mega<false, 4, false, true, 0x28u, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (fulltex && tune.prim_specialise && scene.prim_mask == 0x1u && occ >= 4) {
                 k_mega<false, 4, false, true, 0x1u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres only (book-1 classic)
             } else if (fulltex && tune.prim_specialise && (scene.prim_mask & ~0x3u) == 0 && occ >= 4) {

@@ -29,7 +29,7 @@ struct RenderTuning {
     int extend_occ = 0;             // k_extend variant: resident 128-thread blocks per SM (4 / 5 / 6); 0 = auto (5, or 4 with media)
     int extend_kind = -1;           // 0: one ray per thread (while-while), 1: persistent warp-scheduled k_extend_p, -1: auto (1 for big meshes without media)
     int force_fulltex = 1;          // 1: k_mega variant with the Noise/Image texture code (measured faster even for scenes without such textures); 0: slim variant
-    int prim_specialise = 1;        // use k_mega variants compiled for the primitive types the scene actually contains
+    int prim_specialise = 2;        // 1: kernel variants compiled for the primitive types the scene contains; 2: also without wrapper handling for wrapper-free scenes; 0: generic
     int extend_waves = 4;           // k_extend grid = 148 * extend_occ * extend_waves blocks (grid-stride over the slots)
 };
 

@@ -32,11 +32,11 @@ RT_DEV D3 operator-(D3 a, D3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
 RT_DEV D3 operator-(D3 a) { return mk3(-a.x, -a.y, -a.z); }
 RT_DEV D3 operator*(D3 a, double s) { return mk3(a.x * s, a.y * s, a.z * s); }
 RT_DEV D3 operator*(double s, D3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
-RT_DEV double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-RT_DEV D3 cross(D3 a, D3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RT_DEV double dot(D3 a, D3 b) { return fma(a.z, b.z, fma(a.y, b.y, a.x * b.x)); }
+RT_DEV D3 cross(D3 a, D3 b) { return mk3(fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)), fma(a.x, b.y, -(a.y * b.x))); }
 RT_DEV double length_squared(D3 a) { return dot(a, a); }
 RT_DEV D3 unit(D3 a) { return a * (1.0 / sqrt(length_squared(a))); }                 // vec3.rs:55-57
-RT_DEV D3 reflect(D3 v, D3 n) { return v - 2.0 * dot(v, n) * n; }                    // vec3.rs:64-66
+RT_DEV D3 reflect(D3 v, D3 n) { const double k = -2.0 * dot(v, n); return mk3(fma(k, n.x, v.x), fma(k, n.y, v.y), fma(k, n.z, v.z)); }                    // vec3.rs:64-66
 RT_DEV bool near_zero(D3 a) { const double s = 1e-8; return fabs(a.x) < s && fabs(a.y) < s && fabs(a.z) < s; } // vec3.rs:59-62
 RT_DEV D3 refract(D3 uv, D3 n, double etai_over_etat) {                              // vec3.rs:116-121
     const double cos_theta = fmin(dot(-uv, n), 1.0);
@@ -50,7 +50,7 @@ struct Ray { // ray.rs:3-8
     D3 o, d;
     double time;
 };
-RT_DEV D3 ray_at(const Ray& r, double t) { return mk3(r.o.x + r.d.x * t, r.o.y + r.d.y * t, r.o.z + r.d.z * t); } // ray.rs:31-33 (mul then add)
+RT_DEV D3 ray_at(const Ray& r, double t) { return mk3(fma(r.d.x, t, r.o.x), fma(r.d.y, t, r.o.y), fma(r.d.z, t, r.o.z)); } // ray.rs:31-33
 
 // ------------------------------------------------------------------ Philox-4x32-10 / PathRng
 RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -109,7 +109,7 @@ struct PathRng {
         return w == 0 ? blk.x : (w == 1 ? blk.y : (w == 2 ? blk.z : blk.w));
     }
     RT_DEV double gen() { return (double)next_u32() * (1.0 / 4294967296.0); }
-    RT_DEV double gen_range(double a, double b) { return a + gen() * (b - a); }
+    RT_DEV double gen_range(double a, double b) { return fma(gen(), b - a, a); }
 };
 RT_DEV double medium_xi(uint64_t seed, uint64_t path_id, uint32_t medium_prim_id, uint32_t segment) {
     const uint4 o = philox4x32_10(make_uint4((uint32_t)path_id, (uint32_t)(path_id >> 32), medium_prim_id, 0x80000000u | segment),
@@ -180,8 +180,8 @@ RT_DEV RayPre make_raypre(const Ray& r, bool planar) {
 RT_DEV double sphere_root(const Ray& r, const RayPre& pre, D3 c, double radius, double t_min, double t_max) {
     const D3 oc = r.o - c;
     const double half_b = dot(oc, r.d);
-    const double cc = length_squared(oc) - radius * radius;
-    const double disc = half_b * half_b - pre.a * cc;
+    const double cc = fma(-radius, radius, length_squared(oc));
+    const double disc = fma(half_b, half_b, -(pre.a * cc));
     if (disc < 0.0) return RT_INF;
     const double sqrtd = sqrt(disc);
     double root = (-half_b - sqrtd) * pre.inv_a;
@@ -193,7 +193,7 @@ RT_DEV double sphere_root(const Ray& r, const RayPre& pre, D3 c, double radius, 
 }
 RT_DEV D3 moving_center(const DMoving& m, double time) { // hit.rs:275-278
     const double f = (time - m.t0) / m.dt;
-    return mk3(m.c0[0] + f * m.dc[0], m.c0[1] + f * m.dc[1], m.c0[2] + f * m.dc[2]);
+    return mk3(fma(f, m.dc[0], m.c0[0]), fma(f, m.dc[1], m.c0[1]), fma(f, m.dc[2], m.c0[2]));
 }
 RT_DEV D3 gravity_center(const DeviceScene& S, const DGravity& g, double time) { // hit.rs:370-379
     const double q = time / 0.001;
@@ -209,8 +209,8 @@ RT_DEV double rect_t(const Ray& r, const RayPre& pre, const DRect& q, double t_m
     const int ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
     const double t = (q.k - axis_of(r.o, ax)) * axis_of(pre.inv_d, ax);
     if (t < t_min || t > t_max) return RT_INF;
-    const double x = axis_of(r.o, ia) + t * axis_of(r.d, ia);
-    const double y = axis_of(r.o, ib) + t * axis_of(r.d, ib);
+    const double x = fma(t, axis_of(r.d, ia), axis_of(r.o, ia));
+    const double y = fma(t, axis_of(r.d, ib), axis_of(r.o, ib));
     if (x < q.a0 || x > q.a1 || y < q.b0 || y > q.b1) return RT_INF;
     return t;
 }
@@ -221,8 +221,8 @@ RT_DEV double box_side_t(const Ray& r, const RayPre& pre, const DBox& b, int s) 
     const double k = (s & 1) ? b.p0[ax] : b.p1[ax];
     const double t = (k - axis_of(r.o, ax)) * axis_of(pre.inv_d, ax);
     if (!(t < RT_INF) || !(t > -RT_INF)) return RT_INF;
-    const double x = axis_of(r.o, ia) + t * axis_of(r.d, ia);
-    const double y = axis_of(r.o, ib) + t * axis_of(r.d, ib);
+    const double x = fma(t, axis_of(r.d, ia), axis_of(r.o, ia));
+    const double y = fma(t, axis_of(r.d, ib), axis_of(r.o, ib));
     if (x < b.p0[ia] || x > b.p1[ia] || y < b.p0[ib] || y > b.p1[ib]) return RT_INF;
     return t;
 }
@@ -390,12 +390,14 @@ RT_DEV bool inst_box_hit(const Instance* ip, const Ray& r, double t_min, double 
 }
 
 // world.hit restricted to the instances [i0, i1): the main world or one medium's boundary.
-template <bool COUNT, uint32_t PM = RT_PM_ALL>
+// XF = false: the scene has no Translate / RotateY wrappers (every chain is empty): no ray transform going in,
+// no chain unwinding coming out
+template <bool COUNT, uint32_t PM = RT_PM_ALL, bool XF = true>
 RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, const Ray& world_ray, double t_min, BestHit& best, TraceCounters* cnt) {
     for (uint32_t i = i0; i < i1; ++i) {
         const Instance* ip = &S.instances[i];
         Ray r = world_ray;
-        xform_ray(S.ops, __ldg(&ip->chain_off), __ldg(&ip->chain_len), r);
+        if (XF) xform_ray(S.ops, __ldg(&ip->chain_off), __ldg(&ip->chain_len), r);
         trace_instance<COUNT, PM>(S, i, r, t_min, best, cnt);
     }
 }
@@ -424,13 +426,14 @@ RT_DEV void sphere_uv(D3 p, double& u, double& v) { // hit.rs:195-200
 // re-face-forwarding quirks.
 // UVMODE: 0 = never compute sphere (u,v) (the scene has no image texture), 1 = always (parity hook),
 // 2 = when the hit material's texture chain reads them
-template <int UVMODE, uint32_t PM = RT_PM_ALL>
+template <int UVMODE, uint32_t PM = RT_PM_ALL, bool XF = true>
 RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const BestHit& b) {
     HitRec h;
     const Instance* ip = &S.instances[b.inst];
-    const uint32_t coff = __ldg(&ip->chain_off), clen = __ldg(&ip->chain_len);
+    uint32_t coff = 0, clen = 0;
+    if (XF) { coff = __ldg(&ip->chain_off); clen = __ldg(&ip->chain_len); }
     Ray r = world_ray;
-    xform_ray(S.ops, coff, clen, r);
+    if (XF) xform_ray(S.ops, coff, clen, r);
     const PrimMeta m = S.meta[b.type][b.idx];
     h.mat = m.mat_id;
     h.prim_id = m.prim_id + b.side;
@@ -475,7 +478,7 @@ RT_DEV HitRec finalize_hit(const DeviceScene& S, const Ray& world_ray, const Bes
     face_forward(r.d, outward, h.n, h.front);
     // unwind the chain: r currently holds the innermost ray
     D3 d_in = r.d;
-    for (int i = (int)clen - 1; i >= 0; --i) {
+    for (int i = XF ? (int)clen - 1 : -1; i >= 0; --i) {
         const XformOp op = S.ops[coff + i];
         if (op.type == XF_TRANSLATE) {
             h.p = mk3(h.p.x + op.a, h.p.y + op.b, h.p.z + op.c);
@@ -513,7 +516,7 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
             const DSphere sp = S.spheres[md.fast_idx];
             const D3 oc = rb.o - mk3(sp.cx, sp.cy, sp.cz);
             const double a = length_squared(rb.d), half_b = dot(oc, rb.d);
-            const double disc = half_b * half_b - a * (length_squared(oc) - sp.r * sp.r);
+            const double disc = fma(half_b, half_b, -(a * fma(-sp.r, sp.r, length_squared(oc))));
             if (disc < 0.0) return;
             const double sq = sqrt(disc), inv_a = 1.0 / a;
             ta = (-half_b - sq) * inv_a;
@@ -570,12 +573,12 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
 
 // world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
 // surface (order independent because medium draws are keyed).
-template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true, uint32_t PM = RT_PM_ALL>
+template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true, uint32_t PM = RT_PM_ALL, bool XF = true>
 RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double t_max, bool media, uint64_t seed, uint64_t path_id, uint32_t segment,
                       HitRec& h, TraceCounters* cnt) {
     BestHit best;
     best_init(best, t_max);
-    trace_instances<COUNT, PM>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
+    trace_instances<COUNT, PM, XF>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
     if (MEDIA) {
         double closest = best.t;
         int32_t mwin = -1;
@@ -591,7 +594,7 @@ RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double
         }
     }
     if (best.type == RT_NONE) return false;
-    h = finalize_hit<UVMODE, PM>(S, ray, best);
+    h = finalize_hit<UVMODE, PM, XF>(S, ray, best);
     return true;
 }
 

@@ -608,6 +608,7 @@ int32_t do_commit(rt_scene* s) {
     }
     if (!perlin.empty()) D.flags |= 8u;     // Perlin-noise textures: expensive, divergent shading
     if (!texels.empty()) D.flags |= 16u;    // image textures (sphere uv needed)
+    if (!ops.empty()) D.flags |= 32u;       // Translate / RotateY wrappers present
     if (tris.size() >= 4096) D.flags |= 4u; // deep triangle BVH: prefer the persistent warp-scheduled extend kernel
     if (s->camera.set) D.cam = s->camera.cam;
     for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];

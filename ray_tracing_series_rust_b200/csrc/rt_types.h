@@ -125,7 +125,7 @@ struct DeviceScene {
     uint32_t n_main_instances;
     uint32_t n_media;
     uint32_t n_prims;
-    uint32_t flags; // bit 0: the scene has axis rects / boxes (per-ray inverse directions are needed); bit 1: every medium has the fast path; bit 2: large triangle mesh; bit 3: Perlin-noise textures; bit 4: image textures
+    uint32_t flags; // bit 0: the scene has axis rects / boxes (per-ray inverse directions are needed); bit 1: every medium has the fast path; bit 2: large triangle mesh; bit 3: Perlin-noise textures; bit 4: image textures; bit 5: Translate / RotateY wrappers present
     DCamera cam;
     float background[3];
     float pad2_;
