@@ -804,7 +804,10 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         const int mode = tune.mode != RT_MODE_AUTO ? tune.mode : ((scene.n_media == 0 && !(scene.flags & 8u)) ? RT_MODE_FUSED : RT_MODE_WAVEFRONT);
         if (mode == RT_MODE_FUSED) {
             k_mega_init<<<1, 32, 0, stream>>>(Q);
-            const int occ = std::max(3, std::min(6, tune.mega_occ));
+            // resident CTAs per SM: the scene-specialised variants fit 96 registers without spills (5 CTAs), the generic ones need 128 (4 CTAs)
+            const bool specialised = tune.prim_specialise == 2 && !media && !(scene.flags & 32u) &&
+                                     (scene.prim_mask == 0x1u || (scene.prim_mask & ~0x3u) == 0 || (scene.prim_mask & ~0x28u) == 0);
+            const int occ = tune.mega_occ > 0 ? std::max(3, std::min(6, tune.mega_occ)) : (specialised ? 5 : 4);
             const int mblocks = 148 * occ;
             // Measured (tools/explore.py ab RTB200_FULLTEX 0,1): the variant WITHOUT the Noise/Image texture code is 15 % slower on
             // the book-1 scene (154.5 vs 134.4 ms; same 128 registers, no spills - a code-layout effect), so the full variant is the default.
@@ -814,6 +817,12 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             } else if (media) {
                 if (occ >= 4) k_mega<true, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega<true, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && scene.prim_mask == 0x1u && occ >= 5) {
+                k_mega<false, 5, false, true, 0x1u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x3u) == 0 && occ >= 5) {
+                k_mega<false, 5, false, true, 0x3u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x28u) == 0 && occ >= 5) {
+                k_mega<false, 5, false, true, 0x28u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && scene.prim_mask == 0x1u && occ >= 4) {
                 k_mega<false, 4, false, true, 0x1u, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres only, no wrappers
             } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x3u) == 0 && occ >= 4) {

@@ -22,7 +22,7 @@ struct RenderJob {
 
 struct RenderTuning {
     int mode = RT_MODE_AUTO;
-    int mega_occ = 4;               // k_mega variant: resident 128-thread blocks per SM (3 .. 6); 4 = 128 registers, no spills
+    int mega_occ = 0;               // k_mega variant: resident 128-thread blocks per SM; 0 = auto (5 for the scene-specialised variants, else 4)
     uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
     int timed_extend = 0;           // 1: bracket every extend launch with CUDA events (for the roofline)
     int count_events = 0;           // 1: count BVH node visits / primitive tests on the device
