@@ -63,6 +63,7 @@ struct JobDev {
     uint64_t seed;
     uint32_t n_slots;
     int32_t count_events;
+    uint32_t wait_thresh; // k_mega_r: finished lanes that end a traversal round
 };
 
 // Path-state chunks are streamed (read once / written once per kernel): evict-first hints keep them from
@@ -153,15 +154,11 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
     split_path_index(L, J.npix_rendered, s_local, pix);
     const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix - (uint32_t)j * (uint32_t)J.W);
     const uint64_t path_id = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
-    PathRng g;
-    g.init(J.seed, path_id, 0);
-    g.prefetch2(); // jitter (2) + lens disk (2 per try) + time (1): two blocks cover 2 disk tries
-    const double u = ((double)ii + g.gen()) / (double)(J.W - 1); // world.rs:1212
-    const double v = ((double)j + g.gen()) / (double)(J.H - 1);  // world.rs:1213
-    const Ray r = camera_get_ray(S.cam, u, v, g);
+    uint32_t draw0;
+    const Ray r = camera_first_ray<PathRng>(S.cam, ii, j, J.W, J.H, J.seed, path_id, draw0); // world.rs:1212-1214
     SlotA a; a.ox = r.o.x; a.oy = r.o.y; a.oz = r.o.z; a.time = r.time;
     SlotB b; b.dx = r.d.x; b.dy = r.d.y; b.dz = r.d.z; b.pad0 = 0; b.pad1 = 0;
-    SlotD d; d.tr = 1.f; d.tg = 1.f; d.tb = 1.f; d.draw = g.draw; d.path_id = path_id; d.segment = 0; d.pixel = pix;
+    SlotD d; d.tr = 1.f; d.tg = 1.f; d.tb = 1.f; d.draw = draw0; d.path_id = path_id; d.segment = 0; d.pixel = pix;
     P.A[slot] = a;
     P.B[slot] = b;
     P.D[slot] = d;
@@ -512,12 +509,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                     split_path_index(L, J.npix_rendered, s_local, pixel);
                     const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
                     path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
-                    PathRng g;
-                    g.init(J.seed, path_id, 0);
-                    const double u = ((double)ii + g.gen()) / (double)(J.W - 1); // world.rs:1212
-                    const double v = ((double)j + g.gen()) / (double)(J.H - 1);  // world.rs:1213
-                    r = camera_get_ray(S.cam, u, v, g);
-                    draw = g.draw;
+                    r = camera_first_ray<PathRngOol>(S.cam, ii, j, J.W, J.H, J.seed, path_id, draw); // world.rs:1212-1214
                     tr = tg = tb = 1.f;
                     segment = 0;
                     alive = true;
@@ -542,7 +534,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                 const F3 e = tex_value<FULLTEX>(S, m.tex, h.u, h.v, h.p);
                 contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
             } else {
-                PathRng g;
+                PathRngOol g;
                 g.init(J.seed, path_id, draw);
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
@@ -557,6 +549,108 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                     draw = g.draw;
                     ++segment;
                     ended = false;
+                }
+            }
+        }
+        if (ended) {
+            accumulate(accum, pixel, contrib.x, contrib.y, contrib.z);
+            alive = false;
+        }
+    }
+    uint32_t segs = my_segments;
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(full, segs, o);
+    if (lane_id() == 0 && segs) atomicAdd(&Q.stats[0], (unsigned long long)segs);
+}
+
+// k_mega_r: k_mega with the resumable traversal (single main instance, no wrappers, no media).  Each round:
+// idle lanes claim new paths -> every lane with a ray walks the BVH until `wait_thresh` lanes have finished ->
+// the finished lanes shade / scatter / start their next segment, the others keep their traversal state and
+// continue in the next round.  Per-path arithmetic and Philox streams are those of k_mega: bit-identical images.
+template <int MINB, bool FULLTEX, uint32_t PM>
+__global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
+                                                        int64_t* __restrict__ accum) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t DONE = 0xffffffffu;
+    unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform
+    Ray r;
+    r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.time = 0.0;
+    float tr = 0.f, tg = 0.f, tb = 0.f;
+    uint32_t pixel = 0, draw = 0, segment = 0;
+    uint64_t path_id = 0;
+    bool alive = false, exhausted = false;
+    uint32_t my_segments = 0;
+    uint32_t stack[RT_STACK];
+    uint32_t cur = DONE;
+    int sp = 0;
+    BestHit best;
+    best_init(best, RT_INF);
+    const uint32_t root = __ldg(&S.instances[0].root);
+    for (;;) {
+        // ---- refill idle lanes
+        const unsigned need = __ballot_sync(full, !alive && !exhausted);
+        if (need) {
+            const uint32_t n_need = __popc(need);
+            unsigned long long avail = chunk_end - chunk_next;
+            unsigned long long second_base = 0;
+            if (avail < n_need) {
+                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)RT_MEGA_CHUNK);
+                second_base = __shfl_sync(full, second_base, 0);
+            }
+            if (!alive && !exhausted) {
+                const uint32_t rank = __popc(need & ((1u << lane_id()) - 1u));
+                unsigned long long L = (rank < avail) ? chunk_next + rank : second_base + (rank - avail);
+                if (L >= J.total_paths) {
+                    exhausted = true;
+                } else {
+                    uint32_t s_local;
+                    split_path_index(L, J.npix_rendered, s_local, pixel);
+                    const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
+                    path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
+                    r = camera_first_ray<PathRngOol>(S.cam, ii, j, J.W, J.H, J.seed, path_id, draw); // world.rs:1212-1214
+                    tr = tg = tb = 1.f;
+                    segment = 0;
+                    alive = true;
+                    best_init(best, RT_INF);
+                    cur = root; sp = 0;
+                }
+            }
+            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + RT_MEGA_CHUNK; }
+            else chunk_next += n_need;
+        }
+        if (!__any_sync(full, alive)) break;
+        // ---- world.hit for every lane that has a ray; returns when enough lanes are ready to shade
+        trace_resume<PM>(S, r, 0.001, best, cur, sp, stack, J.wait_thresh);
+        if (!alive || cur != DONE) continue;
+        // ---- the rest of this ray_color iteration (world.rs:63-91)
+        ++my_segments;
+        F3 contrib = mkf3(0.f, 0.f, 0.f);
+        bool ended = true;
+        if (best.type == RT_NONE) {
+            contrib = mkf3(tr * S.background[0], tg * S.background[1], tb * S.background[2]);
+        } else {
+            const HitRec h = finalize_hit<FULLTEX ? 2 : 0, PM, false>(S, r, best);
+            const DMaterial m = S.materials[h.mat];
+            if (m.type == MAT_LIGHT) {
+                const F3 e = tex_value<FULLTEX>(S, m.tex, h.u, h.v, h.p);
+                contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
+            } else {
+                PathRngOol g;
+                g.init(J.seed, path_id, draw);
+                D3 dir = mk3(0, 0, 0);
+                F3 att = mkf3(0.f, 0.f, 0.f);
+                bool scattered;
+                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian<FULLTEX>(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
+                else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
+                else scattered = scatter_isotropic<FULLTEX>(S, m, h.p, h.u, h.v, g, dir, att);
+                if (scattered && (int32_t)(segment + 1) < J.max_depth) {
+                    tr *= att.x; tg *= att.y; tb *= att.z;
+                    r.o = h.p; r.d = dir;
+                    draw = g.draw;
+                    ++segment;
+                    ended = false;
+                    best_init(best, RT_INF);
+                    cur = root; sp = 0;
                 }
             }
         }
@@ -812,11 +906,26 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             // Measured (tools/explore.py ab RTB200_FULLTEX 0,1): the variant WITHOUT the Noise/Image texture code is 15 % slower on
             // the book-1 scene (154.5 vs 134.4 ms; same 128 registers, no spills - a code-layout effect), so the full variant is the default.
             const bool fulltex = tune.force_fulltex != 0 || (scene.flags & (8u | 16u)) != 0;
+            // resumable traversal: single wrapper-free instance, no media
+            // measured (tools/explore.py ab RTB200_MEGA_WAIT ...): +7 % on the 871k-triangle mesh at 20 lanes, -4 .. -40 % on the
+            // sphere scenes, whose shading share is too large to run it with half-empty warps
+            const int mega_wait = tune.mega_wait >= 0 ? tune.mega_wait : ((scene.flags & 4u) ? 20 : 0);
+            const bool resumable = mega_wait > 0 && specialised && fulltex && scene.n_main_instances == 1;
+            J.wait_thresh = (uint32_t)std::max(1, std::min(32, mega_wait));
             if (media && !(scene.flags & 2u)) {
                 k_mega<true, 3, true, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (media) {
                 if (occ >= 4) k_mega<true, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega<true, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (resumable && scene.prim_mask == 0x1u) {
+                if (occ >= 5) k_mega_r<5, true, 0x1u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega_r<4, true, 0x1u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (resumable && (scene.prim_mask & ~0x3u) == 0) {
+                if (occ >= 5) k_mega_r<5, true, 0x3u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega_r<4, true, 0x3u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (resumable && (scene.prim_mask & ~0x28u) == 0) {
+                if (occ >= 5) k_mega_r<5, true, 0x28u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega_r<4, true, 0x28u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && scene.prim_mask == 0x1u && occ >= 5) {
                 k_mega<false, 5, false, true, 0x1u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x3u) == 0 && occ >= 5) {

@@ -22,6 +22,7 @@ struct RenderJob {
 
 struct RenderTuning {
     int mode = RT_MODE_AUTO;
+    int mega_wait = -1;             // k_mega_r (resumable traversal): finished lanes that end a traversal round; 0 = plain k_mega, -1 = auto (20 on large meshes)
     int mega_occ = 0;               // k_mega variant: resident 128-thread blocks per SM; 0 = auto (5 for the scene-specialised variants, else 4)
     uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
     int timed_extend = 0;           // 1: bracket every extend launch with CUDA events (for the roofline)

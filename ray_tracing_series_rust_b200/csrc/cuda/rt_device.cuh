@@ -52,6 +52,18 @@ struct Ray { // ray.rs:3-8
 };
 RT_DEV D3 ray_at(const Ray& r, double t) { return mk3(fma(r.d.x, t, r.o.x), fma(r.d.y, t, r.o.y), fma(r.d.z, t, r.o.z)); } // ray.rs:31-33
 
+// Build-time alternatives, A/B-measured on B200 with tools/ab_libs.sh (book-1 final, 500 spp; same box, same call):
+//   Philox inlined at its 19 call sites 100.4 ms | one out-of-line copy 94.4 ms  (-8 KB of code; the kernel stalls on
+//   instruction fetch for 19 % of its samples)  -> out of line.
+//   Sampler draws resolved at compile time (random_in_unit_sphere_aligned, camera_first_ray): 101.6 / 104.1 ms alone,
+//   105.8 ms together, 108.6 ms with the out-of-line Philox -> off.  Fewer instructions, slower kernel: at ~11 active
+//   lanes per instruction the kernel is bound by fetch / issue latency of divergent code, not by instruction count.
+#ifndef RT_STATIC_SPHERE
+#define RT_STATIC_SPHERE 0
+#endif
+#ifndef RT_STATIC_CAMERA
+#define RT_STATIC_CAMERA 0
+#endif
 // ------------------------------------------------------------------ Philox-4x32-10 / PathRng
 RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -63,10 +75,17 @@ RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
+// One out-of-line copy for the fused kernels, whose ~19 inlined call sites cost 8 KB of code (see the A/B note above)
+static __device__ __noinline__ uint4 philox4x32_10_ool(uint4 c, uint2 k) { return philox4x32_10(c, k); }
 
 // Draw k of a path = word (k & 3) of block (path_lo, path_hi, k >> 2, 0) under key (seed_lo, seed_hi);
 // xi = u32 * 2^-32 (identical in oracle/rt_oracle.hpp PathCtx); scatters start on block boundaries.
-struct PathRng {
+template <bool OOL>
+struct PathRngT {
+    RT_DEV uint4 block(uint32_t b) const {
+        const uint4 c = make_uint4(path.x, path.y, b, 0u);
+        return OOL ? philox4x32_10_ool(c, key) : philox4x32_10(c, key);
+    }
     uint2 key, path;
     uint32_t draw, cached; // cached = index of the block held in blk; blk2 holds block cached + 1 when have2
     uint4 blk, blk2;
@@ -84,7 +103,7 @@ struct PathRng {
     RT_DEV void begin_event() {
         draw = (draw + 3u) & ~3u;
         const uint32_t b = draw >> 2;
-        blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
+        blk = block(b);
         cached = b;
         have2 = false;
     }
@@ -92,8 +111,8 @@ struct PathRng {
     // them diverge, and a Philox block generated inside them runs with a handful of active lanes.
     RT_DEV void prefetch2() {
         const uint32_t b = draw >> 2;
-        blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
-        blk2 = philox4x32_10(make_uint4(path.x, path.y, b + 1u, 0u), key);
+        blk = block(b);
+        blk2 = block(b + 1u);
         cached = b;
         have2 = true;
     }
@@ -101,7 +120,7 @@ struct PathRng {
         const uint32_t b = draw >> 2;
         if (b != cached) {
             if (have2 && b == cached + 1u) { blk = blk2; have2 = false; }
-            else blk = philox4x32_10(make_uint4(path.x, path.y, b, 0u), key);
+            else blk = block(b);
             cached = b;
         }
         const uint32_t w = draw & 3u;
@@ -111,20 +130,43 @@ struct PathRng {
     RT_DEV double gen() { return (double)next_u32() * (1.0 / 4294967296.0); }
     RT_DEV double gen_range(double a, double b) { return fma(gen(), b - a, a); }
 };
+using PathRng = PathRngT<false>;    // wavefront kernels, parity hooks
+using PathRngOol = PathRngT<true>;  // fused kernels
 RT_DEV double medium_xi(uint64_t seed, uint64_t path_id, uint32_t medium_prim_id, uint32_t segment) {
     const uint4 o = philox4x32_10(make_uint4((uint32_t)path_id, (uint32_t)(path_id >> 32), medium_prim_id, 0x80000000u | segment),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     return (double)o.x * (1.0 / 4294967296.0);
 }
 
-RT_DEV D3 random_in_unit_sphere(PathRng& g) { // vec3.rs:287-295
+template <class G> RT_DEV D3 random_in_unit_sphere(G& g) { // vec3.rs:287-295
     for (;;) {
         const double a = g.gen_range(-1.0, 1.0), b = g.gen_range(-1.0, 1.0), c = g.gen_range(-1.0, 1.0);
         const D3 p = mk3(a, b, c);
         if (length_squared(p) < 1.0) return p;
     }
 }
-RT_DEV D3 random_unit_vector(PathRng& g) { return unit(random_in_unit_sphere(g)); } // vec3.rs:297-299
+template <class G> RT_DEV D3 random_unit_vector(G& g) { return unit(random_in_unit_sphere(g)); } // vec3.rs:297-299
+// xi -> 2 xi - 1, the arithmetic of gen_range(-1, 1)
+RT_DEV double sym_unit(uint32_t w) { return fma((double)w * (1.0 / 4294967296.0), 2.0, -1.0); }
+// random_in_unit_sphere right after begin_event(): the draw index is a multiple of 4 and g.blk holds that block, so
+// the first two tries read fixed words (x y z | w x' y') instead of going through next_u32's word selection; 77 % of
+// the calls end here.  Later tries continue in the general loop from draw + 6.  Same draws, same arithmetic.
+template <class G> RT_DEV D3 random_in_unit_sphere_aligned(G& g) {
+#if !RT_STATIC_SPHERE
+    return random_in_unit_sphere(g);
+#endif
+    const uint4 A = g.blk;
+    D3 p = mk3(sym_unit(A.x), sym_unit(A.y), sym_unit(A.z));
+    if (length_squared(p) < 1.0) { g.draw += 3u; return p; }
+    const uint32_t b = (g.draw >> 2) + 1u;
+    const uint4 B = g.block(b);
+    g.blk = B; g.cached = b; g.have2 = false;
+    g.draw += 6u;
+    p = mk3(sym_unit(A.w), sym_unit(B.x), sym_unit(B.y));
+    if (length_squared(p) < 1.0) return p;
+    return random_in_unit_sphere(g);
+}
+template <class G> RT_DEV D3 random_unit_vector_aligned(G& g) { return unit(random_in_unit_sphere_aligned(g)); }
 
 // ------------------------------------------------------------------ transforms (hit.rs:802-807, 893-904)
 RT_DEV void xform_ray(const XformOp* __restrict__ ops, uint32_t off, uint32_t len, Ray& r) {
@@ -378,6 +420,55 @@ RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r
             }
         }
         tmaxf = f32_up(best.t);
+    }
+}
+
+// Resumable form of trace_instance for the fused kernel (single instance, no wrappers).  The walk is the
+// same; its state (cur, sp, stack, best) lives in the caller, and the warp leaves the loop as soon as
+// `wait_thresh` of the lanes that entered with work have finished, instead of idling them until the slowest
+// lane is done.  The unfinished lanes come back with the next call (after the finished ones have shaded and
+// started their next segment) and continue where they stopped.  Called by all 32 lanes.
+template <uint32_t PM = RT_PM_ALL>
+RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, uint32_t* stack, uint32_t wait_thresh) {
+    const unsigned full = 0xffffffffu;
+    const RayF f = make_rayf(r);
+    const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
+    const float tminf = f32_down(t_min);
+    float tmaxf = f32_up(best.t);
+    const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
+    const uint32_t DONE = 0xffffffffu;
+    const uint32_t n0 = __popc(__ballot_sync(full, cur != DONE));
+    for (;;) {
+        uint32_t leaf_first0 = 0, leaf_cnt0 = 0, leaf_first1 = 0, leaf_cnt1 = 0;
+        while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0) {
+            const float4 lo0 = __ldg(nodes + 2 * cur), hi0 = __ldg(nodes + 2 * cur + 1);
+            const float4 lo1 = __ldg(nodes + 2 * cur + 2), hi1 = __ldg(nodes + 2 * cur + 3);
+            float tn0, tn1;
+            bool h0 = slab(lo0, hi0, f, tminf, tmaxf, tn0);
+            bool h1 = slab(lo1, hi1, f, tminf, tmaxf, tn1);
+            const uint32_t c0 = __float_as_uint(hi0.w), c1 = __float_as_uint(hi1.w);
+            if (h0 && c0) { leaf_first0 = __float_as_uint(lo0.w); leaf_cnt0 = c0 & 0x7fffffffu; h0 = false; }
+            if (h1 && c1) { leaf_first1 = __float_as_uint(lo1.w); leaf_cnt1 = c1 & 0x7fffffffu; h1 = false; }
+            if (h0 && h1) {
+                const uint32_t n0i = __float_as_uint(lo0.w), n1i = __float_as_uint(lo1.w);
+                const bool first0 = tn0 <= tn1;
+                cur = first0 ? n0i : n1i;
+                if (sp < RT_STACK) stack[sp++] = first0 ? n1i : n0i;
+            } else if (h0) {
+                cur = __float_as_uint(lo0.w);
+            } else if (h1) {
+                cur = __float_as_uint(lo1.w);
+            } else {
+                cur = sp ? stack[--sp] : DONE;
+            }
+        }
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t lc = k ? leaf_cnt1 : leaf_cnt0, lf = k ? leaf_first1 : leaf_first0;
+            if (lc & 0xffffffu) leaf_test<PM>(S, r, pre, t_min, best, lc >> 24, lf, lc & 0xffffffu, 0u);
+        }
+        tmaxf = f32_up(best.t);
+        const uint32_t still = __popc(__ballot_sync(full, cur != DONE));
+        if (still == 0 || n0 - still >= wait_thresh) break;
     }
 }
 
@@ -666,19 +757,19 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
 
 // ------------------------------------------------------------------ Material::scatter (hit.rs:1004-1152)
 // Returns true when the path continues; `dir` = scattered direction, `att` = attenuation.
-template <bool FULLTEX = true>
-RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, PathRng& g, D3& dir, F3& att) {
+template <bool FULLTEX = true, class G>
+RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, G& g, D3& dir, F3& att) {
     g.begin_event();
-    D3 sd = n + random_unit_vector(g);
+    D3 sd = n + random_unit_vector_aligned(g);
     if (near_zero(sd)) sd = n;
     dir = sd;
     att = tex_value<FULLTEX>(S, m.tex, u, v, p);
     return true;
 }
-RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, PathRng& g, D3& dir, F3& att) {
+template <class G> RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, G& g, D3& dir, F3& att) {
     g.begin_event();
     const D3 reflected = reflect(unit(d_in), n);
-    dir = reflected + m.fuzz_or_ir * random_in_unit_sphere(g); // the draw happens even when fuzz == 0
+    dir = reflected + m.fuzz_or_ir * random_in_unit_sphere_aligned(g); // the draw happens even when fuzz == 0
     att = mkf3(m.albedo[0], m.albedo[1], m.albedo[2]);
     return dot(dir, n) > 0.0;
 }
@@ -688,7 +779,7 @@ RT_DEV double reflectance(double cosine, double ref_idx) { // hit.rs:1095-1099
     const double x = 1.0 - cosine;
     return r0 + (1.0 - r0) * (x * x * x * x * x);
 }
-RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D3 n, bool front, PathRng& g, D3& dir, F3& att) {
+template <class G> RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D3 n, bool front, G& g, D3& dir, F3& att) {
     g.begin_event();
     att = mkf3(1.f, 1.f, 1.f);
     const double ratio = front ? 1.0 / m.fuzz_or_ir : m.fuzz_or_ir;
@@ -700,16 +791,16 @@ RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D3 n, bool front, Pa
     else dir = refract(ud, n, ratio);
     return true;
 }
-template <bool FULLTEX = true>
-RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, PathRng& g, D3& dir, F3& att) {
+template <bool FULLTEX = true, class G>
+RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, G& g, D3& dir, F3& att) {
     g.begin_event();
-    dir = random_in_unit_sphere(g); // not normalised (hit.rs:1007)
+    dir = random_in_unit_sphere_aligned(g); // not normalised (hit.rs:1007)
     att = tex_value<FULLTEX>(S, m.tex, u, v, p);
     return true;
 }
 
 // ------------------------------------------------------------------ Camera::get_ray (camera.rs:59-71)
-RT_DEV Ray camera_get_ray(const DCamera& c, double s, double t, PathRng& g) {
+template <class G> RT_DEV Ray camera_get_ray(const DCamera& c, double s, double t, G& g) {
     double rx, ry;
     for (;;) { // random_in_unit_disk, vec3.rs:310-322 (runs even when lens_radius == 0)
         rx = g.gen_range(-1.0, 1.0);
@@ -726,6 +817,59 @@ RT_DEV Ray camera_get_ray(const DCamera& c, double s, double t, PathRng& g) {
     r.o = origin + offset;
     r.d = llc + s * hor + t * ver - origin - offset;
     r.time = g.gen_range(c.time1, c.time2);
+    return r;
+}
+
+// The first draws of a path with their positions resolved at compile time: pixel jitter = words 0, 1 of block 0
+// (world.rs:1212-1213), lens disk tries = (2, 3), (4, 5), ... and the shutter time right after the accepted try.
+// Blocks 0 and 1 are generated back to back (two independent Philox chains); 95 % of the paths need nothing else.
+template <class G> RT_DEV Ray camera_first_ray(const DCamera& c, int32_t ii, int32_t j, int32_t W, int32_t H, uint64_t seed, uint64_t path_id, uint32_t& draw_out) {
+    G g;
+    g.init(seed, path_id, 0);
+#if !RT_STATIC_CAMERA
+    {
+        const double s0 = ((double)ii + g.gen()) / (double)(W - 1);
+        const double t0 = ((double)j + g.gen()) / (double)(H - 1);
+        const Ray r0 = camera_get_ray(c, s0, t0, g);
+        draw_out = g.draw;
+        return r0;
+    }
+#endif
+    const uint4 A = g.block(0u);
+    const uint4 B = g.block(1u);
+    const double s = ((double)ii + (double)A.x * (1.0 / 4294967296.0)) / (double)(W - 1);
+    const double t = ((double)j + (double)A.y * (1.0 / 4294967296.0)) / (double)(H - 1);
+    double rx = sym_unit(A.z), ry = sym_unit(A.w), time;
+    uint32_t tw = B.x;
+    g.draw = 5u;
+    bool found = rx * rx + ry * ry + 0.0 < 1.0;
+    if (!found) {
+        rx = sym_unit(B.x); ry = sym_unit(B.y); tw = B.z;
+        g.draw = 7u;
+        found = rx * rx + ry * ry + 0.0 < 1.0;
+    }
+    if (found) {
+        time = fma((double)tw * (1.0 / 4294967296.0), c.time2 - c.time1, c.time1);
+    } else {
+        g.blk = B; g.cached = 1u; g.draw = 6u;
+        for (;;) {
+            rx = g.gen_range(-1.0, 1.0);
+            ry = g.gen_range(-1.0, 1.0);
+            if (rx * rx + ry * ry + 0.0 < 1.0) break;
+        }
+        time = g.gen_range(c.time1, c.time2);
+    }
+    draw_out = g.draw;
+    rx *= c.lens_radius; ry *= c.lens_radius;
+    const D3 u = mk3(c.u[0], c.u[1], c.u[2]), v = mk3(c.v[0], c.v[1], c.v[2]);
+    const D3 offset = u * rx + v * ry;
+    const D3 origin = mk3(c.origin[0], c.origin[1], c.origin[2]);
+    const D3 llc = mk3(c.lower_left_corner[0], c.lower_left_corner[1], c.lower_left_corner[2]);
+    const D3 hor = mk3(c.horizontal[0], c.horizontal[1], c.horizontal[2]), ver = mk3(c.vertical[0], c.vertical[1], c.vertical[2]);
+    Ray r;
+    r.o = origin + offset;
+    r.d = llc + s * hor + t * ver - origin - offset;
+    r.time = time;
     return r;
 }
 

@@ -632,6 +632,7 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_FULLTEX"))) s->tuning.force_fulltex = std::atoi(e);
     if ((e = std::getenv("RTB200_PRIM_SPECIALISE"))) s->tuning.prim_specialise = std::atoi(e);
     if ((e = std::getenv("RTB200_MEGA_OCC"))) s->tuning.mega_occ = std::atoi(e);
+    if ((e = std::getenv("RTB200_MEGA_WAIT"))) s->tuning.mega_wait = std::atoi(e);
     return s;
 }
 void rt_scene_destroy(rt_scene* s) { delete s; }

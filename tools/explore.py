@@ -78,6 +78,11 @@ if __name__ == "__main__":
                 run(14, 1000, 1.0, 10, param=660, label=f"mesh {var}={v} #{rep}")
                 run(5, 600, 1.0, 200, label=f"smoke {var}={v} #{rep}")
                 run(6, 1000, 1.0, 50, label=f"book2 {var}={v} #{rep}")
+    elif what == "fused":
+        run(13, 800, 1.5, 50, label="warm")
+        run(13, 800, 1.5, 500, label="book1 final")
+        run(99, 800, 1.5, 200, label="book1 shipped")
+        run(14, 1000, 1.0, 10, param=660, label="mesh 871k")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
