@@ -368,10 +368,21 @@ def main():
         ref_ach = (algo["bytes_per_segment"] - (B_STATE if fused else 0)) * seg_per_launch / (ext_ms_avg * 1e-3) / 1e9
         roofline["reference_counts"] = {"bytes_per_segment": algo["bytes_per_segment"] - (B_STATE if fused else 0), "box_tests_per_segment": algo["box_tests_per_segment"],
                                         "prim_tests_per_segment": algo["prim_tests_per_segment"], "achieved": ref_ach, "frac": ref_ach / hbm}
+    # second ceiling: FP32 issue, nominal 148 SMs x 128 lanes x 2 x SM clock; flops per segment from the same
+    # device counters with the survey's per-test constants (box 20, sphere 30, moving sphere 40, rect 12, triangle 70, shading ~90)
+    f_prim = {13: 30, 99: 40, 5: 12, 6: 30, 14: 70}.get(sid, 30)
+    fps = 20.0 * st_c["box_tests"] / own_seg + f_prim * st_c["prim_tests"][0] / own_seg + 90.0
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    fl_ach = fps * seg_per_launch / (ext_ms_avg * 1e-3) / 1e12
+    roofline["second_ceiling"] = {"kind": "fp32 issue, nominal (148 SM x 128 lanes x 2 x 1.965 GHz)", "flops_per_segment": fps, "achieved": fl_ach,
+                                  "peak": fp32_peak, "unit": "TFLOP/s", "frac": fl_ach / fp32_peak}
     prof = os.path.join(ROOT, "profiles", "extend_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(args.workload, {}).get("fused" if fused else "wavefront", {}).get("dram_bytes_per_launch")
+            pj = json.load(open(prof)).get(args.workload, {}).get("fused" if fused else "wavefront", {})
+            roofline["traffic"] = pj.get("dram_bytes_per_launch")
+            if "ncu" in pj:
+                roofline["ncu"] = pj["ncu"]  # issue-slot utilisation, active threads per instruction, stalls: what actually bounds the kernel
         except Exception:
             pass
 

@@ -2,7 +2,7 @@
 usage: python tools/sass_lines.py source.csv k.sass [top]
 k.sass = nvdisasm --print-line-info of the cubin (cuobjdump -xelf all librtb200.so).  The n-th instruction of the kernel
 in the csv is matched with the instruction at the same offset in the disassembly."""
-import csv, re, sys, collections, os
+import csv, re, sys, collections, os, subprocess
 src_csv, sass, top = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40
 rows = list(csv.reader(open(src_csv)))
 kname = rows[0][1]
@@ -32,9 +32,11 @@ for l in lines[start + 1:]:
 # function map from the source files
 fn_of = {}
 for f in ("rt_device.cuh", "kernels.cu"):
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "ray_tracing_series_rust_b200", "csrc", "cuda", f)
+    p = os.path.join("ray_tracing_series_rust_b200", "csrc", "cuda", f)
+    rev = os.environ.get("SRC_REV")  # the profile was taken from an older build: read the sources of that commit
+    text = subprocess.run(["git", "show", f"{rev}:{p}"], capture_output=True, text=True, check=True).stdout if rev else open(p).read()
     name = "?"
-    for n, l in enumerate(open(p).read().split("\n"), 1):
+    for n, l in enumerate(text.split("\n"), 1):
         m = re.match(r"^\s*(?:template\s*<[^>]*>\s*)?(?:__device__|__global__|static|RT_DEV|__forceinline__|inline|\s)+[\w:<>\*&\s]*?\b(\w+)\s*\([^;]*$", l)
         if m and ("__device__" in l or "__global__" in l or "RT_DEV" in l): name = m.group(1)
         fn_of[(f, n)] = name
