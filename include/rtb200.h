@@ -288,9 +288,17 @@ RTB_EXPORT int32_t RTB_FN(trace_batch)(rt_scene* s, const rt_ray* rays, int64_t 
 RTB_EXPORT int32_t rt_unit_op(rt_scene* s, int32_t op, uint32_t ia, uint32_t ib, uint32_t ic,
                               uint32_t id, const double* in8, double* out8);
 RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots);
+/* Which builder rt_scene_commit uses in place of BvhNode::new   [ref: src/bvh.rs:14-83; SURVEY.md 8(f) n1].
+ * RT_BVH_HOST_SAH (default): binned SAH on the host, best trees.  RT_BVH_DEVICE_LBVH: instances of >= 4096
+ * primitives are built on the GPU (Morton sort + Karras hierarchy, csrc/cuda/lbvh.cu): ~100x faster commit of
+ * large meshes, trees that cost more boxes per ray.  Results are identical (closest hit is topology independent). */
+#define RT_BVH_HOST_SAH 0
+#define RT_BVH_DEVICE_LBVH 1
+RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder);
 /* Host-only self check of the flattener and BVH builder (needs no GPU): out[0] nodes, [1] max depth,
  * [2] main instances, [3] instances, [4] media, [5..10] primitives per rt_prim_type, [11] leaves,
- * [12] invariant violations (0 = valid), [13] numbered prims, [14] bytes the last commit uploaded. */
+ * [12] invariant violations (0 = valid), [13] numbered prims, [14] bytes the last commit uploaded,
+ * [15] primitives whose BVH the last commit built on the device. */
 RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]);
 #endif
 

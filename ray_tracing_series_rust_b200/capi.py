@@ -296,6 +296,23 @@ class Scene:
     def num_prims(self):
         return self._c(self.api.scene_num_prims(self.h))
 
+    # ---- product-only controls / diagnostics (librtb200.so; the oracle has neither)
+    def set_bvh_builder(self, builder: int):
+        """RT_BVH_HOST_SAH = 0 (default) | RT_BVH_DEVICE_LBVH = 1: who builds the BVH at commit."""
+        fn = self.api.lib.rt_scene_set_bvh_builder
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32]
+        return self._c(fn(self.h, int(builder)))
+
+    def host_check(self):
+        """rt_scene_host_check: flattener / BVH invariants + counters of the last commit (include/rtb200.h)."""
+        fn = self.api.lib.rt_scene_host_check
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.POINTER(C.c_int64)]
+        out = (C.c_int64 * 16)()
+        self._c(fn(self.h, out))
+        keys = ("nodes", "max_depth", "main_instances", "instances", "media", "spheres", "movings", "gravities", "rects", "boxes", "tris", "leaves",
+                "violations", "prims", "bytes_uploaded", "device_built_prims")
+        return dict(zip(keys, [int(x) for x in out]))
+
     # ---- render / trace
     def image_height(self, cfg: RenderConfig) -> int:
         return self._c(self.api.image_height(C.byref(cfg)))

@@ -1,6 +1,8 @@
 // kernels.h — host-callable launchers of the sm_100a kernels (implemented in kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <vector>
 #include <stdint.h>
 
 #include "../../../include/rtb200.h"
@@ -22,6 +24,8 @@ struct RenderJob {
 
 struct RenderTuning {
     int mode = RT_MODE_AUTO;
+    int bvh_builder = 0;            // 0 = host binned SAH (best trees), 1 = device LBVH for instances of >= bvh_device_min primitives (fast commit)
+    int bvh_device_min = 4096;
     int mega_wait = -1;             // k_mega_r (resumable traversal): finished lanes that end a traversal round; 0 = plain k_mega, -1 = auto (20 on large meshes)
     int mega_occ = 0;               // k_mega variant: resident 128-thread blocks per SM; 0 = auto (5 for the scene-specialised variants, else 4)
     uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
@@ -54,6 +58,10 @@ cudaError_t launch_trace_batch(const DeviceScene& scene, const rt_ray* d_rays, i
 // op 1: perlin noise / turbulence of perlin table ia at p = in[0..3) -> out[0], out[1]
 // op 2: philox block ctr = (ia, ib, ic, id) key = (in[0], in[1]) as u32 -> out[0..4) as doubles
 // op 3: camera ray for (seed = ia|ib<<32, path_id = ic|id<<32, i = in[0], j = in[1], W = in[2], H = in[3]) -> out[0..7)
+// Device-side LBVH build of one instance (lbvh.cu); *ok = false -> use the host builder.
+cudaError_t lbvh_build_device(const float* h_boxes, const uint8_t* h_types, uint32_t n, uint32_t max_leaf, uint32_t base, uint32_t type_cursor[PRIM_TYPE_COUNT],
+                              std::vector<BvhNode32>& out_nodes, std::vector<uint32_t>& leaf_order, int* max_depth, float* ms_device, bool* ok);
+
 cudaError_t launch_unit_op(const DeviceScene& scene, int op, uint32_t ia, uint32_t ib, uint32_t ic, uint32_t id, const double* in8, double* out8);
 
 } // namespace rtb

@@ -82,6 +82,8 @@ struct DeviceBuffers { // one grow-only device arena + one pinned staging buffer
     DeviceScene scene;
     bool valid = false;
     size_t bytes = 0; // bytes uploaded by the last commit
+    int64_t device_built_prims = 0; // primitives whose BVH the last commit built on the device (lbvh.cu)
+    float device_build_ms = 0.f;
     void release() {
         if (arena) cudaFree(arena);
         if (staging) cudaFreeHost(staging);
@@ -361,6 +363,8 @@ bool tex_reads_uv(const rt_scene* s, int32_t t, int depth = 0) {
 }
 
 struct HostFlat {
+    float device_build_ms = 0.f;      // device LBVH time (CUDA events), 0 when the host builder ran
+    int64_t device_built_prims = 0;
     std::vector<BvhNode32> nodes;
     std::vector<DSphere> spheres; std::vector<DMoving> movings; std::vector<DGravity> gravities; std::vector<double> gtable;
     std::vector<DRect> rects; std::vector<DBox> boxes; std::vector<DTri> tris;
@@ -378,8 +382,20 @@ struct HostFlat {
 };
 
 // host half of rt_scene_commit: numbering, flattening, BVH build (no CUDA needed)
-int32_t flatten_host(rt_scene* s, HostFlat& HF) {
+struct PhaseTimer { // RTB200_COMMIT_TIMING=1: phase times of rt_scene_commit on stderr
+    bool on = std::getenv("RTB200_COMMIT_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rtb200 commit] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
+int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false) {
     if (s->root < 0) return fail(RT_ERR_STATE, "no root set (rt_scene_set_root)");
+    PhaseTimer pt;
     int32_t next = s->n_prims;
     number_leaves(s, s->root, next);
     s->n_prims = next;
@@ -395,6 +411,7 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF) {
         F.visit(s->root, 0, key, chain, false, 0);
     }
     if (F.status != RT_OK) return fail(F.status, F.error);
+    pt.lap("number + visit");
 
     // domain radius: every coordinate the f32 slab test can see (boxes in instance space, camera origin)
     double R = 1.0;
@@ -436,8 +453,38 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF) {
                 bp[i].type = ib.prims[i].type;
                 bp[i].src = (uint32_t)i;
             }
-            BvhBuilder builder(nodes, bo);
-            BuildResult br = builder.build(bp, cursor);
+            pt.lap("build prims");
+            BuildResult br;
+            bool built = false;
+            if (allow_device_build && s->tuning.bvh_builder == 1 && bp.size() >= (size_t)std::max(16, s->tuning.bvh_device_min)) {
+                // device LBVH (lbvh.cu): the host only rounds the boxes outward to f32 (+ pad), as BvhBuilder does for its nodes
+                std::vector<float> fb(6 * bp.size());
+                std::vector<uint8_t> ft(bp.size());
+                for (size_t i = 0; i < bp.size(); ++i) {
+                    for (int a = 0; a < 3; ++a) { fb[6 * i + a] = f32_floor(bp[i].bmin[a] - bo.pad); fb[6 * i + 3 + a] = f32_ceil(bp[i].bmax[a] + bo.pad); }
+                    ft[i] = (uint8_t)bp[i].type;
+                }
+                if (nodes.size() & 1u) nodes.push_back(BvhNode32{});
+                std::vector<BvhNode32> dn;
+                float ms = 0.f;
+                int depth = 0;
+                const cudaError_t ce = lbvh_build_device(fb.data(), ft.data(), (uint32_t)bp.size(), (uint32_t)bo.max_leaf, (uint32_t)nodes.size(), cursor, dn,
+                                                         br.leaf_order, &depth, &ms, &built);
+                if (ce != cudaSuccess) return fail_cuda(ce, "device BVH build");
+                if (built) {
+                    br.root = (uint32_t)nodes.size();
+                    br.max_depth = depth;
+                    nodes.insert(nodes.end(), dn.begin(), dn.end());
+                    HF.device_build_ms += ms;
+                    HF.device_built_prims += (int64_t)bp.size();
+                }
+            }
+            if (!built) {
+                BvhBuilder builder(nodes, bo);
+                br = builder.build(bp, cursor);
+            }
+            pt.lap(built ? "bvh build (device)" : "bvh build (host SAH)");
+            if (built && pt.on) std::fprintf(stderr, "[rtb200 commit]   of which device kernels %8.3f ms (%zu primitives)\n", (double)HF.device_build_ms, bp.size());
             max_depth = std::max(max_depth, br.max_depth);
             for (uint32_t src : br.leaf_order) {
                 const FlatPrim& p = ib.prims[src];
@@ -486,6 +533,7 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF) {
                 } break;
                 }
             }
+            pt.lap("typed buffers");
             Instance in;
             in.root = br.root;
             in.chain_off = (uint32_t)ops.size();
@@ -567,11 +615,14 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF) {
 
 int32_t do_commit(rt_scene* s) {
     HostFlat HF;
-    const int32_t fr = flatten_host(s, HF);
-    if (fr != RT_OK) return fr;
     int dev_count = 0;
     cudaError_t ce = cudaGetDeviceCount(&dev_count);
-    if (ce != cudaSuccess || dev_count == 0) return fail(RT_ERR_CUDA, "no CUDA device: librtb200 has no CPU fallback");
+    const bool have_device = ce == cudaSuccess && dev_count > 0;
+    const int32_t fr = flatten_host(s, HF, have_device); // scene errors are reported before the missing device
+    if (fr != RT_OK) return fr;
+    if (!have_device) return fail(RT_ERR_CUDA, "no CUDA device: librtb200 has no CPU fallback");
+    s->dev.device_built_prims = HF.device_built_prims;
+    s->dev.device_build_ms = HF.device_build_ms;
     std::vector<BvhNode32>& nodes = HF.nodes;
     std::vector<DSphere>& spheres = HF.spheres; std::vector<DMoving>& movings = HF.movings; std::vector<DGravity>& gravities = HF.gravities;
     std::vector<double>& gtable = HF.gtable;
@@ -633,6 +684,8 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_PRIM_SPECIALISE"))) s->tuning.prim_specialise = std::atoi(e);
     if ((e = std::getenv("RTB200_MEGA_OCC"))) s->tuning.mega_occ = std::atoi(e);
     if ((e = std::getenv("RTB200_MEGA_WAIT"))) s->tuning.mega_wait = std::atoi(e);
+    if ((e = std::getenv("RTB200_BVH_BUILDER"))) s->tuning.bvh_builder = (std::strcmp(e, "lbvh") == 0 || std::strcmp(e, "1") == 0) ? 1 : 0;
+    if ((e = std::getenv("RTB200_BVH_DEVICE_MIN"))) s->tuning.bvh_device_min = std::atoi(e);
     return s;
 }
 void rt_scene_destroy(rt_scene* s) { delete s; }
@@ -1119,10 +1172,18 @@ RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]) {
             if (v != 1) ++violations;
     out[11] = leaves; out[12] = violations; out[13] = s->n_prims;
     out[14] = (int64_t)s->dev.bytes; // bytes uploaded host->device by the last rt_scene_commit
+    out[15] = s->dev.device_built_prims; // primitives whose BVH the last rt_scene_commit built on the device
     return RT_OK;
 }
 
 // wavefront tuning knobs (bench / profiling): wave_slots = resident path slots
+RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder) {
+    CHECK_SCENE(s);
+    if (builder != RT_BVH_HOST_SAH && builder != RT_BVH_DEVICE_LBVH) return fail(RT_ERR_INVALID, "unknown BVH builder");
+    s->tuning.bvh_builder = builder;
+    return RT_OK;
+}
+
 RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots) {
     CHECK_SCENE(s);
     if (wave_slots) s->tuning.wave_slots = wave_slots < 128 ? 128 : wave_slots;

@@ -317,6 +317,34 @@ def test_fused_mode_is_bit_identical_to_wavefront(scene_id):
     assert res[1][2] == 2 and res[0][2] > 2
 
 
+@pytest.mark.parametrize("scene_id,param", [(14, 48), (6, 0), (13, 0), (99, 0)])
+def test_device_lbvh_builder_parity(orc, scene_id, param, monkeypatch):
+    # SURVEY.md 8(f) n1 (csrc/cuda/lbvh.cu replaces BvhNode::new, bvh.rs:14-83): the tree built on the device gives
+    # the oracle's hits and, bit for bit, the image of the host SAH tree (closest hit is topology independent)
+    monkeypatch.setenv("RTB200_BVH_DEVICE_MIN", "16")
+    g, g_sah, o = rtb.new_scene(), rtb.new_scene(), orc.new_scene()
+    g.set_bvh_builder(1)
+    for s in (g, g_sah, o):
+        s.world_build(scene_id, 0xB001, param)
+        s.commit()
+    assert g.host_check()["device_built_prims"] >= 400 and g_sah.host_check()["device_built_prims"] == 0
+    lo, hi, frac = SCENES[scene_id][:3]
+    ties = SCENES[scene_id][3] if len(SCENES[scene_id]) > 3 else 0.0
+    cam = pu.camera_fields(orc, o)
+    tfrac = 1e-3 if scene_id == 14 else 0.0
+    for name, rays in (("primary", pu.primary_rays(cam, 160, 90)), ("random", pu.random_rays(40000, lo, hi, seed=11, time_range=(cam["time1"], cam["time2"])))):
+        hg, ho = g.trace_batch(rays), o.trace_batch(rays)
+        pu.assert_parity(hg, ho, f"lbvh scene {scene_id} {name}", max_id_frac=frac, max_tie_frac=ties, max_t_frac=tfrac, rays=rays)
+        assert np.array_equal(hg["prim_id"], g_sah.trace_batch(rays)["prim_id"])
+    aspect = 1.5 if scene_id == 13 else (16 / 9 if scene_id == 99 else 1.0)
+    cfg = capi.make_config(72, aspect, 6, 50, seed=4)
+    _, a_dev, st_dev = g.render(cfg, want_accum=True)
+    _, a_sah, st_sah = g_sah.render(cfg, want_accum=True)
+    assert np.array_equal(a_dev, a_sah) and st_dev["segments"] == st_sah["segments"]
+    with pytest.raises(capi.RtError):
+        g.set_bvh_builder(7)
+
+
 def test_compat_threads_black_rows_and_ppm(orc, tmp_path):
     # world.rs:1198-1202: rows >= threads * (H / threads) are never rendered (top rows of the PPM)
     g, o = pu.build_pair(orc, 13)

@@ -83,6 +83,21 @@ if __name__ == "__main__":
         run(13, 800, 1.5, 500, label="book1 final")
         run(99, 800, 1.5, 200, label="book1 shipped")
         run(14, 1000, 1.0, 10, param=660, label="mesh 871k")
+    elif what == "bvh":
+        # host binned SAH vs device LBVH: commit wall time (with RTB200_COMMIT_TIMING phases on stderr) and the
+        # cost of the lower-quality tree when tracing (boxes per segment, paths/s)
+        run(13, 800, 1.5, 50, label="warm")
+        os.environ["RTB200_COMMIT_TIMING"] = "1"
+        for b in ("sah", "lbvh", "sah", "lbvh"):
+            os.environ["RTB200_BVH_BUILDER"] = b
+            run(14, 1000, 1.0, 20, param=660, label=f"mesh871k {b}")
+            run(14, 1000, 1.0, 4, param=660, flags=3, label=f"mesh871k {b} COUNTED")
+        os.environ["RTB200_BVH_DEVICE_MIN"] = "16"
+        for b in ("sah", "lbvh"):
+            os.environ["RTB200_BVH_BUILDER"] = b
+            run(13, 800, 1.5, 200, label=f"book1 {b}")
+            run(13, 800, 1.5, 50, flags=3, label=f"book1 {b} COUNTED")
+            run(6, 1000, 1.0, 40, label=f"book2 {b}")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
