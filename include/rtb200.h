@@ -281,6 +281,16 @@ RTB_EXPORT int32_t RTB_FN(trace_batch)(rt_scene* s, const rt_ray* rays, int64_t 
                                        double t_max, int32_t flags, uint64_t seed, rt_hit* out);
 
 #ifndef RTB_PREFIX_ORC
+/* ---------------------------------------------------------------- binary I/O fast paths (product only)
+ * The reference writes P3 text (src/screen.rs:40-59) and reads ASCII PLY / P3 (src/model.rs:13-62, screen.rs:61-95);
+ * those stay byte / parse compatible above.  At 10^6 pixels and 0.87 M faces the text formats are the slowest part
+ * of a run, so: rt_write_ppm_binary writes the same Screen as P6; rt_ply_load and rt_tex_image_ppm accept
+ * "format binary_little_endian 1.0" PLY (vertex = three leading float/double properties, triangle faces) and P6
+ * files, chosen by the file's own header; rt_write_ply_binary / rt_ply_convert_binary produce such PLY files. */
+RTB_EXPORT int32_t rt_write_ppm_binary(const char* path_or_null, const double* screen, int32_t width, int32_t height);
+RTB_EXPORT int32_t rt_write_ply_binary(const char* path, const double* verts, int64_t nv, const uint32_t* idx, int64_t nt);
+RTB_EXPORT int32_t rt_ply_convert_binary(const char* ascii_path, const char* binary_path);
+
 /* ---------------------------------------------------------------- diagnostics (product only)
  * rt_unit_op evaluates one device function on the GPU for unit-level parity checks (SURVEY.md
  * Appendix E3): op 0 Texture::value, 1 Perlin::noise/turbulence, 2 Philox block, 3 camera ray.

@@ -356,6 +356,28 @@ def make_rays(o, d, time=0.0) -> np.ndarray:
     return r
 
 
+def write_ppm_binary(api: Api, path, screen: np.ndarray):
+    """P6 fast path of Screen::write_to_ppm_file (product only, SURVEY.md 8(f) n2)."""
+    s = np.ascontiguousarray(screen, dtype=np.float64)
+    fn = api.lib.rt_write_ppm_binary
+    fn.restype, fn.argtypes = C.c_int32, [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]
+    api.check(fn(str(path).encode() if path is not None else None, s.ctypes.data, s.shape[1], s.shape[0]))
+
+
+def write_ply_binary(api: Api, path, verts: np.ndarray, faces: np.ndarray):
+    v = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1, 3)
+    f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+    fn = api.lib.rt_write_ply_binary
+    fn.restype, fn.argtypes = C.c_int32, [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    api.check(fn(str(path).encode(), v.ctypes.data, v.shape[0], f.ctypes.data, f.shape[0]))
+
+
+def ply_convert_binary(api: Api, ascii_path, binary_path):
+    fn = api.lib.rt_ply_convert_binary
+    fn.restype, fn.argtypes = C.c_int32, [C.c_char_p, C.c_char_p]
+    api.check(fn(str(ascii_path).encode(), str(binary_path).encode()))
+
+
 def write_ppm(api: Api, path, screen: np.ndarray):
     s = np.ascontiguousarray(screen, dtype=np.float64)
     H, W = s.shape[0], s.shape[1]

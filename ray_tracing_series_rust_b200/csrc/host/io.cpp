@@ -2,6 +2,7 @@
 // of the dragon-scale config (~40 MB of text) parses in well under a second.
 #include "io.hpp"
 
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -151,6 +152,186 @@ bool read_ply_ascii(const char* path, double scale, std::vector<double>& verts, 
         p = nl ? nl + 1 : end;
     }
     return true;
+}
+
+// ------------------------------------------------------------------ binary fast paths
+bool write_ppm_p6(const char* path, const double* screen, int32_t W, int32_t H, std::string& err) {
+    std::string out;
+    char hdr[64];
+    const int hn = std::sprintf(hdr, "P6\n%d %d\n255\n", W, H);
+    out.resize((size_t)hn + (size_t)W * H * 3);
+    std::memcpy(&out[0], hdr, (size_t)hn);
+    unsigned char* q = reinterpret_cast<unsigned char*>(&out[0]) + hn;
+    for (int32_t j = H - 1; j >= 0; --j) {
+        const double* row = screen + (size_t)j * W * 3;
+        for (int32_t i = 0; i < 3 * W; ++i) {
+            const double v = row[i];
+            *q++ = (unsigned char)(v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (int)v));
+        }
+    }
+    FILE* f = path ? std::fopen(path, "wb") : stdout;
+    if (!f) { err = std::string("cannot open for writing: ") + path; return false; }
+    const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (path) std::fclose(f); else std::fflush(f);
+    if (!ok) err = "short write";
+    return ok;
+}
+
+bool read_ppm_any(const char* path, int32_t& W, int32_t& H, std::vector<double>& rgb, std::string& err) {
+    {
+        FILE* f = std::fopen(path, "rb");
+        if (!f) { err = std::string("Couldn't open the file: ") + path; return false; }
+        char magic[2] = {0, 0};
+        const size_t got = std::fread(magic, 1, 2, f);
+        std::fclose(f);
+        if (got != 2 || magic[0] != 'P' || magic[1] != '6') return read_ppm_p3(path, W, H, rgb, err);
+    }
+    std::string s;
+    if (!slurp(path, s, err)) return false;
+    // header tokens: P6 W H maxval, separated by whitespace, '#' comments to end of line; one whitespace byte before the samples
+    size_t p = 2;
+    long vals[3] = {0, 0, 0};
+    for (int k = 0; k < 3; ++k) {
+        for (;;) {
+            while (p < s.size() && std::isspace((unsigned char)s[p])) ++p;
+            if (p < s.size() && s[p] == '#') { while (p < s.size() && s[p] != '\n') ++p; continue; }
+            break;
+        }
+        char* e;
+        vals[k] = std::strtol(s.c_str() + p, &e, 10);
+        if (e == s.c_str() + p) { err = "ppm: bad P6 header"; return false; }
+        p = (size_t)(e - s.c_str());
+    }
+    ++p;
+    W = (int32_t)vals[0]; H = (int32_t)vals[1];
+    if (W <= 0 || H <= 0 || vals[2] <= 0 || vals[2] > 255) { err = "ppm: unsupported P6 header"; return false; }
+    const size_t want = (size_t)W * H * 3;
+    if (s.size() < p + want) { err = "ppm: not enough samples"; return false; }
+    rgb.resize(want);
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(s.data()) + p;
+    for (size_t i = 0; i < want; ++i) rgb[i] = (double)q[i];
+    return true;
+}
+
+namespace {
+int ply_type_size(const std::string& t) {
+    if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+    if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+    if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+    if (t == "double" || t == "float64") return 8;
+    return 0;
+}
+bool ply_is_float(const std::string& t) { return t == "float" || t == "float32" || t == "double" || t == "float64"; }
+std::vector<std::string> split_ws(const std::string& line) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i < line.size()) {
+        while (i < line.size() && std::isspace((unsigned char)line[i])) ++i;
+        size_t j = i;
+        while (j < line.size() && !std::isspace((unsigned char)line[j])) ++j;
+        if (j > i) out.push_back(line.substr(i, j - i));
+        i = j;
+    }
+    return out;
+}
+uint64_t load_uint(const unsigned char* p, int size) {
+    uint64_t v = 0;
+    for (int k = 0; k < size; ++k) v |= (uint64_t)p[k] << (8 * k); // little endian
+    return v;
+}
+} // namespace
+
+bool read_ply_any(const char* path, double scale, std::vector<double>& verts, std::vector<uint32_t>& faces, std::string& err) {
+    std::string s;
+    if (!slurp(path, s, err)) return false;
+    // header
+    size_t p = 0;
+    bool binary = false, header_done = false;
+    long nv = 0, nf = 0;
+    int elem = 0; // 1 = vertex, 2 = face, 3 = other
+    std::vector<std::pair<std::string, int>> vprops; // (type, size)
+    int face_count_size = 0, face_index_size = 0, face_props = 0;
+    while (p < s.size()) {
+        size_t nl = s.find('\n', p);
+        if (nl == std::string::npos) nl = s.size();
+        std::string line = s.substr(p, nl - p);
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        p = nl + 1;
+        const std::vector<std::string> tk = split_ws(line);
+        if (tk.empty()) continue;
+        if (tk[0] == "end_header") { header_done = true; break; }
+        if (tk[0] == "format" && tk.size() >= 2) {
+            if (tk[1] == "binary_little_endian") binary = true;
+            else if (tk[1] != "ascii") { err = "ply: unsupported format " + tk[1]; return false; }
+        } else if (tk[0] == "element" && tk.size() >= 3) {
+            elem = tk[1] == "vertex" ? 1 : (tk[1] == "face" ? 2 : 3);
+            if (elem == 1) nv = std::strtol(tk[2].c_str(), nullptr, 10);
+            if (elem == 2) nf = std::strtol(tk[2].c_str(), nullptr, 10);
+        } else if (tk[0] == "property") {
+            if (elem == 1 && tk.size() >= 3) vprops.emplace_back(tk[1], ply_type_size(tk[1]));
+            if (elem == 2) {
+                ++face_props;
+                if (tk.size() >= 5 && tk[1] == "list") { face_count_size = ply_type_size(tk[2]); face_index_size = ply_type_size(tk[3]); }
+            }
+        }
+    }
+    if (!header_done) { err = "ply: no end_header line"; return false; }
+    if (!binary) return read_ply_ascii(path, scale, verts, faces, err);
+    if (nv < 0 || nf < 0) { err = "ply: negative counts"; return false; }
+    if (vprops.size() < 3 || !ply_is_float(vprops[0].first) || !ply_is_float(vprops[1].first) || !ply_is_float(vprops[2].first)) {
+        err = "ply: binary vertices need three leading float/double properties"; return false;
+    }
+    size_t vstride = 0;
+    for (const auto& pr : vprops) { if (pr.second == 0) { err = "ply: unknown vertex property type " + pr.first; return false; } vstride += (size_t)pr.second; }
+    if (face_props != 1 || face_count_size == 0 || face_index_size == 0) { err = "ply: binary faces need exactly one list property"; return false; }
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(s.data()) + p;
+    const unsigned char* end = reinterpret_cast<const unsigned char*>(s.data()) + s.size();
+    if ((size_t)(end - q) < vstride * (size_t)nv) { err = "ply: truncated vertex list"; return false; }
+    verts.resize((size_t)nv * 3);
+    for (long i = 0; i < nv; ++i) {
+        const unsigned char* r = q + vstride * (size_t)i;
+        for (int k = 0; k < 3; ++k) {
+            double v;
+            if (vprops[k].second == 4) { float f; std::memcpy(&f, r, 4); v = (double)f; } else { std::memcpy(&v, r, 8); }
+            verts[3 * (size_t)i + k] = v * scale;
+            r += vprops[k].second;
+        }
+    }
+    q += vstride * (size_t)nv;
+    faces.resize((size_t)nf * 3);
+    for (long i = 0; i < nf; ++i) {
+        if (q + face_count_size > end) { err = "ply: truncated face list"; return false; }
+        const uint64_t cnt = load_uint(q, face_count_size);
+        q += face_count_size;
+        if (cnt != 3) { err = "ply: binary faces must be triangles"; return false; }
+        if (q + 3 * (size_t)face_index_size > end) { err = "ply: truncated face list"; return false; }
+        for (int k = 0; k < 3; ++k) {
+            const uint64_t v = load_uint(q, face_index_size);
+            q += face_index_size;
+            if (v >= (uint64_t)nv) { err = "ply: vertex index out of range"; return false; }
+            faces[3 * (size_t)i + k] = (uint32_t)v;
+        }
+    }
+    return true;
+}
+
+bool write_ply_binary(const char* path, const std::vector<double>& verts, const std::vector<uint32_t>& faces, std::string& err) {
+    FILE* f = std::fopen(path, "wb");
+    if (!f) { err = std::string("cannot open for writing: ") + path; return false; }
+    std::fprintf(f, "ply\nformat binary_little_endian 1.0\nelement vertex %zu\nproperty float x\nproperty float y\nproperty float z\nelement face %zu\n"
+                    "property list uchar int vertex_indices\nend_header\n", verts.size() / 3, faces.size() / 3);
+    std::vector<unsigned char> buf;
+    buf.resize(verts.size() * 4 + faces.size() / 3 * 13);
+    unsigned char* q = buf.data();
+    for (double v : verts) { const float x = (float)v; std::memcpy(q, &x, 4); q += 4; }
+    for (size_t i = 0; i + 2 < faces.size(); i += 3) {
+        *q++ = 3;
+        for (int k = 0; k < 3; ++k) { const int32_t v = (int32_t)faces[i + k]; std::memcpy(q, &v, 4); q += 4; }
+    }
+    const bool ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    std::fclose(f);
+    if (!ok) err = "short write";
+    return ok;
 }
 
 } // namespace rtb

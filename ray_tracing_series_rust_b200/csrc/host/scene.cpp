@@ -741,7 +741,7 @@ int32_t rt_tex_image_ppm(rt_scene* s, const char* path) {
     int32_t w, h;
     std::vector<double> rgb;
     std::string err;
-    if (!read_ppm_p3(path, w, h, rgb, err)) return fail(RT_ERR_IO, err);
+    if (!read_ppm_any(path, w, h, rgb, err)) return fail(RT_ERR_IO, err); // P3 as the reference, or P6
     return rt_tex_image(s, w, h, rgb.data());
 }
 
@@ -834,7 +834,7 @@ int32_t rt_ply_load(rt_scene* s, const char* path, double scale, int32_t mat) {
     Node n; n.kind = N_MESH; n.mat = mat;
     n.mesh = std::make_shared<MeshData>();
     std::string err;
-    if (!read_ply_ascii(path, scale, n.mesh->verts, n.mesh->faces, err)) return fail(RT_ERR_IO, err);
+    if (!read_ply_any(path, scale, n.mesh->verts, n.mesh->faces, err)) return fail(RT_ERR_IO, err); // ASCII as the reference, or binary_little_endian
     return add_node(s, std::move(n));
 }
 int32_t rt_list(rt_scene* s, const int32_t* ids, int32_t cnt) {
@@ -1034,6 +1034,28 @@ int32_t rt_write_ppm(const char* path, const double* screen, int32_t width, int3
     if (!screen || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad screen");
     std::string err;
     if (!write_ppm_p3(path, screen, width, height, err)) return fail(RT_ERR_IO, err);
+    return RT_OK;
+}
+
+int32_t rt_write_ppm_binary(const char* path, const double* screen, int32_t width, int32_t height) {
+    if (!screen || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad screen");
+    std::string err;
+    if (!write_ppm_p6(path, screen, width, height, err)) return fail(RT_ERR_IO, err);
+    return RT_OK;
+}
+int32_t rt_write_ply_binary(const char* path, const double* verts, int64_t nv, const uint32_t* idx, int64_t nt) {
+    if (!path || !verts || !idx || nv <= 0 || nt <= 0) return fail(RT_ERR_INVALID, "bad mesh");
+    std::vector<double> v(verts, verts + 3 * nv);
+    std::vector<uint32_t> f(idx, idx + 3 * nt);
+    std::string err;
+    if (!write_ply_binary(path, v, f, err)) return fail(RT_ERR_IO, err);
+    return RT_OK;
+}
+int32_t rt_ply_convert_binary(const char* ascii_path, const char* binary_path) {
+    if (!ascii_path || !binary_path) return fail(RT_ERR_INVALID, "null path");
+    std::vector<double> v; std::vector<uint32_t> f;
+    std::string err;
+    if (!read_ply_any(ascii_path, 1.0, v, f, err) || !write_ply_binary(binary_path, v, f, err)) return fail(RT_ERR_IO, err);
     return RT_OK;
 }
 

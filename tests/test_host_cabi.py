@@ -189,6 +189,53 @@ def test_ply_and_ppm_io_roundtrip(api, orc, tmp_path):
     assert tuple(out) == tuple(scr[4, 0] / 255.0)
 
 
+def test_binary_io_fast_paths(api, tmp_path):
+    # P6 out/in and binary_little_endian PLY in, next to the byte-compatible text formats
+    rng = np.random.default_rng(1)
+    scr = rng.integers(0, 256, size=(6, 9, 3)).astype(np.float64)
+    p6 = tmp_path / "a6.ppm"
+    capi.write_ppm_binary(api, p6, scr)
+    raw = p6.read_bytes()
+    assert raw.startswith(b"P6\n9 6\n255\n") and len(raw) == len(b"P6\n9 6\n255\n") + 6 * 9 * 3
+    px = np.frombuffer(raw[len(b"P6\n9 6\n255\n"):], dtype=np.uint8).reshape(6, 9, 3)
+    assert np.array_equal(px, scr[::-1].astype(np.uint8))  # rows top-down like the P3 writer
+    s = rtb.new_scene()
+    assert s.tex_image_ppm(p6) == 0  # P6 accepted as an Image texture source
+    p3 = tmp_path / "a3.ppm"
+    capi.write_ppm(api, p3, scr)
+    assert s.tex_image_ppm(p3) == 1
+    # the same mesh as ASCII and as binary PLY flattens to the same scene
+    v = rng.uniform(-1, 1, size=(40, 3)).astype(np.float32).astype(np.float64)
+    f = rng.integers(0, 40, size=(64, 3)).astype(np.uint32)
+    f = f[(f[:, 0] != f[:, 1]) & (f[:, 1] != f[:, 2]) & (f[:, 0] != f[:, 2])]
+    pa, pb, pc = tmp_path / "m_ascii.ply", tmp_path / "m_bin.ply", tmp_path / "m_conv.ply"
+    pa.write_text("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nelement face %d\n"
+                  "property list uchar int vertex_indices\nend_header\n" % (len(v), len(f))
+                  + "".join("%r %r %r\n" % tuple(float(x) for x in r) for r in v) + "".join("3 %d %d %d\n" % tuple(r) for r in f))
+    capi.write_ply_binary(api, pb, v, f)
+    capi.ply_convert_binary(api, pa, pc)
+    assert pb.read_bytes() == pc.read_bytes()
+    checks = []
+    for path in (pa, pb):
+        g = rtb.new_scene()
+        g.set_root(g.bvh([g.ply_load(path, 10.0, g.lambertian((0.2, 0.2, 0.2)))], 0, 1))
+        checks.append(g.host_check())
+    assert checks[0] == checks[1] and checks[0]["tris"] == len(f) and checks[0]["violations"] == 0
+    # a binary PLY with double vertices, an extra vertex property and uint indices
+    hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex 3\nproperty double x\nproperty double y\nproperty double z\nproperty uchar q\n"
+           "element face 1\nproperty list uchar uint vertex_indices\nend_header\n").encode()
+    body = b"".join(np.array(r, dtype="<f8").tobytes() + b"\x07" for r in ((0, 0, 0), (1, 0, 0), (0, 1, 0))) + b"\x03" + np.array([0, 1, 2], dtype="<u4").tobytes()
+    pd = tmp_path / "m_d.ply"
+    pd.write_bytes(hdr + body)
+    g = rtb.new_scene()
+    g.set_root(g.bvh([g.ply_load(pd, 1.0, g.lambertian((0.2, 0.2, 0.2)))], 0, 1))
+    assert g.host_check()["tris"] == 1
+    for bad in (hdr + body[:-2], hdr.replace(b"little", b"big") + body, hdr + body[:-13] + b"\x04" + body[-12:]):
+        pd.write_bytes(bad)
+        with pytest.raises(capi.RtError):
+            g.ply_load(pd, 1.0, 0)
+
+
 @pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
 def test_commit_fails_loudly_without_gpu(api):
     s = rtb.new_scene()
