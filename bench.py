@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--workload", default="book1_final", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (marks the line as a non-headline configuration)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--sharding", default="samples", choices=["samples", "tiles"],
+                    help="N>1: sample ranges of every pixel (default) or 4-row tile bands dealt round-robin (SURVEY 8e alternative)")
     ap.add_argument("--slots", type=int, default=0, help="resident path slots of the wavefront (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads reported under 'also'")
@@ -226,6 +228,10 @@ def main():
     # sample-range shard of this rank
     from ray_tracing_series_rust_b200 import sharding
     spp_total, s_begin, s_end = sharding.sample_range(spp, rank, world, args.scaling)
+    shard_flags = 0
+    if args.sharding == "tiles" and world > 1:  # every rank renders all samples of its own bands; weak scaling still grows spp with N
+        s_begin, s_end = 0, spp_total
+        shard_flags = sharding.tile_flags(rank, world)
     paths_all = W * H * spp_total
 
     stream = torch.cuda.current_stream()
@@ -235,7 +241,7 @@ def main():
     host_screen = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
 
     def one_step(step, timed_extend=False, count=False, local_only=False):
-        cfg = capi.make_config(W, aspect, spp_total, depth, seed=1 + step, sample_begin=s_begin, sample_end=s_end, flags=(1 if timed_extend else 0) | (2 if count else 0))
+        cfg = capi.make_config(W, aspect, spp_total, depth, seed=1 + step, sample_begin=s_begin, sample_end=s_end, flags=(1 if timed_extend else 0) | (2 if count else 0) | shard_flags)
         accum.zero_()
         st = capi.Stats()
         api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
@@ -260,6 +266,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     segments = 0
+    paths_local = 0
     t_wall0 = time.time()
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (outside the timed events)
@@ -269,6 +276,7 @@ def main():
         ev[k][1].record(stream)
         launches += st["kernel_launches"] + (1 if rank == 0 else 0)
         segments += st["segments"]
+        paths_local += st["paths"]
     barrier()
     t_wall = time.time() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
@@ -289,7 +297,7 @@ def main():
         t0 = time.time()
         scene.commit()
         t_commit = time.time()
-        cfg = capi.make_config(W, aspect, spp_total, depth, seed=100 + k, sample_begin=s_begin, sample_end=s_end)
+        cfg = capi.make_config(W, aspect, spp_total, depth, seed=100 + k, sample_begin=s_begin, sample_end=s_end, flags=shard_flags)
         accum.zero_()
         st = capi.Stats()
         api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
@@ -392,8 +400,9 @@ def main():
         "vs_baseline": (value / README_BOOK1_10T_PATHS_PER_S) if (args.workload == "book1_final" and not args.spp) else None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "image": [W, H], "spp_per_gpu": s_end - s_begin, "spp_total": spp_total, "max_depth": depth,
-                   "paths_per_step": paths_all, "segments_per_path": segments / max(1, (s_end - s_begin) * W * H * args.steps),
-                   "sharding": "sample ranges + one NCCL int64 reduce to rank 0" if world > 1 else "single GPU",
+                   "paths_per_step": paths_all, "segments_per_path": segments / max(1, paths_local),
+                   "sharding": ("single GPU" if world == 1 else ("4-row tile bands round-robin + one NCCL int64 reduce (disjoint pixels) to rank 0" if shard_flags
+                                                                      else "sample ranges + one NCCL int64 reduce to rank 0")),
                    "render_mode": "fused persistent kernel (RT_MODE_AUTO)" if fused else "wavefront (RT_MODE_AUTO)",
                    "l2": "flushed between timed steps (256 MiB memset, untimed); path state > L2",
                    "vs_baseline_note": "README.md:23 146.440 s on 10 threads of an unspecified CPU => 1.456e6 paths/s (derived)",
@@ -553,6 +562,48 @@ def extra_workloads(api, rtb, capi, stream):
             del accum
         except Exception as e:  # a secondary workload must not take the headline line down
             out[name] = {"error": str(e)}
+    try:  # SURVEY.md 8(f) n1 / n2 on the mesh-room inputs: commit with the host SAH vs the device LBVH builder, text vs binary I/O
+        import glob
+        import numpy as np
+        sid, sseed, param, W, aspect, spp, depth, cam, desc = WORKLOADS["mesh_room"]
+        rec = {}
+        for label, builder in (("host_sah", 0), ("device_lbvh", 1)):
+            s = rtb.new_scene()
+            s.world_build(sid, sseed, param)
+            s.set_bvh_builder(builder)
+            t0 = time.time()
+            s.commit()
+            rec[label + "_commit_s"] = time.time() - t0
+            rec[label + "_device_built_prims"] = s.host_check()["device_built_prims"] if builder else 0
+            cfg = capi.make_config(W, aspect, 20, depth, seed=7)
+            s.render(cfg)
+            st = s.render(cfg)[2]
+            rec[label + "_paths_per_s"] = st["paths"] / (st["ms_device"] * 1e-3)
+            s.close()
+        plys = sorted(glob.glob("/tmp/rtb200_mesh_*_%d.ply" % param))
+        if plys:
+            binp = plys[-1] + ".bin.ply"
+            capi.ply_convert_binary(api, plys[-1], binp)
+            for label, path in (("ply_ascii", plys[-1]), ("ply_binary", binp)):
+                s = rtb.new_scene()
+                m = s.lambertian((0.2, 0.2, 0.2))
+                t0 = time.time()
+                s.ply_load(path, 1.0, m)
+                rec[label + "_load_s"] = time.time() - t0
+                rec[label + "_MB"] = os.path.getsize(path) / 1e6
+                s.close()
+            os.remove(binp)
+        scr = np.random.default_rng(0).integers(0, 256, size=(1000, 1000, 3)).astype(np.float64)
+        outp = os.path.join(ROOT, "gpurun_out", "_bench_io.ppm") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "/tmp/_bench_io.ppm"
+        for label, fn in (("ppm_p3", capi.write_ppm), ("ppm_p6", capi.write_ppm_binary)):
+            t0 = time.time()
+            fn(api, outp, scr)
+            rec[label + "_write_s"] = time.time() - t0
+        os.remove(outp)
+        out["next_rows"] = {"description": "SURVEY 8(f): n1 commit of the 871200-triangle mesh room per BVH builder (+ paths/s of the tree at 20 spp); "
+                                           "n2 ASCII vs binary PLY load of that mesh, P3 vs P6 write of a 1000x1000 Screen (host)", **rec}
+    except Exception as e:
+        out["next_rows"] = {"error": str(e)}
     return out
 
 

@@ -191,6 +191,15 @@ typedef struct rt_render_config {
 #define RT_RENDER_COUNT_EVENTS 2    /* count BVH boxes tested / primitive tests on the device -> rt_stats */
 #define RT_RENDER_FORCE_WAVEFRONT 4 /* wavefront mode: k_extend + k_shade_all per iteration, per-material queues */
 #define RT_RENDER_FORCE_FUSED 8     /* fused mode: one persistent kernel, path state in registers */
+/* Tile sharding (the GPU analogue of the reference's row bands, world.rs:1198-1227): the image is cut
+ * into bands of RT_TILE_ROWS rows; a call with RT_RENDER_TILE_SHARD(rank, count) in `flags` renders only the bands
+ * b with b % count == rank (all samples of their pixels); the other pixels of out_accum / out_screen stay 0.  Path ids
+ * use the global pixel index, so the sum of the `count` shards is bit-identical to the unsharded render.  Both
+ * libraries implement it; it composes with sample_begin / sample_end. */
+#define RT_TILE_ROWS 4
+#define RT_RENDER_TILE_SHARD(rank, count) ((((rank) & 0x7f) << 16) | (((count) & 0x7f) << 24))
+#define RT_RENDER_TILE_RANK(flags) (((flags) >> 16) & 0x7f)
+#define RT_RENDER_TILE_COUNT(flags) (((flags) >> 24) & 0x7f)
 /* fixed-point scale of the radiance accumulator: sum of samples * 2^32 in an int64 per channel */
 #define RT_ACCUM_SCALE_LOG2 32
 

@@ -390,6 +390,9 @@ int32_t orc_render(rt_scene* s, const rt_render_config* cfg, double* out_screen,
     const Color background = s->background;
     const int32_t max_depth = cfg->max_depth;
     const uint64_t seed = cfg->seed;
+    const int32_t tile_count = RT_RENDER_TILE_COUNT(cfg->flags) > 1 ? RT_RENDER_TILE_COUNT(cfg->flags) : 1;
+    const int32_t tile_rank = tile_count > 1 ? RT_RENDER_TILE_RANK(cfg->flags) : 0;
+    if (tile_rank >= tile_count) return fail(RT_ERR_INVALID, "tile shard rank >= count");
     // static contiguous row bands, one per thread (world.rs:1198-1227)
     const int32_t chunk = (rows + threads - 1) / threads;
     std::vector<std::thread> pool;
@@ -400,6 +403,7 @@ int32_t orc_render(rt_scene* s, const rt_render_config* cfg, double* out_screen,
             PathCtx c;
             tls_ctx() = &c;
             for (int32_t j = start; j < end; ++j) {
+                if (tile_count > 1 && (j / RT_TILE_ROWS) % tile_count != tile_rank) continue; // RT_RENDER_TILE_SHARD: not this shard's band
                 for (int32_t i = 0; i < W; ++i) {
                     Vec3 pixel(0, 0, 0);
                     for (int32_t sidx = s0; sidx < s1; ++sidx) {

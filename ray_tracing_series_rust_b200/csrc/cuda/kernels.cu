@@ -64,6 +64,7 @@ struct JobDev {
     uint32_t n_slots;
     int32_t count_events;
     uint32_t wait_thresh; // k_mega_r: finished lanes that end a traversal round
+    uint32_t tile_rank, tile_count; // RT_RENDER_TILE_SHARD: npix_rendered counts this shard's pixels only
 };
 
 // Path-state chunks are streamed (read once / written once per kernel): evict-first hints keep them from
@@ -126,6 +127,14 @@ __global__ void k_init(PathState P, Queues Q, uint32_t n) {
     if (blockIdx.x == 0 && threadIdx.x < 9) Q.stats[threadIdx.x] = 0ull;
 }
 
+// Tile sharding: the shard's pixels are enumerated densely (local row lr = band lr / 4 of this rank, line lr % 4);
+// the global pixel index (accumulator address, Philox path id) is that of the unsharded image.
+RT_DEV uint32_t shard_pixel(const JobDev& J, uint32_t q) {
+    if (J.tile_count <= 1u) return q;
+    const uint32_t W = (uint32_t)J.W, lr = q / W, x = q - lr * W;
+    const uint32_t band = (lr / RT_TILE_ROWS) * J.tile_count + J.tile_rank;
+    return (band * RT_TILE_ROWS + lr % RT_TILE_ROWS) * W + x;
+}
 // L -> (sample, pixel) without 64-bit integer division: quotient estimate in f64 (exact for L < 2^53) + one correction step
 RT_DEV void split_path_index(unsigned long long L, uint32_t npix, uint32_t& s_local, uint32_t& pix) {
     uint32_t q = (uint32_t)__double2uint_rz(__ull2double_rz(L) / (double)npix);
@@ -152,6 +161,7 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
     // sample-major order: consecutive path indices are neighbouring pixels of one sample => coherent primary rays
     uint32_t s_local, pix;
     split_path_index(L, J.npix_rendered, s_local, pix);
+    pix = shard_pixel(J, pix);
     const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix - (uint32_t)j * (uint32_t)J.W);
     const uint64_t path_id = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
     uint32_t draw0;
@@ -507,6 +517,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                 } else {
                     uint32_t s_local;
                     split_path_index(L, J.npix_rendered, s_local, pixel);
+                    pixel = shard_pixel(J, pixel);
                     const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
                     path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
                     r = camera_first_ray<PathRngOol>(S.cam, ii, j, J.W, J.H, J.seed, path_id, draw); // world.rs:1212-1214
@@ -604,6 +615,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
                 } else {
                     uint32_t s_local;
                     split_path_index(L, J.npix_rendered, s_local, pixel);
+                    pixel = shard_pixel(J, pixel);
                     const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
                     path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
                     r = camera_first_ray<PathRngOol>(S.cam, ii, j, J.W, J.H, J.seed, path_id, draw); // world.rs:1212-1214
@@ -862,7 +874,14 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
     JobDev J;
     J.W = job.width; J.H = job.height; J.rows = job.rows; J.spp_total = job.spp_total;
     J.sample_begin = job.sample_begin; J.max_depth = job.max_depth;
-    J.npix_rendered = (uint32_t)job.width * (uint32_t)job.rows;
+    J.tile_rank = (uint32_t)job.tile_rank; J.tile_count = (uint32_t)std::max(1, job.tile_count);
+    uint32_t local_rows = (uint32_t)job.rows;
+    if (J.tile_count > 1u) { // rows of [0, rows) whose band belongs to this shard; only the image's last band can be partial
+        local_rows = 0;
+        for (uint32_t b = J.tile_rank; b * RT_TILE_ROWS < (uint32_t)job.rows; b += J.tile_count)
+            local_rows += std::min<uint32_t>(RT_TILE_ROWS, (uint32_t)job.rows - b * RT_TILE_ROWS);
+    }
+    J.npix_rendered = (uint32_t)job.width * local_rows;
     J.total_paths = (unsigned long long)J.npix_rendered * (unsigned long long)(job.sample_end - job.sample_begin);
     J.seed = job.seed;
     J.count_events = tune.count_events;

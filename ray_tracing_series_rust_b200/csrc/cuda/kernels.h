@@ -16,6 +16,7 @@ struct RenderJob {
     int32_t sample_begin, sample_end; // this call's shard
     int32_t max_depth;
     uint64_t seed;
+    int32_t tile_rank = 0, tile_count = 1; // RT_RENDER_TILE_SHARD: this call renders the row bands b with b % tile_count == tile_rank
 };
 
 #define RT_MODE_WAVEFRONT 0 // k_extend + k_shade_all per iteration, per-material queues, path state in HBM

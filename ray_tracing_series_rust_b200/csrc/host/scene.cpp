@@ -968,6 +968,9 @@ static int32_t make_job(rt_scene* s, const rt_render_config* cfg, RenderJob& job
     if (job.sample_begin < 0 || job.sample_end > job.spp_total || job.sample_begin > job.sample_end) return fail(RT_ERR_INVALID, "bad sample range");
     job.max_depth = cfg->max_depth;
     job.seed = cfg->seed;
+    job.tile_count = RT_RENDER_TILE_COUNT(cfg->flags) > 1 ? RT_RENDER_TILE_COUNT(cfg->flags) : 1;
+    job.tile_rank = job.tile_count > 1 ? RT_RENDER_TILE_RANK(cfg->flags) : 0;
+    if (job.tile_rank >= job.tile_count) return fail(RT_ERR_INVALID, "tile shard rank >= count");
     return RT_OK;
 }
 

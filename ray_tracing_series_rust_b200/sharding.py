@@ -35,3 +35,20 @@ def frames_for_rank(n_frames: int, rank: int, world: int):
     if world < 1 or not (0 <= rank < world) or n_frames < 0:
         raise ValueError("bad shard request")
     return list(range(rank, n_frames, world))
+
+
+TILE_ROWS = 4  # RT_TILE_ROWS (include/rtb200.h)
+
+
+def tile_flags(rank: int, world: int) -> int:
+    """rt_render_config.flags bits of RT_RENDER_TILE_SHARD(rank, world): rank renders the 4-row bands b with
+    b % world == rank (SURVEY.md 8e "tile sharding", the GPU analogue of the row bands of world.rs:1198-1227).
+    The shards are disjoint, so the image is their sum (same reduce as sample sharding) or a gather of the bands."""
+    if world < 1 or world > 127 or not (0 <= rank < world):
+        raise ValueError("bad shard request")
+    return 0 if world == 1 else ((rank & 0x7F) << 16) | ((world & 0x7F) << 24)
+
+
+def tile_rows(height: int, rank: int, world: int):
+    """Row indices (Screen rows, 0 = bottom) rank owns under tile sharding."""
+    return [j for j in range(height) if (j // TILE_ROWS) % world == rank]

@@ -345,6 +345,36 @@ def test_device_lbvh_builder_parity(orc, scene_id, param, monkeypatch):
         g.set_bvh_builder(7)
 
 
+def test_tile_sharding_is_bit_identical_and_matches_oracle(orc):
+    # SURVEY.md 8(e) tile sharding: 4-row bands dealt round-robin; H = 53 (not a multiple of 4), 3 shards, both render modes
+    from ray_tracing_series_rust_b200 import sharding
+    g, o = pu.build_pair(orc, 13)
+    W, aspect, spp = 80, 1.5, 5
+    for mode in (4, 8):
+        _, full, st = g.render(capi.make_config(W, aspect, spp, 50, seed=6, flags=mode), want_accum=True)
+        H = full.shape[0]
+        assert H == 53
+        total, paths = np.zeros_like(full), 0
+        for r in range(3):
+            fl = mode | sharding.tile_flags(r, 3)
+            scr, part, stp = g.render(capi.make_config(W, aspect, spp, 50, seed=6, flags=fl), want_accum=True)
+            mine = sharding.tile_rows(H, r, 3)
+            other = [j for j in range(H) if j not in mine]
+            assert np.array_equal(part[mine], full[mine]) and not part[other].any() and not scr[other].any()
+            assert stp["paths"] == len(mine) * W * spp
+            total += part
+            paths += stp["paths"]
+        assert np.array_equal(total, full) and paths == st["paths"]
+    # a tile shard combined with a sample range and the compat_threads row limit, against the oracle
+    cfg = capi.make_config(W, aspect, spp, 50, seed=6, compat_threads=10, sample_begin=1, sample_end=4, flags=sharding.tile_flags(2, 3))
+    _, ag, sg = g.render(cfg, want_accum=True)
+    _, ao, so = o.render(cfg, want_accum=True)
+    assert sg["paths"] == so["paths"] and sg["segments"] == so["segments"]
+    fg, fo = ag / capi.ACCUM_SCALE, ao / capi.ACCUM_SCALE
+    assert (np.abs(fg - fo) <= 1e-5 * np.maximum(1e-3, np.abs(fo))).all()
+    assert not ag[50:].any()  # rows >= 10 * (53 / 10) stay unrendered (world.rs:1198-1202)
+
+
 def test_compat_threads_black_rows_and_ppm(orc, tmp_path):
     # world.rs:1198-1202: rows >= threads * (H / threads) are never rendered (top rows of the PPM)
     g, o = pu.build_pair(orc, 13)

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, scaling, out_path):
+def _worker(rank, world, port, scaling, out_path, tiles=False):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -35,8 +35,12 @@ def _worker(rank, world, port, scaling, out_path):
     s.world_build(5, 0xB002)
     s.commit()
     spp = 6
-    total, b, e = sharding.sample_range(spp, rank, world, scaling)
-    cfg = capi.make_config(40, 1.0, total, 50, seed=3, sample_begin=b, sample_end=e, threads=2)
+    if tiles:  # tile sharding: every rank renders all samples of its own 4-row bands
+        total, b, e = spp, 0, spp
+        cfg = capi.make_config(40, 1.0, total, 50, seed=3, threads=2, flags=sharding.tile_flags(rank, world))
+    else:
+        total, b, e = sharding.sample_range(spp, rank, world, scaling)
+        cfg = capi.make_config(40, 1.0, total, 50, seed=3, sample_begin=b, sample_end=e, threads=2)
     _, acc, st = s.render(cfg, want_accum=True)
     t = torch.from_numpy(acc)
     paths = torch.tensor([st["paths"]], dtype=torch.int64)
@@ -65,6 +69,30 @@ def test_two_rank_sample_sharding_matches_single_process(orc, tmp_path, scaling)
     assert paths == st["paths"] == 40 * 40 * total
     # the oracle rounds each shard's f64 sum to fixed point once, so shards differ from the whole by at most one unit per rank
     assert np.abs(got - ref).max() <= world
+
+
+def test_two_rank_tile_sharding_matches_single_process(orc, tmp_path):
+    from ray_tracing_series_rust_b200 import capi, sharding
+    world = 2
+    out = str(tmp_path / "acc_tiles.npy")
+    mp.spawn(_worker, args=(world, _free_port(), "strong", out, True), nprocs=world, join=True)
+    got = np.load(out)
+    s = orc.new_scene()
+    s.world_build(5, 0xB002)
+    s.commit()
+    _, ref, st = s.render(capi.make_config(40, 1.0, 6, 50, seed=3, threads=2), want_accum=True)
+    assert int(np.load(out + ".paths.npy")[0]) == st["paths"] == 40 * 40 * 6
+    assert np.array_equal(got, ref)  # disjoint pixels: the sum is exact
+    # one shard alone: its bands equal the full render, the other rows are untouched zeros
+    _, part, stp = s.render(capi.make_config(40, 1.0, 6, 50, seed=3, threads=2, flags=sharding.tile_flags(1, 3)), want_accum=True)
+    mine = sharding.tile_rows(40, 1, 3)
+    other = [j for j in range(40) if j not in mine]
+    assert np.array_equal(part[mine], ref[mine]) and not part[other].any() and stp["paths"] == len(mine) * 40 * 6
+    assert sorted(sum((sharding.tile_rows(41, r, 3) for r in range(3)), [])) == list(range(41))
+    with pytest.raises(capi.RtError):
+        s.render(capi.make_config(40, 1.0, 6, 50, flags=(5 << 16) | (3 << 24)))
+    with pytest.raises(ValueError):
+        sharding.tile_flags(3, 3)
 
 
 def test_sample_range_partition():
