@@ -346,7 +346,7 @@ def main():
 
     cpu = None
     algo = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N=1 only (the other ranks have left; keep the N>1 lines short)
         c = run_cpu_sample(wl, args.cpu_seconds, os.cpu_count() or 1)
         algo = oracle_counts_per_segment(c["stats"])
         cpu = {"value": c["paths_per_s"], "unit": "paths/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": c["sample"],
