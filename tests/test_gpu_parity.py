@@ -454,3 +454,64 @@ def test_full_size_book1_properties(orc):
     # quantisation (vec3.rs:89-107) of the GPU accumulator equals the Screen the library returned
     ref = np.floor(255.9 * np.clip(np.sqrt(ag / capi.ACCUM_SCALE * (1.0 / spp)), 0, 1))
     assert np.array_equal(ref, sg)
+
+
+@pytest.mark.parametrize("name,scene_id,W,aspect,spp,camera", [
+    ("C2 cornell smoke", 5, 600, 1.0, 1000, None),                 # BASELINE configs[1] at full size
+    ("C3 book-2 final", 6, 1000, 1.0, 200, None),                  # configs[2]: full image, 200 of the 10 000 spp (the bench runs all of them)
+    ("C5 animation frame 100", 8, 800, 1.5, 200, ((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.1, 10.0, 40.0, 40.4)),  # configs[4], one frame
+])
+def test_full_size_config_properties(orc, name, scene_id, W, aspect, spp, camera):
+    """The other BASELINE configs at their full image size: path count, sample-range and tile-shard linearity
+    (bit-exact), and random pixels recomputed path by path by the oracle."""
+    from ray_tracing_series_rust_b200 import sharding
+    g, o = pu.build_pair(orc, scene_id, seed={5: 0xB002, 6: 0xB002, 8: 0xB005}[scene_id], camera=camera)
+    cfg = capi.make_config(W, aspect, spp, 50, seed=3)
+    sg, ag, st = g.render(cfg, want_accum=True)
+    H = sg.shape[0]
+    assert st["paths"] == W * H * spp and 2.0 < st["segments"] / st["paths"] < 12.0
+    a, b = spp // 3, spp
+    parts = [g.render(capi.make_config(W, aspect, spp, 50, seed=3, sample_begin=x, sample_end=y), want_accum=True)[1] for x, y in ((0, a), (a, b))]
+    assert np.array_equal(ag, parts[0] + parts[1])
+    tiles = [g.render(capi.make_config(W, aspect, spp, 50, seed=3, flags=sharding.tile_flags(r, 2)), want_accum=True)[1] for r in range(2)]
+    assert np.array_equal(ag, tiles[0] + tiles[1])
+    rng = np.random.default_rng(4)
+    bad = 0
+    pix = rng.integers(0, W * H, size=24)
+    for p in pix:
+        ids = np.arange(spp, dtype=np.uint64) + np.uint64(p) * np.uint64(spp)
+        rad = orc.path_radiance(o, cfg, ids).sum(axis=0)
+        got = ag[p // W, p % W] / capi.ACCUM_SCALE
+        if np.abs(got - rad).max() > 1e-5 * max(rad.max(), 1.0):
+            bad += 1  # a path that took another branch at a documented tie / f32 slab grazing case: bounded, not systematic
+            assert np.abs(got - rad).max() < 0.05 * max(rad.max(), 1.0), (name, int(p))
+    assert bad <= 4, (name, bad)
+    ref = np.floor(255.9 * np.clip(np.sqrt(ag / capi.ACCUM_SCALE * (1.0 / spp)), 0, 1))
+    assert np.array_equal(ref, sg)
+
+
+def test_full_size_mesh_room_properties():
+    """BASELINE configs[3] (871 200 triangles, 1000x1000) without the oracle (its reference-style build of that mesh is too slow
+    for a test): the resumable fused kernel, the plain fused kernel and the wavefront agree bit for bit, the device-built
+    BVH gives the same image, and sample ranges add up."""
+    g = rtb.new_scene()
+    g.world_build(14, 0xB004, 660)
+    g.commit()
+    assert g.host_check()["tris"] == 871200
+    W, spp = 1000, 6
+    res = {}
+    for label, flags in (("auto", 0), ("fused", 8), ("wavefront", 4)):
+        _, acc, st = g.render(capi.make_config(W, 1.0, spp, 50, seed=9, flags=flags), want_accum=True)
+        res[label] = acc
+        assert st["paths"] == W * W * spp
+    assert np.array_equal(res["auto"], res["fused"]) and np.array_equal(res["auto"], res["wavefront"])
+    halves = [g.render(capi.make_config(W, 1.0, spp, 50, seed=9, sample_begin=x, sample_end=y), want_accum=True)[1] for x, y in ((0, 2), (2, 6))]
+    assert np.array_equal(res["auto"], halves[0] + halves[1])
+    gl = rtb.new_scene()
+    gl.set_bvh_builder(1)
+    gl.world_build(14, 0xB004, 660)
+    gl.commit()
+    assert gl.host_check()["device_built_prims"] >= 871200
+    _, acc_l, _ = gl.render(capi.make_config(W, 1.0, spp, 50, seed=9), want_accum=True)
+    assert np.array_equal(acc_l, res["auto"])
+
