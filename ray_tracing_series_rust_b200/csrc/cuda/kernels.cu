@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
 // two modes produce bit-identical images.
 #define RT_MEGA_CHUNK 512u
-template <bool MEDIA, int MINB, bool GENERAL_MEDIA, bool FULLTEX, uint32_t PM = RT_PM_ALL, bool XF = true>
+template <bool MEDIA, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL, bool XF = true>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         if (!alive) continue;
         // ---- one ray_color iteration (world.rs:63-91)
         HitRec h;
-        const bool hit = world_hit<false, FULLTEX ? 2 : 0, MEDIA, GENERAL_MEDIA, PM, XF>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        const bool hit = world_hit<false, 2, MEDIA, GENERAL_MEDIA, PM, XF>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
         ++my_segments;
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         } else {
             const DMaterial m = S.materials[h.mat];
             if (m.type == MAT_LIGHT) {
-                const F3 e = tex_value<FULLTEX>(S, m.tex, h.u, h.v, h.p);
+                const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
                 contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
             } else {
                 PathRngOol g;
@@ -550,10 +550,10 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
                 bool scattered;
-                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian<FULLTEX>(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
                 else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
                 else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
-                else scattered = scatter_isotropic<FULLTEX>(S, m, h.p, h.u, h.v, g, dir, att);
+                else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
                 if (scattered && (int32_t)(segment + 1) < J.max_depth) {
                     tr *= att.x; tg *= att.y; tb *= att.z;
                     r.o = h.p; r.d = dir;
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
 // idle lanes claim new paths -> every lane with a ray walks the BVH until `wait_thresh` lanes have finished ->
 // the finished lanes shade / scatter / start their next segment, the others keep their traversal state and
 // continue in the next round.  Per-path arithmetic and Philox streams are those of k_mega: bit-identical images.
-template <int MINB, bool FULLTEX, uint32_t PM>
+template <int MINB, uint32_t PM>
 __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                         int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
@@ -640,10 +640,10 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
         if (best.type == RT_NONE) {
             contrib = mkf3(tr * S.background[0], tg * S.background[1], tb * S.background[2]);
         } else {
-            const HitRec h = finalize_hit<FULLTEX ? 2 : 0, PM, false>(S, r, best);
+            const HitRec h = finalize_hit<2, PM, false>(S, r, best);
             const DMaterial m = S.materials[h.mat];
             if (m.type == MAT_LIGHT) {
-                const F3 e = tex_value<FULLTEX>(S, m.tex, h.u, h.v, h.p);
+                const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
                 contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
             } else {
                 PathRngOol g;
@@ -651,10 +651,10 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
                 bool scattered;
-                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian<FULLTEX>(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
                 else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
                 else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
-                else scattered = scatter_isotropic<FULLTEX>(S, m, h.p, h.u, h.v, g, dir, att);
+                else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
                 if (scattered && (int32_t)(segment + 1) < J.max_depth) {
                     tr *= att.x; tg *= att.y; tb *= att.z;
                     r.o = h.p; r.d = dir;
@@ -842,29 +842,31 @@ static cudaError_t ensure_workspace(Workspace*& w, uint32_t N) {
 
 static int g_prim_specialise = 1;
 
-template <bool MEDIA, bool COUNT>
-static void launch_extend_p(int occ, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
-    // persistent: exactly the resident number of CTAs (148 SMs x occ)
-    if (occ >= 5) k_extend_p<MEDIA, COUNT, 5><<<148 * 5, 128, 0, st>>>(scene, J, P, Q, parity);
-    else if (occ == 4) k_extend_p<MEDIA, COUNT, 4><<<148 * 4, 128, 0, st>>>(scene, J, P, Q, parity);
-    else k_extend_p<MEDIA, COUNT, 3><<<148 * 3, 128, 0, st>>>(scene, J, P, Q, parity);
+template <bool COUNT>
+static void launch_extend_p(cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
+    // persistent: exactly the resident number of CTAs (148 SMs x 4); chosen only for media-free scenes with large meshes
+    k_extend_p<false, COUNT, 4><<<148 * 4, 128, 0, st>>>(scene, J, P, Q, parity);
 }
 
 template <bool MEDIA, bool COUNT>
-static void launch_extend(int occ, int blocks, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
-    // occ = resident 128-thread blocks per SM the kernel is compiled for (register budget 128 / 96 / 80).
-    // Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without the general two-traversal path.
-    const bool general = MEDIA && !(scene.flags & 2u);
-    if (general) {
-        k_extend<MEDIA, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-    } else if (MEDIA && !COUNT && g_prim_specialise && (scene.prim_mask & ~0x18u) == 0) {
-        k_extend<MEDIA, COUNT, 4, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
-    } else if (MEDIA && !COUNT && g_prim_specialise && (scene.prim_mask & ~0x1bu) == 0) {
-        k_extend<MEDIA, COUNT, 4, false, 0x1bu><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // spheres, moving spheres, rects, boxes (book-2 final)
+static void launch_extend(int blocks, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
+    // MINB = resident 128-thread blocks per SM the kernel is compiled for: 4 (128 registers) with media or event counters,
+    // 5 (96 registers) otherwise.  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
+    // the general two-traversal path; the two media scenes of the reference also get their primitive mask compiled in.
+    if constexpr (MEDIA) {
+        if (!(scene.flags & 2u)) {
+            k_extend<true, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        } else if (!COUNT && g_prim_specialise && (scene.prim_mask & ~0x18u) == 0) {
+            k_extend<true, false, 4, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
+        } else if (!COUNT && g_prim_specialise && (scene.prim_mask & ~0x1bu) == 0) {
+            k_extend<true, false, 4, false, 0x1bu><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // spheres, moving spheres, rects, boxes (book-2 final)
+        } else {
+            k_extend<true, COUNT, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        }
+    } else if constexpr (COUNT) {
+        k_extend<false, true, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
     } else {
-        if (occ >= 6) k_extend<MEDIA, COUNT, 6, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-        else if (occ == 5) k_extend<MEDIA, COUNT, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-        else k_extend<MEDIA, COUNT, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        k_extend<false, false, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
     }
 }
 
@@ -906,7 +908,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         const int qblocks = (int)std::min<uint32_t>((N + 255) / 256, 148 * 8);
         const bool media = scene.n_media != 0;
         g_prim_specialise = tune.prim_specialise;
-        const int ext_occ = tune.extend_occ > 0 ? tune.extend_occ : (media ? 4 : 5);
+        const int ext_occ = (media || tune.count_events) ? 4 : 5; // resident CTAs per SM of the k_extend variant launch_extend picks
         // measured (profiles/): the warp-scheduled persistent kernel wins on deep triangle BVHs (+22 % on the 871k mesh),
         // the one-ray-per-thread kernel on small scenes and on scenes with media
         const int ext_kind = tune.extend_kind >= 0 ? tune.extend_kind : ((!media && (scene.flags & 4u)) ? 1 : 0);
@@ -917,60 +919,35 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         const int mode = tune.mode != RT_MODE_AUTO ? tune.mode : ((scene.n_media == 0 && !(scene.flags & 8u)) ? RT_MODE_FUSED : RT_MODE_WAVEFRONT);
         if (mode == RT_MODE_FUSED) {
             k_mega_init<<<1, 32, 0, stream>>>(Q);
-            // resident CTAs per SM: the scene-specialised variants fit 96 registers without spills (5 CTAs), the generic ones need 128 (4 CTAs)
-            const bool specialised = tune.prim_specialise == 2 && !media && !(scene.flags & 32u) &&
-                                     (scene.prim_mask == 0x1u || (scene.prim_mask & ~0x3u) == 0 || (scene.prim_mask & ~0x28u) == 0);
-            const int occ = tune.mega_occ > 0 ? std::max(3, std::min(6, tune.mega_occ)) : (specialised ? 5 : 4);
-            const int mblocks = 148 * occ;
-            // Measured (tools/explore.py ab RTB200_FULLTEX 0,1): the variant WITHOUT the Noise/Image texture code is 15 % slower on
-            // the book-1 scene (154.5 vs 134.4 ms; same 128 registers, no spills - a code-layout effect), so the full variant is the default.
-            const bool fulltex = tune.force_fulltex != 0 || (scene.flags & (8u | 16u)) != 0;
-            // resumable traversal: single wrapper-free instance, no media
-            // measured (tools/explore.py ab RTB200_MEGA_WAIT ...): +7 % on the 871k-triangle mesh at 20 lanes, -4 .. -40 % on the
-            // sphere scenes, whose shading share is too large to run it with half-empty warps
+            // Variant choice (every step A/B-measured on B200): compile-time primitive mask when the scene
+            // holds only spheres / spheres + moving spheres / rects + triangles; wrapper-free (XF = false) variants at 5 CTAs/SM
+            // (96 registers, no spills), everything else at 4 (128 registers); media: 4, or 3 with the general two-traversal path.
+            const uint32_t pm = !tune.prim_specialise ? RT_PM_ALL
+                                : (scene.prim_mask == 0x1u ? 0x1u : ((scene.prim_mask & ~0x3u) == 0 ? 0x3u : ((scene.prim_mask & ~0x28u) == 0 ? 0x28u : RT_PM_ALL)));
+            const bool wrapper_free = !(scene.flags & 32u) && tune.prim_specialise == 2;
+            // resumable traversal: +7 % on the 871k-triangle mesh at 20 lanes, -4 .. -40 % on the sphere scenes, whose shading share
+            // is too large to run it with half-empty warps (tools/explore.py ab RTB200_MEGA_WAIT ...)
             const int mega_wait = tune.mega_wait >= 0 ? tune.mega_wait : ((scene.flags & 4u) ? 20 : 0);
-            const bool resumable = mega_wait > 0 && specialised && fulltex && scene.n_main_instances == 1;
             J.wait_thresh = (uint32_t)std::max(1, std::min(32, mega_wait));
-            if (media && !(scene.flags & 2u)) {
-                k_mega<true, 3, true, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (media) {
-                if (occ >= 4) k_mega<true, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<true, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (resumable && scene.prim_mask == 0x1u) {
-                if (occ >= 5) k_mega_r<5, true, 0x1u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega_r<4, true, 0x1u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (resumable && (scene.prim_mask & ~0x3u) == 0) {
-                if (occ >= 5) k_mega_r<5, true, 0x3u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega_r<4, true, 0x3u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (resumable && (scene.prim_mask & ~0x28u) == 0) {
-                if (occ >= 5) k_mega_r<5, true, 0x28u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega_r<4, true, 0x28u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && scene.prim_mask == 0x1u && occ >= 5) {
-                k_mega<false, 5, false, true, 0x1u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x3u) == 0 && occ >= 5) {
-                k_mega<false, 5, false, true, 0x3u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x28u) == 0 && occ >= 5) {
-                k_mega<false, 5, false, true, 0x28u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && scene.prim_mask == 0x1u && occ >= 4) {
-                k_mega<false, 4, false, true, 0x1u, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres only, no wrappers
-            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x3u) == 0 && occ >= 4) {
-                k_mega<false, 4, false, true, 0x3u, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (fulltex && tune.prim_specialise == 2 && !(scene.flags & 32u) && (scene.prim_mask & ~0x28u) == 0 && occ >= 4) {
-                k_mega<false, 4, false, true, 0x28u, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (fulltex && tune.prim_specialise && scene.prim_mask == 0x1u && occ >= 4) {
-                k_mega<false, 4, false, true, 0x1u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres only (book-1 classic)
-            } else if (fulltex && tune.prim_specialise && (scene.prim_mask & ~0x3u) == 0 && occ >= 4) {
-                k_mega<false, 4, false, true, 0x3u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);   // spheres + moving spheres (book-1 as shipped)
-            } else if (fulltex && tune.prim_specialise && (scene.prim_mask & ~0x28u) == 0 && occ >= 4) {
-                k_mega<false, 4, false, true, 0x28u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);  // axis rects + triangles (mesh room)
-            } else if (fulltex) {
-                if (occ >= 4) k_mega<false, 4, false, true><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<false, 3, false, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+            if (media) {
+                if (!(scene.flags & 2u)) k_mega<true, 3, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<true, 4, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (wrapper_free && pm != RT_PM_ALL && mega_wait > 0 && scene.n_main_instances == 1) {
+                if (pm == 0x1u) k_mega_r<5, 0x1u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (pm == 0x3u) k_mega_r<5, 0x3u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega_r<5, 0x28u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (wrapper_free && pm != RT_PM_ALL) {
+                if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);       // book-1 final
+                else if (pm == 0x3u) k_mega<false, 5, false, 0x3u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);  // book-1 as shipped, animation
+                else k_mega<false, 5, false, 0x28u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);                 // mesh room
+            } else if (pm == 0x1u) {
+                k_mega<false, 4, false, 0x1u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (pm == 0x3u) {
+                k_mega<false, 4, false, 0x3u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (pm == 0x28u) {
+                k_mega<false, 4, false, 0x28u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else {
-                if (occ >= 6) k_mega<false, 6, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else if (occ == 5) k_mega<false, 5, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else if (occ == 4) k_mega<false, 4, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega<false, 3, false, false><<<mblocks, 128, 0, stream>>>(scene, J, Q, d_accum);
+                k_mega<false, 4, false><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);
             }
             CK(cudaGetLastError());
             launches += 2;
@@ -999,12 +976,13 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                     CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb));
                     CK(cudaEventRecord(ea, stream));
                 }
-                if (ext_kind == 1 && (!media || (scene.flags & 2u))) {
-                    const int pocc = tune.extend_occ > 0 ? tune.extend_occ : 4;
-                    if (media) { if (tune.count_events) launch_extend_p<true, true>(pocc, stream, scene, J, P, Q, parity); else launch_extend_p<true, false>(pocc, stream, scene, J, P, Q, parity); }
-                    else { if (tune.count_events) launch_extend_p<false, true>(pocc, stream, scene, J, P, Q, parity); else launch_extend_p<false, false>(pocc, stream, scene, J, P, Q, parity); }
-                } else if (media) { if (tune.count_events) launch_extend<true, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(ext_occ, eblocks, stream, scene, J, P, Q, parity); }
-                else { if (tune.count_events) launch_extend<false, true>(4, eblocks, stream, scene, J, P, Q, parity); else launch_extend<false, false>(ext_occ, eblocks, stream, scene, J, P, Q, parity); }
+                if (ext_kind == 1 && !media) {
+                    if (tune.count_events) launch_extend_p<true>(stream, scene, J, P, Q, parity); else launch_extend_p<false>(stream, scene, J, P, Q, parity);
+                } else if (media) {
+                    if (tune.count_events) launch_extend<true, true>(eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(eblocks, stream, scene, J, P, Q, parity);
+                } else {
+                    if (tune.count_events) launch_extend<false, true>(eblocks, stream, scene, J, P, Q, parity); else launch_extend<false, false>(eblocks, stream, scene, J, P, Q, parity);
+                }
                 if (tune.timed_extend) {
                     CK(cudaEventRecord(eb, stream));
                     ext_events.push_back(ea); ext_events.push_back(eb);

@@ -28,15 +28,12 @@ struct RenderTuning {
     int bvh_builder = 0;            // 0 = host binned SAH (best trees), 1 = device LBVH for instances of >= bvh_device_min primitives (fast commit)
     int bvh_device_min = 4096;
     int mega_wait = -1;             // k_mega_r (resumable traversal): finished lanes that end a traversal round; 0 = plain k_mega, -1 = auto (20 on large meshes)
-    int mega_occ = 0;               // k_mega variant: resident 128-thread blocks per SM; 0 = auto (5 for the scene-specialised variants, else 4)
     uint32_t wave_slots = 1u << 20; // resident paths (path-state slots)
     int timed_extend = 0;           // 1: bracket every extend launch with CUDA events (for the roofline)
     int count_events = 0;           // 1: count BVH node visits / primitive tests on the device
-    int extend_occ = 0;             // k_extend variant: resident 128-thread blocks per SM (4 / 5 / 6); 0 = auto (5, or 4 with media)
     int extend_kind = -1;           // 0: one ray per thread (while-while), 1: persistent warp-scheduled k_extend_p, -1: auto (1 for big meshes without media)
-    int force_fulltex = 1;          // 1: k_mega variant with the Noise/Image texture code (measured faster even for scenes without such textures); 0: slim variant
     int prim_specialise = 2;        // 1: kernel variants compiled for the primitive types the scene contains; 2: also without wrapper handling for wrapper-free scenes; 0: generic
-    int extend_waves = 4;           // k_extend grid = 148 * extend_occ * extend_waves blocks (grid-stride over the slots)
+    int extend_waves = 4;           // k_extend grid = 148 SMs * resident CTAs * extend_waves blocks (grid-stride over the slots)
 };
 
 // Wavefront render of one shard into a device-resident int64 fixed-point accumulator (W*H*3).

@@ -676,13 +676,10 @@ rt_scene* rt_scene_create(void) {
     rt_scene* s = new rt_scene();
     const char* e = std::getenv("RTB200_WAVE_SLOTS");
     if (e) s->tuning.wave_slots = (uint32_t)std::max(128L, std::atol(e));
-    if ((e = std::getenv("RTB200_EXTEND_OCC"))) s->tuning.extend_occ = std::atoi(e);
     if ((e = std::getenv("RTB200_EXTEND_WAVES"))) s->tuning.extend_waves = std::atoi(e);
     if ((e = std::getenv("RTB200_MODE"))) s->tuning.mode = std::atoi(e);
     if ((e = std::getenv("RTB200_EXTEND_KIND"))) s->tuning.extend_kind = std::atoi(e);
-    if ((e = std::getenv("RTB200_FULLTEX"))) s->tuning.force_fulltex = std::atoi(e);
     if ((e = std::getenv("RTB200_PRIM_SPECIALISE"))) s->tuning.prim_specialise = std::atoi(e);
-    if ((e = std::getenv("RTB200_MEGA_OCC"))) s->tuning.mega_occ = std::atoi(e);
     if ((e = std::getenv("RTB200_MEGA_WAIT"))) s->tuning.mega_wait = std::atoi(e);
     if ((e = std::getenv("RTB200_BVH_BUILDER"))) s->tuning.bvh_builder = (std::strcmp(e, "lbvh") == 0 || std::strcmp(e, "1") == 0) ? 1 : 0;
     if ((e = std::getenv("RTB200_BVH_DEVICE_MIN"))) s->tuning.bvh_device_min = std::atoi(e);

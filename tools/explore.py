@@ -38,33 +38,13 @@ if __name__ == "__main__":
             run(13, 800, 1.5, 100, slots=s, label="slots")
     elif what == "modes":
         run(13, 800, 1.5, 50, label="warm")
-        for mode, occ in ((0, 0), (1, 4)):
-            os.environ["RTB200_MODE"] = str(mode); os.environ["RTB200_MEGA_OCC"] = str(occ); os.environ["RTB200_EXTEND_OCC"] = "5"
-            tag = f"mode{mode} occ{occ}"
+        for mode in (0, 1):  # 0 = wavefront, 1 = fused
+            os.environ["RTB200_MODE"] = str(mode)
+            tag = f"mode{mode}"
             run(13, 800, 1.5, 500, label=f"book1 {tag}")
             run(99, 800, 1.5, 200, label=f"book1b {tag}")
             run(5, 600, 1.0, 200, label=f"smoke {tag}")
             run(6, 1000, 1.0, 40, label=f"book2 {tag}")
-            run(14, 1000, 1.0, 10, param=660, label=f"mesh871k {tag}")
-    elif what == "sah":
-        run(13, 800, 1.5, 50, label="warm")
-        os.environ["RTB200_EXTEND_OCC"] = "5"
-        for leaf, cp in ((4, 2), (1, 2), (2, 2), (2, 4), (4, 4), (4, 8), (8, 1), (8, 2), (3, 3)):
-            os.environ["RTB200_MAX_LEAF"] = str(leaf); os.environ["RTB200_COST_PRIM"] = str(cp)
-            tag = f"leaf{leaf} cp{cp}"
-            run(13, 800, 1.5, 100, flags=2, label=f"book1 {tag} COUNT")
-            run(13, 800, 1.5, 200, label=f"book1 {tag}")
-            run(6, 1000, 1.0, 20, label=f"book2 {tag}")
-            run(14, 1000, 1.0, 8, param=660, label=f"mesh871k {tag}")
-    elif what == "kinds":
-        run(13, 800, 1.5, 50, label="warm")
-        for kind, occ in ((0, 0), (1, 4), (1, 3), (1, 5)):
-            os.environ["RTB200_EXTEND_KIND"] = str(kind); os.environ["RTB200_EXTEND_OCC"] = str(occ)
-            tag = f"kind{kind} occ{occ}"
-            run(13, 800, 1.5, 300, label=f"book1 {tag}")
-            run(99, 800, 1.5, 100, label=f"book1b {tag}")
-            run(5, 600, 1.0, 200, label=f"smoke {tag}")
-            run(6, 1000, 1.0, 50, label=f"book2 {tag}")
             run(14, 1000, 1.0, 10, param=660, label=f"mesh871k {tag}")
     elif what == "ab":
         # A/B inside one process (same GPU, same clocks): env var name, values, scenes
@@ -108,17 +88,3 @@ if __name__ == "__main__":
         run(5, 600, 1.0, 30, flags=3, label="cornell smoke COUNT")
         run(6, 1000, 1.0, 10, flags=3, label="book2 COUNT")
         run(14, 1000, 1.0, 4, param=660, flags=3, label="mesh COUNT")
-    elif what == "sweep":
-        run(13, 800, 1.5, 50, label="warm")
-        for occ in (4, 5, 6):
-            for waves in (1, 4, 16):
-                os.environ["RTB200_EXTEND_OCC"] = str(occ); os.environ["RTB200_EXTEND_WAVES"] = str(waves)
-                run(13, 800, 1.5, 100, label=f"book1 occ{occ} w{waves}")
-        os.environ["RTB200_EXTEND_WAVES"] = "4"
-        for occ in (4, 5, 6):
-            os.environ["RTB200_EXTEND_OCC"] = str(occ)
-            for s in (1 << 18, 1 << 19, 1 << 20, 1 << 21):
-                run(13, 800, 1.5, 100, slots=s, label=f"book1 occ{occ} slots{s}")
-            run(5, 600, 1.0, 50, label=f"smoke occ{occ}")
-            run(6, 1000, 1.0, 10, label=f"book2 occ{occ}")
-            run(14, 1000, 1.0, 5, param=200, label=f"mesh80k occ{occ}")
