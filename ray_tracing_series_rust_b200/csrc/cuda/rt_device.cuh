@@ -52,18 +52,11 @@ struct Ray { // ray.rs:3-8
 };
 RT_DEV D3 ray_at(const Ray& r, double t) { return mk3(fma(r.d.x, t, r.o.x), fma(r.d.y, t, r.o.y), fma(r.d.z, t, r.o.z)); } // ray.rs:31-33
 
-// Build-time alternatives, A/B-measured on B200 with tools/ab_libs.sh (book-1 final, 500 spp; same box, same call):
-//   Philox inlined at its 19 call sites 100.4 ms | one out-of-line copy 94.4 ms  (-8 KB of code; the kernel stalls on
-//   instruction fetch for 19 % of its samples)  -> out of line.
-//   Sampler draws resolved at compile time (random_in_unit_sphere_aligned, camera_first_ray): 101.6 / 104.1 ms alone,
-//   105.8 ms together, 108.6 ms with the out-of-line Philox -> off.  Fewer instructions, slower kernel: at ~11 active
-//   lanes per instruction the kernel is bound by fetch / issue latency of divergent code, not by instruction count.
-#ifndef RT_STATIC_SPHERE
-#define RT_STATIC_SPHERE 0
-#endif
-#ifndef RT_STATIC_CAMERA
-#define RT_STATIC_CAMERA 0
-#endif
+// Measured on B200 (tools/ab_libs.sh, book-1 final, 500 spp, same box): Philox inlined at its 19 call sites 100.4 ms, one
+// out-of-line copy 94.4 ms (the kernel stalled on instruction fetch for 19 % of its samples).  Resolving the samplers'
+// draw positions at compile time removes next_u32's word selection but was 1-8 % slower in every combination (fewer
+// instructions, slower kernel: at ~11 active lanes per instruction the bound is fetch / issue latency of divergent
+// code), so the samplers below go through next_u32.
 // ------------------------------------------------------------------ Philox-4x32-10 / PathRng
 RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -87,15 +80,13 @@ struct PathRngT {
         return OOL ? philox4x32_10_ool(c, key) : philox4x32_10(c, key);
     }
     uint2 key, path;
-    uint32_t draw, cached; // cached = index of the block held in blk; blk2 holds block cached + 1 when have2
-    uint4 blk, blk2;
-    bool have2;
+    uint32_t draw, cached; // cached = index of the block held in blk
+    uint4 blk;
     RT_DEV void init(uint64_t seed, uint64_t path_id, uint32_t draw0) {
         key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
         path = make_uint2((uint32_t)path_id, (uint32_t)(path_id >> 32));
         draw = draw0;
         cached = 0xffffffffu;
-        have2 = false;
     }
     // RNG contract: every Material::scatter starts at the next multiple-of-4 draw index (as PathCtx::begin_event
     // in the oracle).  The first block of the event is generated right here, while all lanes of the material
@@ -105,22 +96,11 @@ struct PathRngT {
         const uint32_t b = draw >> 2;
         blk = block(b);
         cached = b;
-        have2 = false;
-    }
-    // Compute the next two blocks now, while the warp is converged: the rejection loops that consume
-    // them diverge, and a Philox block generated inside them runs with a handful of active lanes.
-    RT_DEV void prefetch2() {
-        const uint32_t b = draw >> 2;
-        blk = block(b);
-        blk2 = block(b + 1u);
-        cached = b;
-        have2 = true;
     }
     RT_DEV uint32_t next_u32() {
         const uint32_t b = draw >> 2;
         if (b != cached) {
-            if (have2 && b == cached + 1u) { blk = blk2; have2 = false; }
-            else blk = block(b);
+            blk = block(b);
             cached = b;
         }
         const uint32_t w = draw & 3u;
@@ -146,27 +126,6 @@ template <class G> RT_DEV D3 random_in_unit_sphere(G& g) { // vec3.rs:287-295
     }
 }
 template <class G> RT_DEV D3 random_unit_vector(G& g) { return unit(random_in_unit_sphere(g)); } // vec3.rs:297-299
-// xi -> 2 xi - 1, the arithmetic of gen_range(-1, 1)
-RT_DEV double sym_unit(uint32_t w) { return fma((double)w * (1.0 / 4294967296.0), 2.0, -1.0); }
-// random_in_unit_sphere right after begin_event(): the draw index is a multiple of 4 and g.blk holds that block, so
-// the first two tries read fixed words (x y z | w x' y') instead of going through next_u32's word selection; 77 % of
-// the calls end here.  Later tries continue in the general loop from draw + 6.  Same draws, same arithmetic.
-template <class G> RT_DEV D3 random_in_unit_sphere_aligned(G& g) {
-#if !RT_STATIC_SPHERE
-    return random_in_unit_sphere(g);
-#endif
-    const uint4 A = g.blk;
-    D3 p = mk3(sym_unit(A.x), sym_unit(A.y), sym_unit(A.z));
-    if (length_squared(p) < 1.0) { g.draw += 3u; return p; }
-    const uint32_t b = (g.draw >> 2) + 1u;
-    const uint4 B = g.block(b);
-    g.blk = B; g.cached = b; g.have2 = false;
-    g.draw += 6u;
-    p = mk3(sym_unit(A.w), sym_unit(B.x), sym_unit(B.y));
-    if (length_squared(p) < 1.0) return p;
-    return random_in_unit_sphere(g);
-}
-template <class G> RT_DEV D3 random_unit_vector_aligned(G& g) { return unit(random_in_unit_sphere_aligned(g)); }
 
 // ------------------------------------------------------------------ transforms (hit.rs:802-807, 893-904)
 RT_DEV void xform_ray(const XformOp* __restrict__ ops, uint32_t off, uint32_t len, Ray& r) {
@@ -760,7 +719,7 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
 template <bool FULLTEX = true, class G>
 RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, G& g, D3& dir, F3& att) {
     g.begin_event();
-    D3 sd = n + random_unit_vector_aligned(g);
+    D3 sd = n + random_unit_vector(g);
     if (near_zero(sd)) sd = n;
     dir = sd;
     att = tex_value<FULLTEX>(S, m.tex, u, v, p);
@@ -769,7 +728,7 @@ RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D
 template <class G> RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, G& g, D3& dir, F3& att) {
     g.begin_event();
     const D3 reflected = reflect(unit(d_in), n);
-    dir = reflected + m.fuzz_or_ir * random_in_unit_sphere_aligned(g); // the draw happens even when fuzz == 0
+    dir = reflected + m.fuzz_or_ir * random_in_unit_sphere(g); // the draw happens even when fuzz == 0
     att = mkf3(m.albedo[0], m.albedo[1], m.albedo[2]);
     return dot(dir, n) > 0.0;
 }
@@ -794,7 +753,7 @@ template <class G> RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D
 template <bool FULLTEX = true, class G>
 RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, G& g, D3& dir, F3& att) {
     g.begin_event();
-    dir = random_in_unit_sphere_aligned(g); // not normalised (hit.rs:1007)
+    dir = random_in_unit_sphere(g); // not normalised (hit.rs:1007)
     att = tex_value<FULLTEX>(S, m.tex, u, v, p);
     return true;
 }
@@ -820,56 +779,14 @@ template <class G> RT_DEV Ray camera_get_ray(const DCamera& c, double s, double 
     return r;
 }
 
-// The first draws of a path with their positions resolved at compile time: pixel jitter = words 0, 1 of block 0
-// (world.rs:1212-1213), lens disk tries = (2, 3), (4, 5), ... and the shutter time right after the accepted try.
-// Blocks 0 and 1 are generated back to back (two independent Philox chains); 95 % of the paths need nothing else.
+// The first ray of a path: pixel jitter (world.rs:1212-1213), then Camera::get_ray (lens disk, shutter time).
 template <class G> RT_DEV Ray camera_first_ray(const DCamera& c, int32_t ii, int32_t j, int32_t W, int32_t H, uint64_t seed, uint64_t path_id, uint32_t& draw_out) {
     G g;
     g.init(seed, path_id, 0);
-#if !RT_STATIC_CAMERA
-    {
-        const double s0 = ((double)ii + g.gen()) / (double)(W - 1);
-        const double t0 = ((double)j + g.gen()) / (double)(H - 1);
-        const Ray r0 = camera_get_ray(c, s0, t0, g);
-        draw_out = g.draw;
-        return r0;
-    }
-#endif
-    const uint4 A = g.block(0u);
-    const uint4 B = g.block(1u);
-    const double s = ((double)ii + (double)A.x * (1.0 / 4294967296.0)) / (double)(W - 1);
-    const double t = ((double)j + (double)A.y * (1.0 / 4294967296.0)) / (double)(H - 1);
-    double rx = sym_unit(A.z), ry = sym_unit(A.w), time;
-    uint32_t tw = B.x;
-    g.draw = 5u;
-    bool found = rx * rx + ry * ry + 0.0 < 1.0;
-    if (!found) {
-        rx = sym_unit(B.x); ry = sym_unit(B.y); tw = B.z;
-        g.draw = 7u;
-        found = rx * rx + ry * ry + 0.0 < 1.0;
-    }
-    if (found) {
-        time = fma((double)tw * (1.0 / 4294967296.0), c.time2 - c.time1, c.time1);
-    } else {
-        g.blk = B; g.cached = 1u; g.draw = 6u;
-        for (;;) {
-            rx = g.gen_range(-1.0, 1.0);
-            ry = g.gen_range(-1.0, 1.0);
-            if (rx * rx + ry * ry + 0.0 < 1.0) break;
-        }
-        time = g.gen_range(c.time1, c.time2);
-    }
+    const double s = ((double)ii + g.gen()) / (double)(W - 1);
+    const double t = ((double)j + g.gen()) / (double)(H - 1);
+    const Ray r = camera_get_ray(c, s, t, g);
     draw_out = g.draw;
-    rx *= c.lens_radius; ry *= c.lens_radius;
-    const D3 u = mk3(c.u[0], c.u[1], c.u[2]), v = mk3(c.v[0], c.v[1], c.v[2]);
-    const D3 offset = u * rx + v * ry;
-    const D3 origin = mk3(c.origin[0], c.origin[1], c.origin[2]);
-    const D3 llc = mk3(c.lower_left_corner[0], c.lower_left_corner[1], c.lower_left_corner[2]);
-    const D3 hor = mk3(c.horizontal[0], c.horizontal[1], c.horizontal[2]), ver = mk3(c.vertical[0], c.vertical[1], c.vertical[2]);
-    Ray r;
-    r.o = origin + offset;
-    r.d = llc + s * hor + t * ver - origin - offset;
-    r.time = time;
     return r;
 }
 
