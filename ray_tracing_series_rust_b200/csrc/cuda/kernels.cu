@@ -21,7 +21,7 @@
 #include <vector>
 
 #ifndef RT_SHADE_MIN_BLOCKS
-#define RT_SHADE_MIN_BLOCKS 4
+#define RT_SHADE_MIN_BLOCKS 3 // 80 registers, no spills: +1 % over 4 (64 registers, 204 B of spills) on Cornell smoke and book-2 final; 5 loses 2 %
 #endif
 
 #include "rt_device.cuh"
@@ -850,16 +850,17 @@ static void launch_extend_p(cudaStream_t st, const DeviceScene& scene, const Job
 
 template <bool MEDIA, bool COUNT>
 static void launch_extend(int blocks, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
-    // MINB = resident 128-thread blocks per SM the kernel is compiled for: 4 (128 registers) with media or event counters,
-    // 5 (96 registers) otherwise.  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
+    // MINB = resident 128-thread blocks per SM the kernel is compiled for: 4 (128 registers) with generic media code or event
+    // counters, 5 (96 registers) otherwise - also for the two primitive-mask-specialised media kernels, which then spill 56-80
+    // bytes but gain 5 % (tools/explore.py ab, Cornell smoke 634 -> 668, book-2 final 325 -> 340 Mpaths/s).  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
     // the general two-traversal path; the two media scenes of the reference also get their primitive mask compiled in.
     if constexpr (MEDIA) {
         if (!(scene.flags & 2u)) {
             k_extend<true, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
         } else if (!COUNT && g_prim_specialise && (scene.prim_mask & ~0x18u) == 0) {
-            k_extend<true, false, 4, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
+            k_extend<true, false, 5, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
         } else if (!COUNT && g_prim_specialise && (scene.prim_mask & ~0x1bu) == 0) {
-            k_extend<true, false, 4, false, 0x1bu><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // spheres, moving spheres, rects, boxes (book-2 final)
+            k_extend<true, false, 5, false, 0x1bu><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // spheres, moving spheres, rects, boxes (book-2 final)
         } else {
             k_extend<true, COUNT, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
         }
@@ -908,7 +909,9 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         const int qblocks = (int)std::min<uint32_t>((N + 255) / 256, 148 * 8);
         const bool media = scene.n_media != 0;
         g_prim_specialise = tune.prim_specialise;
-        const int ext_occ = (media || tune.count_events) ? 4 : 5; // resident CTAs per SM of the k_extend variant launch_extend picks
+        // resident CTAs per SM of the k_extend variant launch_extend picks (only sizes the grid)
+        const bool media_specialised = media && (scene.flags & 2u) && tune.prim_specialise && ((scene.prim_mask & ~0x18u) == 0 || (scene.prim_mask & ~0x1bu) == 0);
+        const int ext_occ = ((media && !media_specialised) || tune.count_events) ? 4 : 5;
         // measured (profiles/): the warp-scheduled persistent kernel wins on deep triangle BVHs (+22 % on the 871k mesh),
         // the one-ray-per-thread kernel on small scenes and on scenes with media
         const int ext_kind = tune.extend_kind >= 0 ? tune.extend_kind : ((!media && (scene.flags & 4u)) ? 1 : 0);

@@ -78,6 +78,10 @@ if __name__ == "__main__":
             run(13, 800, 1.5, 200, label=f"book1 {b}")
             run(13, 800, 1.5, 50, flags=3, label=f"book1 {b} COUNTED")
             run(6, 1000, 1.0, 40, label=f"book2 {b}")
+    elif what == "wave":
+        run(13, 800, 1.5, 50, label="warm")
+        run(5, 600, 1.0, 300, label="cornell smoke")
+        run(6, 1000, 1.0, 100, label="book2 final")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
