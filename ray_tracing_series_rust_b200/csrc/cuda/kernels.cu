@@ -926,7 +926,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             // holds only spheres / spheres + moving spheres / rects + triangles; wrapper-free (XF = false) variants at 5 CTAs/SM
             // (96 registers, no spills), everything else at 4 (128 registers); media: 4, or 3 with the general two-traversal path.
             const uint32_t pm = !tune.prim_specialise ? RT_PM_ALL
-                                : (scene.prim_mask == 0x1u ? 0x1u : ((scene.prim_mask & ~0x3u) == 0 ? 0x3u : ((scene.prim_mask & ~0x28u) == 0 ? 0x28u : RT_PM_ALL)));
+                                : (scene.prim_mask == 0x1u ? 0x1u : ((scene.prim_mask & ~0x3u) == 0 ? 0x3u : ((scene.prim_mask & ~0x5u) == 0 ? 0x5u : ((scene.prim_mask & ~0x28u) == 0 ? 0x28u : RT_PM_ALL))));
             const bool wrapper_free = !(scene.flags & 32u) && tune.prim_specialise == 2;
             // resumable traversal: +7 % on the 871k-triangle mesh at 20 lanes, -4 .. -40 % on the sphere scenes, whose shading share
             // is too large to run it with half-empty warps (tools/explore.py ab RTB200_MEGA_WAIT ...)
@@ -938,10 +938,12 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             } else if (wrapper_free && pm != RT_PM_ALL && mega_wait > 0 && scene.n_main_instances == 1) {
                 if (pm == 0x1u) k_mega_r<5, 0x1u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else if (pm == 0x3u) k_mega_r<5, 0x3u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega_r<5, 0x28u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (wrapper_free && pm != RT_PM_ALL) {
                 if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);       // book-1 final
-                else if (pm == 0x3u) k_mega<false, 5, false, 0x3u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);  // book-1 as shipped, animation
+                else if (pm == 0x3u) k_mega<false, 5, false, 0x3u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);  // book-1 as shipped
+                else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);  // bouncing-spheres animation (GravitySphere)
                 else k_mega<false, 5, false, 0x28u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);                 // mesh room
             } else if (pm == 0x1u) {
                 k_mega<false, 4, false, 0x1u><<<148 * 4, 128, 0, stream>>>(scene, J, Q, d_accum);

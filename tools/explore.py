@@ -82,6 +82,10 @@ if __name__ == "__main__":
         run(13, 800, 1.5, 50, label="warm")
         run(5, 600, 1.0, 300, label="cornell smoke")
         run(6, 1000, 1.0, 100, label="book2 final")
+    elif what == "anim":
+        run(13, 800, 1.5, 50, label="warm")
+        run(8, 800, 1.5, 200, label="bouncing frame (scene 8)")
+        run(8, 800, 1.5, 200, label="bouncing frame (scene 8)")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
