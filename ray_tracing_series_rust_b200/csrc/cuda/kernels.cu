@@ -852,7 +852,8 @@ template <bool MEDIA, bool COUNT>
 static void launch_extend(int blocks, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
     // MINB = resident 128-thread blocks per SM the kernel is compiled for: 4 (128 registers) with generic media code or event
     // counters, 5 (96 registers) otherwise - also for the two primitive-mask-specialised media kernels, which then spill 56-80
-    // bytes but gain 5 % (tools/explore.py ab, Cornell smoke 634 -> 668, book-2 final 325 -> 340 Mpaths/s).  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
+    // bytes but gain 5 % (tools/explore.py ab, Cornell smoke 634 -> 668, book-2 final 325 -> 340 Mpaths/s); 6 CTAs/SM (80
+    // registers, 130-340 B spilled) is +1 % on Cornell smoke and -1.4 % on book-2 final.  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
     // the general two-traversal path; the two media scenes of the reference also get their primitive mask compiled in.
     if constexpr (MEDIA) {
         if (!(scene.flags & 2u)) {
@@ -939,7 +940,9 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 if (pm == 0x1u) k_mega_r<5, 0x1u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else if (pm == 0x3u) k_mega_r<5, 0x3u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-                else k_mega_r<5, 0x28u><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                // the mesh walk is L2-latency bound (long-scoreboard 3.6 per issue): more resident warps beat fewer spills:
+                // 5 CTAs/SM (96 regs, 132 B spilled) 126, 6 (80 regs) 134.5, 7 (72 regs, 652 B spilled) 139.7, 8 (64 regs) 135 Mpaths/s
+                else k_mega_r<7, 0x28u><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (wrapper_free && pm != RT_PM_ALL) {
                 if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);       // book-1 final
                 else if (pm == 0x3u) k_mega<false, 5, false, 0x3u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);  // book-1 as shipped

@@ -86,6 +86,11 @@ if __name__ == "__main__":
         run(13, 800, 1.5, 50, label="warm")
         run(8, 800, 1.5, 200, label="bouncing frame (scene 8)")
         run(8, 800, 1.5, 200, label="bouncing frame (scene 8)")
+    elif what == "mesh":
+        run(14, 1000, 1.0, 4, param=660, label="warm mesh")
+        for wait in (16, 20, 24, 0):
+            os.environ["RTB200_MEGA_WAIT"] = str(wait)
+            run(14, 1000, 1.0, 20, param=660, label=f"mesh wait{wait}")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
