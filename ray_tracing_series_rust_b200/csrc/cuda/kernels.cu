@@ -840,8 +840,6 @@ static cudaError_t ensure_workspace(Workspace*& w, uint32_t N) {
     return cudaSuccess;
 }
 
-static int g_prim_specialise = 1;
-
 template <bool COUNT>
 static void launch_extend_p(cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
     // persistent: exactly the resident number of CTAs (148 SMs x 4); chosen only for media-free scenes with large meshes
@@ -849,7 +847,7 @@ static void launch_extend_p(cudaStream_t st, const DeviceScene& scene, const Job
 }
 
 template <bool MEDIA, bool COUNT>
-static void launch_extend(int blocks, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
+static void launch_extend(int blocks, bool specialise, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
     // MINB = resident 128-thread blocks per SM the kernel is compiled for: 4 (128 registers) with generic media code or event
     // counters, 5 (96 registers) otherwise - also for the two primitive-mask-specialised media kernels, which then spill 56-80
     // bytes but gain 5 % (tools/explore.py ab, Cornell smoke 634 -> 668, book-2 final 325 -> 340 Mpaths/s); 6 CTAs/SM (80
@@ -858,9 +856,9 @@ static void launch_extend(int blocks, cudaStream_t st, const DeviceScene& scene,
     if constexpr (MEDIA) {
         if (!(scene.flags & 2u)) {
             k_extend<true, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-        } else if (!COUNT && g_prim_specialise && (scene.prim_mask & ~0x18u) == 0) {
+        } else if (!COUNT && specialise && (scene.prim_mask & ~0x18u) == 0) {
             k_extend<true, false, 5, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
-        } else if (!COUNT && g_prim_specialise && (scene.prim_mask & ~0x1bu) == 0) {
+        } else if (!COUNT && specialise && (scene.prim_mask & ~0x1bu) == 0) {
             k_extend<true, false, 5, false, 0x1bu><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // spheres, moving spheres, rects, boxes (book-2 final)
         } else {
             k_extend<true, COUNT, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
@@ -909,7 +907,6 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         Queues& Q = w->Q;
         const int qblocks = (int)std::min<uint32_t>((N + 255) / 256, 148 * 8);
         const bool media = scene.n_media != 0;
-        g_prim_specialise = tune.prim_specialise;
         // resident CTAs per SM of the k_extend variant launch_extend picks (only sizes the grid)
         const bool media_specialised = media && (scene.flags & 2u) && tune.prim_specialise && ((scene.prim_mask & ~0x18u) == 0 || (scene.prim_mask & ~0x1bu) == 0);
         const int ext_occ = ((media && !media_specialised) || tune.count_events) ? 4 : 5;
@@ -987,9 +984,9 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 if (ext_kind == 1 && !media) {
                     if (tune.count_events) launch_extend_p<true>(stream, scene, J, P, Q, parity); else launch_extend_p<false>(stream, scene, J, P, Q, parity);
                 } else if (media) {
-                    if (tune.count_events) launch_extend<true, true>(eblocks, stream, scene, J, P, Q, parity); else launch_extend<true, false>(eblocks, stream, scene, J, P, Q, parity);
+                    if (tune.count_events) launch_extend<true, true>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity); else launch_extend<true, false>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity);
                 } else {
-                    if (tune.count_events) launch_extend<false, true>(eblocks, stream, scene, J, P, Q, parity); else launch_extend<false, false>(eblocks, stream, scene, J, P, Q, parity);
+                    if (tune.count_events) launch_extend<false, true>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity); else launch_extend<false, false>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity);
                 }
                 if (tune.timed_extend) {
                     CK(cudaEventRecord(eb, stream));
