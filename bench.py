@@ -568,12 +568,15 @@ def extra_workloads(api, rtb, capi, stream):
         sid, sseed, param, W, aspect, spp, depth, cam, desc = WORKLOADS["mesh_room"]
         rec = {}
         for label, builder in (("host_sah", 0), ("device_lbvh", 1)):
-            s = rtb.new_scene()
-            s.world_build(sid, sseed, param)
-            s.set_bvh_builder(builder)
-            t0 = time.time()
-            s.commit()
-            rec[label + "_commit_s"] = time.time() - t0
+            for attempt in ("first", "warm"):  # the first device build also pays CUDA's lazy loading of the sort / scan kernels
+                s = rtb.new_scene()
+                s.world_build(sid, sseed, param)
+                s.set_bvh_builder(builder)
+                t0 = time.time()
+                s.commit()
+                rec[label + ("_commit_first_s" if attempt == "first" else "_commit_s")] = time.time() - t0
+                if attempt == "first":
+                    s.close()
             rec[label + "_device_built_prims"] = s.host_check()["device_built_prims"] if builder else 0
             cfg = capi.make_config(W, aspect, 20, depth, seed=7)
             s.render(cfg)

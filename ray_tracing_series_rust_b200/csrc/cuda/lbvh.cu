@@ -187,6 +187,15 @@ struct DevBuf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+struct Carve { // offsets into one device allocation, 256-byte aligned
+    size_t used = 0;
+    size_t take(size_t bytes) { const size_t o = used; used = (used + bytes + 255) & ~(size_t)255; return o; }
+};
+struct View {
+    char* p;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 #define LB_CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
 } // namespace
@@ -222,21 +231,30 @@ cudaError_t lbvh_build_device(const float* h_boxes, const uint8_t* h_types, uint
     const float3 ci = make_float3(cmax[0] > cmin[0] ? 1.f / (cmax[0] - cmin[0]) : 0.f, cmax[1] > cmin[1] ? 1.f / (cmax[1] - cmin[1]) : 0.f,
                                   cmax[2] > cmin[2] ? 1.f / (cmax[2] - cmin[2]) : 0.f);
 
-    DevBuf d_boxes, d_types, d_keys, d_keys2, d_vals, d_vals2, d_left, d_right, d_first, d_last, d_pint, d_pleaf, d_lbox, d_nbox, d_ticket, d_keep, d_rank, d_depth, d_tmp,
-        d_out;
+    // one device allocation for every intermediate and the worst-case output (2 * n nodes): cudaMalloc dominates small builds
     const size_t ni = n - 1;
-    LB_CK(d_boxes.alloc(sizeof(Box6) * n)); LB_CK(d_types.alloc(n));
-    LB_CK(d_keys.alloc(8 * (size_t)n)); LB_CK(d_keys2.alloc(8 * (size_t)n)); LB_CK(d_vals.alloc(4 * (size_t)n)); LB_CK(d_vals2.alloc(4 * (size_t)n));
-    LB_CK(d_left.alloc(4 * ni)); LB_CK(d_right.alloc(4 * ni)); LB_CK(d_first.alloc(4 * ni)); LB_CK(d_last.alloc(4 * ni));
-    LB_CK(d_pint.alloc(4 * ni)); LB_CK(d_pleaf.alloc(4 * (size_t)n));
-    LB_CK(d_lbox.alloc(sizeof(Box6) * n)); LB_CK(d_nbox.alloc(sizeof(Box6) * ni));
-    LB_CK(d_ticket.alloc(4 * ni)); LB_CK(d_keep.alloc(4 * ni)); LB_CK(d_rank.alloc(4 * ni)); LB_CK(d_depth.alloc(4));
     size_t tmp_sort = 0, tmp_scan = 0;
+    {
+        cub::DoubleBuffer<uint64_t> kb0(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t> vb0(nullptr, nullptr);
+        LB_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, kb0, vb0, (int)n, 0, 63));
+        LB_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)ni));
+    }
+    Carve cv;
+    const size_t o_boxes = cv.take(sizeof(Box6) * n), o_types = cv.take(n), o_keys = cv.take(8 * (size_t)n), o_keys2 = cv.take(8 * (size_t)n),
+                 o_vals = cv.take(4 * (size_t)n), o_vals2 = cv.take(4 * (size_t)n), o_left = cv.take(4 * ni), o_right = cv.take(4 * ni),
+                 o_first = cv.take(4 * ni), o_last = cv.take(4 * ni), o_pint = cv.take(4 * ni), o_pleaf = cv.take(4 * (size_t)n),
+                 o_lbox = cv.take(sizeof(Box6) * n), o_nbox = cv.take(sizeof(Box6) * ni), o_ticket = cv.take(4 * ni), o_keep = cv.take(4 * ni),
+                 o_rank = cv.take(4 * ni), o_depth = cv.take(4), o_tmp = cv.take(tmp_sort > tmp_scan ? tmp_sort : tmp_scan),
+                 o_out = cv.take(sizeof(BvhNode32) * 2 * (size_t)n);
+    DevBuf arena;
+    LB_CK(arena.alloc(cv.used));
+    char* const A = arena.as<char>();
+    const View d_boxes{A + o_boxes}, d_types{A + o_types}, d_keys{A + o_keys}, d_keys2{A + o_keys2}, d_vals{A + o_vals}, d_vals2{A + o_vals2},
+        d_left{A + o_left}, d_right{A + o_right}, d_first{A + o_first}, d_last{A + o_last}, d_pint{A + o_pint}, d_pleaf{A + o_pleaf}, d_lbox{A + o_lbox},
+        d_nbox{A + o_nbox}, d_ticket{A + o_ticket}, d_keep{A + o_keep}, d_rank{A + o_rank}, d_depth{A + o_depth}, d_tmp{A + o_tmp}, d_out{A + o_out};
     cub::DoubleBuffer<uint64_t> kb(d_keys.as<uint64_t>(), d_keys2.as<uint64_t>());
     cub::DoubleBuffer<uint32_t> vb(d_vals.as<uint32_t>(), d_vals2.as<uint32_t>());
-    LB_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, kb, vb, (int)n, 0, 63));
-    LB_CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, d_keep.as<uint32_t>(), d_rank.as<uint32_t>(), (int)ni));
-    LB_CK(d_tmp.alloc(tmp_sort > tmp_scan ? tmp_sort : tmp_scan));
 
     cudaEvent_t e0, e1;
     LB_CK(cudaEventCreate(&e0)); LB_CK(cudaEventCreate(&e1));
@@ -266,7 +284,6 @@ cudaError_t lbvh_build_device(const float* h_boxes, const uint8_t* h_types, uint
         return cudaSuccess;
     }
     const size_t n_out = 2 * (size_t)(1 + kept);
-    LB_CK(d_out.alloc(sizeof(BvhNode32) * n_out));
     k_lbvh_emit<<<gi, T>>>(keys, (int)n, d_left.as<uint32_t>(), d_right.as<uint32_t>(), d_first.as<uint32_t>(), d_last.as<uint32_t>(), d_keep.as<uint32_t>(),
                            d_rank.as<uint32_t>(), d_lbox.as<Box6>(), d_nbox.as<Box6>(), max_leaf, base, td, d_out.as<BvhNode32>());
     LB_CK(cudaGetLastError());
