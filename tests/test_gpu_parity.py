@@ -260,6 +260,34 @@ def test_E2_render_matches_oracle_sample_by_sample(orc, scene_id, W, aspect, spp
     assert q_bad < 0.02
 
 
+def _psnr(a, b):
+    mse = float(np.mean((a - b) ** 2))
+    return 99.0 if mse == 0.0 else 10.0 * math.log10(255.0 ** 2 / mse)
+
+
+@pytest.mark.parametrize("scene_id,W,aspect,spp", [(13, 120, 1.5, 32), (5, 96, 1.0, 48), (6, 96, 1.0, 32)])
+def test_E2_statistical_image_parity(orc, scene_id, W, aspect, spp):
+    # SURVEY.md Appendix E2 / BASELINE north_star "images at equal spp within a stated RMSE/PSNR bound": with DIFFERENT seeds on
+    # the two sides the quantised 8-bit images (the reference's output space, vec3.rs:89-107) must be as close as two
+    # independent renders of the oracle are to each other: PSNR(GPU, oracle A) >= PSNR(oracle B, oracle A) - 0.5 dB,
+    # RMSE within 6 % of the noise floor, mean colour within 0.5/255 + 4 sigma and mean linear radiance within 4 sigma.
+    g, o = pu.build_pair(orc, scene_id)
+    so_a, ao_a, _ = o.render(capi.make_config(W, aspect, spp, 50, seed=101), want_accum=True)
+    so_b, ao_b, _ = o.render(capi.make_config(W, aspect, spp, 50, seed=202), want_accum=True)
+    sg_c, ag_c, _ = g.render(capi.make_config(W, aspect, spp, 50, seed=303), want_accum=True)
+    floor, got = _psnr(so_b, so_a), _psnr(sg_c, so_a)
+    assert got >= floor - 0.5, (scene_id, got, floor)
+    rmse_floor, rmse_got = math.sqrt(np.mean((so_b - so_a) ** 2)), math.sqrt(np.mean((sg_c - so_a) ** 2))
+    assert rmse_got <= 1.06 * rmse_floor, (rmse_got, rmse_floor)
+    npix = so_a.shape[0] * so_a.shape[1]
+    sig8 = (so_b - so_a).std(axis=(0, 1)) / math.sqrt(2.0 * npix)  # standard error of a channel mean, from the two oracle renders
+    assert (np.abs(sg_c.mean(axis=(0, 1)) - so_a.mean(axis=(0, 1))) <= 0.5 + 4.0 * math.sqrt(2.0) * sig8).all()
+    # bias check on linear radiance: the GPU mean must sit within 4 sigma of the oracle mean, sigma estimated from the two oracle runs
+    la, lb, lc = (x / capi.ACCUM_SCALE / spp for x in (ao_a, ao_b, ag_c))
+    sigma = np.abs(la.mean(axis=(0, 1)) - lb.mean(axis=(0, 1))) / math.sqrt(2.0) + la.std(axis=(0, 1)) / math.sqrt(la.shape[0] * la.shape[1])
+    assert (np.abs(lc.mean(axis=(0, 1)) - 0.5 * (la + lb).mean(axis=(0, 1))) <= 4.0 * sigma + 1e-4).all()
+
+
 def test_depth_limit_and_background(orc):
     g, o = pu.build_pair(orc, 13)
     for depth in (1, 2, 5):

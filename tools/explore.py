@@ -1,7 +1,7 @@
 """Ad-hoc GPU exploration (not part of the product): times full-size renders of the BASELINE configs."""
 import sys, time, os, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np
 import ray_tracing_series_rust_b200 as rtb
 from ray_tracing_series_rust_b200 import capi
