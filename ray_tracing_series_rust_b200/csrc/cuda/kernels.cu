@@ -404,6 +404,17 @@ __global__ void __launch_bounds__(128, MINB) k_extend_p(const __grid_constant__ 
 // slot is refilled in place with the next camera path.
 __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q,
                                                    int64_t* __restrict__ accum, int parity) {
+    // perlin.rs tables of the scene's first Noise texture staged in shared memory (6.9 KB: 256 f64 gradients + 3 x 256 byte
+    // permutations): the 7-octave turbulence gathers 8 x 7 = 56 gradients per shaded point from here instead of L1 / L2
+    __shared__ PerlinTable s_perlin;
+    const bool stage_perlin = (S.flags & 8u) != 0;
+    if (stage_perlin) {
+        const uint4* src = reinterpret_cast<const uint4*>(S.perlin);
+        uint4* dst = reinterpret_cast<uint4*>(&s_perlin);
+        for (uint32_t i = threadIdx.x; i < sizeof(PerlinTable) / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    const PerlinTable* perlin0 = stage_perlin ? &s_perlin : nullptr;
     const uint32_t* counts = Q.counts + 8 * parity;
     uint32_t start[Q_COUNT + 1];
     start[0] = 0;
@@ -444,7 +455,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
                 hu = uv.x; hv = uv.y;
             }
             if (q == MAT_LIGHT) {
-                const F3 e = tex_value(S, m.tex, hu, hv, p); // hit.rs:1146-1151, world.rs:78-84
+                const F3 e = tex_value(S, m.tex, hu, hv, p, perlin0); // hit.rs:1146-1151, world.rs:78-84
                 contrib = mkf3(sd.tr * e.x, sd.tg * e.y, sd.tb * e.z);
             } else {
                 PathRng g;
@@ -453,10 +464,10 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
                 D3 dir = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
                 bool scattered;
-                if (q == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, p, n3, hu, hv, g, dir, att);
+                if (q == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, p, n3, hu, hv, g, dir, att, perlin0);
                 else if (q == MAT_METAL) scattered = scatter_metal(m, d_in, n3, g, dir, att);
                 else if (q == MAT_DIELECTRIC) scattered = scatter_dielectric(m, d_in, n3, (hm >> 31) != 0, g, dir, att);
-                else scattered = scatter_isotropic(S, m, p, hu, hv, g, dir, att);
+                else scattered = scatter_isotropic(S, m, p, hu, hv, g, dir, att, perlin0);
                 const uint32_t seg = sd.segment + 1;
                 if (scattered && (int32_t)seg < J.max_depth) { // world.rs:64-67: at most max_depth hit queries per path
                     sd.tr *= att.x; sd.tg *= att.y; sd.tb *= att.z; // world.rs:75

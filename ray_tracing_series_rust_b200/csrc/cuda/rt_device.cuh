@@ -744,8 +744,9 @@ RT_DEV double perlin_turbulence(const PerlinTable* __restrict__ pt, D3 p, int de
 
 // FULL = false compiles only SolidColor and Checker (kernels picked for scenes without Noise / Image
 // textures: the Perlin and image code would only cost instruction-cache space)
+// perlin0 = the scene's first Perlin table staged in shared memory by the caller (k_shade_all), or nullptr
 template <bool FULL = true>
-RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p) { // texture.rs:7-9
+RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p, const PerlinTable* perlin0 = nullptr) { // texture.rs:7-9
     for (int guard = 0; guard < 64; ++guard) {
         const DTexture* t = &S.textures[tex];
         const uint32_t type = __ldg(&t->type);
@@ -757,7 +758,9 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
         }
         if (!FULL) break;
         if (type == TEX_NOISE) { // texture.rs:80-88
-            const double s = 0.5 * (1.0 + sin(t->scale * p.z + 10.0 * perlin_turbulence(&S.perlin[t->a], p, 7)));
+            const uint32_t pi = __ldg(&t->a);
+            const PerlinTable* pt = (perlin0 && pi == 0u) ? perlin0 : &S.perlin[pi];
+            const double s = 0.5 * (1.0 + sin(t->scale * p.z + 10.0 * perlin_turbulence(pt, p, 7)));
             return mkf3((float)s, (float)s, (float)s);
         }
         // TEX_IMAGE, texture.rs:102-121: nearest texel, row 0 = top of file, v flipped
@@ -777,12 +780,13 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
 // ------------------------------------------------------------------ Material::scatter (hit.rs:1004-1152)
 // Returns true when the path continues; `dir` = scattered direction, `att` = attenuation.
 template <bool FULLTEX = true, class G>
-RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, G& g, D3& dir, F3& att) {
+RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, G& g, D3& dir, F3& att,
+                               const PerlinTable* perlin0 = nullptr) {
     g.begin_event();
     D3 sd = n + random_unit_vector(g);
     if (near_zero(sd)) sd = n;
     dir = sd;
-    att = tex_value<FULLTEX>(S, m.tex, u, v, p);
+    att = tex_value<FULLTEX>(S, m.tex, u, v, p, perlin0);
     return true;
 }
 template <class G> RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, G& g, D3& dir, F3& att) {
@@ -811,10 +815,11 @@ template <class G> RT_DEV bool scatter_dielectric(const DMaterial& m, D3 d_in, D
     return true;
 }
 template <bool FULLTEX = true, class G>
-RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, G& g, D3& dir, F3& att) {
+RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, G& g, D3& dir, F3& att,
+                              const PerlinTable* perlin0 = nullptr) {
     g.begin_event();
     dir = random_in_unit_sphere(g); // not normalised (hit.rs:1007)
-    att = tex_value<FULLTEX>(S, m.tex, u, v, p);
+    att = tex_value<FULLTEX>(S, m.tex, u, v, p, perlin0);
     return true;
 }
 
