@@ -91,6 +91,13 @@ if __name__ == "__main__":
         for wait in (16, 20, 24, 0):
             os.environ["RTB200_MEGA_WAIT"] = str(wait)
             run(14, 1000, 1.0, 20, param=660, label=f"mesh wait{wait}")
+    elif what == "lbvh_leaf":
+        run(14, 1000, 1.0, 4, param=660, label="warm")
+        os.environ["RTB200_BVH_BUILDER"] = "lbvh"
+        for leaf in (1, 2, 3, 4, 6, 8):
+            os.environ["RTB200_MAX_LEAF"] = str(leaf)
+            run(14, 1000, 1.0, 20, param=660, label=f"mesh lbvh max_leaf {leaf}")
+            run(14, 1000, 1.0, 4, param=660, flags=3, label=f"mesh lbvh max_leaf {leaf} COUNTED")
     elif what == "all":
         run(13, 800, 1.5, 50, label="warm")
         run(13, 800, 1.5, 500, label="book1 final")
