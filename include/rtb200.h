@@ -155,6 +155,11 @@ RTB_EXPORT int32_t RTB_FN(scene_set_camera)(rt_scene* s, const double lookfrom[3
                                             double vfov_deg, double aspect_ratio, double aperture,
                                             double focus_dist, double time1, double time2);
 /* the `background` argument of render_scene        [ref: src/world.rs:1184, 86-89] */
+/* The same camera from the 24 f64 fields the reference's Camera stores, in declaration order: origin[3],
+ * lower_left_corner[3], horizontal[3], vertical[3], u[3], v[3], w[3], lens_radius, time1, time2
+ * [ref: src/camera.rs:6-17].  A Rust `Camera` keeps only these (not its constructor arguments), so this is the call
+ * its flatten() makes; rt_scene_set_camera derives the same block from Camera::new's arguments. */
+RTB_EXPORT int32_t RTB_FN(scene_set_camera_fields)(rt_scene* s, const double fields[24]);
 RTB_EXPORT int32_t RTB_FN(scene_set_background)(rt_scene* s, const double rgb[3]);
 /* Freeze the scene: number the leaves depth-first, flatten, build the device BVH, upload to the
  * current CUDA device.  Replaces "Arc::new(world)" hand-off at src/world.rs:1181-1186. */

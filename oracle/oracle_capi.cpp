@@ -331,6 +331,17 @@ int32_t orc_scene_set_camera(rt_scene* s, const double lf[3], const double la[3]
     s->has_cam = true;
     return RT_OK;
 }
+int32_t orc_scene_set_camera_fields(rt_scene* s, const double f[24]) {
+    CHECK_SCENE(s);
+    if (!f) return fail(RT_ERR_INVALID, "null camera fields");
+    Camera c;
+    Vec3* v[7] = {&c.origin, &c.lower_left_corner, &c.horizontal, &c.vertical, &c.u, &c.v, &c.w};
+    for (int i = 0; i < 7; ++i) *v[i] = Vec3(f[3 * i], f[3 * i + 1], f[3 * i + 2]);
+    c.lens_radius = f[21]; c.time1 = f[22]; c.time2 = f[23];
+    s->cam = c;
+    s->has_cam = true;
+    return RT_OK;
+}
 int32_t orc_scene_set_background(rt_scene* s, const double rgb[3]) {
     CHECK_SCENE(s);
     s->background = Color(rgb[0], rgb[1], rgb[2]);

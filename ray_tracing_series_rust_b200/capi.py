@@ -99,6 +99,7 @@ SIGNATURES = {
     "constant_medium": (C.c_int32, [_P, c_d3, C.c_double, C.c_int32]),
     "scene_set_root": (C.c_int32, [_P, C.c_int32]),
     "scene_set_camera": (C.c_int32, [_P, c_d3, c_d3, c_d3] + [C.c_double] * 6),
+    "scene_set_camera_fields": (C.c_int32, [_P, c_d3]),
     "scene_set_background": (C.c_int32, [_P, c_d3]),
     "scene_commit": (C.c_int32, [_P]),
     "world_build": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_int32]),
@@ -283,6 +284,11 @@ class Scene:
     def set_camera(self, lookfrom, lookat, vup, vfov, aspect, aperture, focus, t1, t2):
         return self._c(self.api.scene_set_camera(self.h, _d3(lookfrom), _d3(lookat), _d3(vup), float(vfov),
                                                  float(aspect), float(aperture), float(focus), float(t1), float(t2)))
+
+    def set_camera_fields(self, fields):
+        """The 24 f64 fields of the reference's Camera struct (camera.rs:6-17), as its flatten() would pass them."""
+        a = (C.c_double * 24)(*[float(x) for x in fields])
+        return self._c(self.api.scene_set_camera_fields(self.h, a))
 
     def set_background(self, rgb):
         return self._c(self.api.scene_set_background(self.h, _d3(rgb)))

@@ -888,6 +888,19 @@ int32_t rt_scene_set_root(rt_scene* s, int32_t id) {
     s->committed = false;
     return RT_OK;
 }
+int32_t rt_scene_set_camera_fields(rt_scene* s, const double f[24]) {
+    CHECK_SCENE(s);
+    if (!f) return fail(RT_ERR_INVALID, "null camera fields");
+    DCamera& c = s->camera.cam;
+    for (int a = 0; a < 3; ++a) {
+        c.origin[a] = f[a]; c.lower_left_corner[a] = f[3 + a]; c.horizontal[a] = f[6 + a]; c.vertical[a] = f[9 + a];
+        c.u[a] = f[12 + a]; c.v[a] = f[15 + a]; c.w[a] = f[18 + a];
+    }
+    c.lens_radius = f[21]; c.time1 = f[22]; c.time2 = f[23];
+    s->camera.set = true;
+    s->committed = false; // moving-primitive bounds depend on the shutter
+    return RT_OK;
+}
 int32_t rt_scene_set_camera(rt_scene* s, const double lf[3], const double la[3], const double vup[3], double vfov, double aspect, double aperture,
                             double focus_dist, double t1, double t2) {
     CHECK_SCENE(s);

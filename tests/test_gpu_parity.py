@@ -403,6 +403,21 @@ def test_tile_sharding_is_bit_identical_and_matches_oracle(orc):
     assert not ag[50:].any()  # rows >= 10 * (53 / 10) stay unrendered (world.rs:1198-1202)
 
 
+def test_camera_fields_entry_point(orc):
+    # rt_scene_set_camera_fields (the call a Rust Camera::flatten makes) == rt_scene_set_camera with Camera::new's arguments
+    g, o = pu.build_pair(orc, 99)
+    out = (C.c_double * 24)()
+    orc.api().check(orc.api().kat_camera(o.h, out))
+    g2 = rtb.new_scene()
+    g2.world_build(99, 0xB001, 0)
+    g2.set_camera_fields(list(out))
+    g2.commit()
+    cfg = capi.make_config(64, 16 / 9, 4, 50, seed=2)
+    _, a1, _ = g.render(cfg, want_accum=True)
+    _, a2, _ = g2.render(cfg, want_accum=True)
+    assert np.array_equal(a1, a2)
+
+
 def test_compat_threads_black_rows_and_ppm(orc, tmp_path):
     # world.rs:1198-1202: rows >= threads * (H / threads) are never rendered (top rows of the PPM)
     g, o = pu.build_pair(orc, 13)

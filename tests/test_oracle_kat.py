@@ -225,6 +225,25 @@ def test_B13_camera_cornell(orc):
     np.testing.assert_allclose(c["llc"], [281.639702342662, 274.360297657338, -790], **tol)
 
 
+def test_camera_fields_round_trip(orc):
+    # rt_scene_set_camera_fields (what a Rust Camera::flatten passes: the struct's 24 stored f64, camera.rs:6-17) gives the
+    # camera that Camera::new's arguments give: same fields, same first ray of a path
+    a, b = orc.new_scene(), orc.new_scene()
+    a.set_camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20, 1.5, 0.1, 10, 0.25, 0.75)
+    out = (C.c_double * 24)()
+    orc.api().check(orc.api().kat_camera(a.h, out))
+    b.set_camera_fields(list(out))
+    out_b = (C.c_double * 24)()
+    orc.api().check(orc.api().kat_camera(b.h, out_b))
+    assert list(out) == list(out_b)
+    ra, rb = np.zeros(1, dtype=capi.RAY_DTYPE), np.zeros(1, dtype=capi.RAY_DTYPE)
+    for sc, r in ((a, ra), (b, rb)):
+        orc.api().check(orc.api().kat_camera_ray(sc.h, 7, 12345, 10, 20, 80, 53, r.ctypes.data))
+    assert ra.tobytes() == rb.tobytes()
+    with pytest.raises(capi.RtError):
+        orc.api().check(orc.api().scene_set_camera_fields(a.h, None))
+
+
 # ------------------------------------------------------------------ B14 Checker, B15 Perlin
 def test_B14_checker(orc):
     s = orc.new_scene()
