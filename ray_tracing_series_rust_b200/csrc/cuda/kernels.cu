@@ -65,6 +65,7 @@ struct JobDev {
     int32_t count_events;
     uint32_t wait_thresh; // k_mega_r: finished lanes that end a traversal round
     uint32_t tile_rank, tile_count; // RT_RENDER_TILE_SHARD: npix_rendered counts this shard's pixels only
+    uint32_t chunk;                 // fused kernels: consecutive path indices a warp claims per atomic
 };
 
 // Path-state chunks are streamed (read once / written once per kernel): evict-first hints keep them from
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // consecutive indices (= neighbouring pixels of one sample), so a warp's primary rays stay spatially
 // close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
 // two modes produce bit-identical images.
-#define RT_MEGA_CHUNK 512u
+#define RT_MEGA_CHUNK 512u // path indices a warp claims at once; the host lowers it (JobDev.chunk) for short renders, see launch_render
 template <bool MEDIA, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL, bool XF = true>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
             unsigned long long avail = chunk_end - chunk_next;
             unsigned long long second_base = 0;
             if (avail < n_need) {
-                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)RT_MEGA_CHUNK);
+                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)J.chunk);
                 second_base = __shfl_sync(full, second_base, 0);
             }
             if (!alive && !exhausted) {
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                     alive = true;
                 }
             }
-            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + RT_MEGA_CHUNK; }
+            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + J.chunk; }
             else chunk_next += n_need;
         }
         if (!__any_sync(full, alive)) break;
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
             unsigned long long avail = chunk_end - chunk_next;
             unsigned long long second_base = 0;
             if (avail < n_need) {
-                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)RT_MEGA_CHUNK);
+                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)J.chunk);
                 second_base = __shfl_sync(full, second_base, 0);
             }
             if (!alive && !exhausted) {
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
                     cur = root; sp = 0;
                 }
             }
-            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + RT_MEGA_CHUNK; }
+            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + J.chunk; }
             else chunk_next += n_need;
         }
         if (!__any_sync(full, alive)) break;
@@ -936,6 +937,15 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             // (96 registers, no spills), everything else at 4 (128 registers); media: 4, or 3 with the general two-traversal path.
             const uint32_t pm = !tune.prim_specialise ? RT_PM_ALL
                                 : (scene.prim_mask == 0x1u ? 0x1u : ((scene.prim_mask & ~0x3u) == 0 ? 0x3u : ((scene.prim_mask & ~0x5u) == 0 ? 0x5u : ((scene.prim_mask & ~0x28u) == 0 ? 0x28u : RT_PM_ALL))));
+            // Path indices are claimed per warp in chunks of consecutive indices (neighbouring pixels of one sample).  512 is best for
+            // long renders (fewer atomics, coherent refills: book-1 final -1.7 % at 128); short renders need smaller chunks or the
+            // last chunks leave most warps idle (871k mesh at 10 spp: 127 -> 141 Mpaths/s at 128, 64 at 4096): aim at >= 64 chunks per warp
+            {
+                const unsigned long long warps = 148ull * 7ull * 4ull;
+                unsigned long long c = J.total_paths / (warps * 64ull);
+                c = std::max(32ull, std::min((unsigned long long)RT_MEGA_CHUNK, c)) & ~31ull;
+                J.chunk = (uint32_t)c;
+            }
             const bool wrapper_free = !(scene.flags & 32u) && tune.prim_specialise == 2;
             // resumable traversal: +7 % on the 871k-triangle mesh at 20 lanes, -4 .. -40 % on the sphere scenes, whose shading share
             // is too large to run it with half-empty warps (tools/explore.py ab RTB200_MEGA_WAIT ...)
