@@ -22,7 +22,7 @@ import oracle  # noqa: E402
 import parity_utils as pu  # noqa: E402
 from ray_tracing_series_rust_b200 import capi  # noqa: E402
 
-SCENES = {13: (-15.0, 15.0), 99: (-15.0, 15.0), 5: (0.0, 555.0), 6: (-600.0, 600.0), 14: (-30.0, 56.0)}
+SCENES = {13: (-15.0, 15.0), 99: (-15.0, 15.0), 5: (0.0, 555.0), 6: (-600.0, 600.0), 14: (-30.0, 56.0), 8: (-15.0, 15.0), 4: (0.0, 555.0)}
 
 
 def rays_for(scene_id, o):
