@@ -400,6 +400,11 @@ RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r
     const float tminf = f32_down(t_min);
     float tmaxf = f32_up(best.t);
     const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
+    // the spheres + moving-spheres kernels walk motion-interpolated boxes (DeviceScene::mnodes) when the scene has them
+    const float4* __restrict__ mnodes = reinterpret_cast<const float4*>(S.mnodes);
+    const bool MOTION = PM == 0x3u && mnodes != nullptr;
+    float ms = 0.f;
+    if (MOTION) { const double sd = (r.time - S.motion_t0) * S.motion_inv_dt; ms = (float)(sd < 0.0 ? 0.0 : (sd > 1.0 ? 1.0 : sd)); }
     uint32_t stack[RT_STACK];
     int sp = 0;
     const uint32_t DONE = 0xffffffffu;
@@ -408,8 +413,20 @@ RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r
         uint32_t leaf_first0 = 0, leaf_cnt0 = 0, leaf_first1 = 0, leaf_cnt1 = 0; // cnt = (type << 24) | n, 0 = none
         while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0) {
             // cur = index of the left node of a sibling pair: one 64-byte fetch, two slab tests
-            const float4 lo0 = __ldg(nodes + 2 * cur), hi0 = __ldg(nodes + 2 * cur + 1);
-            const float4 lo1 = __ldg(nodes + 2 * cur + 2), hi1 = __ldg(nodes + 2 * cur + 3);
+            float4 lo0, hi0, lo1, hi1;
+            if (MOTION) { // box(t) = box at the shutter's start + s * delta: 128 bytes per sibling pair
+                lo0 = __ldg(mnodes + 4 * cur); hi0 = __ldg(mnodes + 4 * cur + 1);
+                lo1 = __ldg(mnodes + 4 * cur + 4); hi1 = __ldg(mnodes + 4 * cur + 5);
+                const float4 dl0 = __ldg(mnodes + 4 * cur + 2), dh0 = __ldg(mnodes + 4 * cur + 3);
+                const float4 dl1 = __ldg(mnodes + 4 * cur + 6), dh1 = __ldg(mnodes + 4 * cur + 7);
+                lo0.x = fmaf(dl0.x, ms, lo0.x); lo0.y = fmaf(dl0.y, ms, lo0.y); lo0.z = fmaf(dl0.z, ms, lo0.z);
+                hi0.x = fmaf(dh0.x, ms, hi0.x); hi0.y = fmaf(dh0.y, ms, hi0.y); hi0.z = fmaf(dh0.z, ms, hi0.z);
+                lo1.x = fmaf(dl1.x, ms, lo1.x); lo1.y = fmaf(dl1.y, ms, lo1.y); lo1.z = fmaf(dl1.z, ms, lo1.z);
+                hi1.x = fmaf(dh1.x, ms, hi1.x); hi1.y = fmaf(dh1.y, ms, hi1.y); hi1.z = fmaf(dh1.z, ms, hi1.z);
+            } else {
+                lo0 = __ldg(nodes + 2 * cur); hi0 = __ldg(nodes + 2 * cur + 1);
+                lo1 = __ldg(nodes + 2 * cur + 2); hi1 = __ldg(nodes + 2 * cur + 3);
+            }
             float tn0, tn1;
             bool h0 = slab(lo0, hi0, f, tminf, tmaxf, tn0);
             bool h1 = slab(lo1, hi1, f, tminf, tmaxf, tn1);

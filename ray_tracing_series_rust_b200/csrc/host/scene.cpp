@@ -4,6 +4,7 @@
 // trace return RT_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -363,6 +364,7 @@ bool tex_reads_uv(const rt_scene* s, int32_t t, int depth = 0) {
 }
 
 struct HostFlat {
+    std::vector<BvhNode32> mnodes;     // motion-interpolated boxes (two entries per node), empty without MovingSpheres
     float device_build_ms = 0.f;      // device LBVH time (CUDA events), 0 when the host builder ran
     int64_t device_built_prims = 0;
     std::vector<BvhNode32> nodes;
@@ -382,6 +384,17 @@ struct HostFlat {
 };
 
 // host half of rt_scene_commit: numbering, flattening, BVH build (no CUDA needed)
+struct MotionBox { // bounds of a primitive / subtree at the two ends of the shutter
+    double lo0[3], hi0[3], lo1[3], hi1[3];
+    void clear() { for (int a = 0; a < 3; ++a) { lo0[a] = lo1[a] = DBL_MAX; hi0[a] = hi1[a] = -DBL_MAX; } }
+    void merge(const MotionBox& o) {
+        for (int a = 0; a < 3; ++a) {
+            lo0[a] = std::fmin(lo0[a], o.lo0[a]); hi0[a] = std::fmax(hi0[a], o.hi0[a]);
+            lo1[a] = std::fmin(lo1[a], o.lo1[a]); hi1[a] = std::fmax(hi1[a], o.hi1[a]);
+        }
+    }
+};
+
 struct PhaseTimer { // RTB200_COMMIT_TIMING=1: phase times of rt_scene_commit on stderr
     bool on = std::getenv("RTB200_COMMIT_TIMING") != nullptr;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -442,6 +455,7 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
     const char* env_cp = std::getenv("RTB200_COST_PRIM");
     if (env_cp) bo.cost_prim = std::atof(env_cp);
 
+    std::vector<MotionBox> mbox[PRIM_TYPE_COUNT];
     std::vector<std::pair<uint32_t, uint32_t>> world_range(F.worlds.size());
     for (size_t wi = 0; wi < F.worlds.size(); ++wi) {
         world_range[wi].first = (uint32_t)instances.size();
@@ -452,6 +466,17 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
                 for (int a = 0; a < 3; ++a) { bp[i].bmin[a] = ib.prims[i].bmin[a]; bp[i].bmax[a] = ib.prims[i].bmax[a]; }
                 bp[i].type = ib.prims[i].type;
                 bp[i].src = (uint32_t)i;
+                if (bp[i].type == PRIM_MOVING) {
+                    // the SAH sees the sphere where it is in the middle of the shutter, not its union over the shutter: tall union
+                    // boxes would keep static and moving spheres in the same subtrees, whose interpolated boxes are then tall too.
+                    // The stored boxes (union in `nodes`, both shutter ends in `mnodes`) are refitted over the topology below.
+                    const Node& mn = s->nodes[(size_t)ib.prims[i].node];
+                    const double t0 = mn.d[6], t1 = mn.d[7], r = std::fabs(mn.d[8]), tm = 0.5 * (s->span0 + s->span1);
+                    for (int a = 0; a < 3; ++a) {
+                        const double c = mn.d[a] + ((tm - t0) / (t1 - t0)) * (mn.d[3 + a] - mn.d[a]);
+                        bp[i].bmin[a] = c - r; bp[i].bmax[a] = c + r;
+                    }
+                }
             }
             pt.lap("build prims");
             BuildResult br;
@@ -489,6 +514,20 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
             for (uint32_t src : br.leaf_order) {
                 const FlatPrim& p = ib.prims[src];
                 const Node& n = s->nodes[(size_t)p.node];
+                {   // box at the start and at the end of the shutter, in typed (leaf) order; static primitives: the same box twice
+                    MotionBox mb;
+                    for (int a = 0; a < 3; ++a) { mb.lo0[a] = mb.lo1[a] = p.bmin[a]; mb.hi0[a] = mb.hi1[a] = p.bmax[a]; }
+                    if (p.type == PRIM_MOVING) {
+                        const double t0 = n.d[6], t1 = n.d[7], r = n.d[8];
+                        for (int a = 0; a < 3; ++a) {
+                            const double c0 = n.d[a] + ((s->span0 - t0) / (t1 - t0)) * (n.d[3 + a] - n.d[a]);
+                            const double c1 = n.d[a] + ((s->span1 - t0) / (t1 - t0)) * (n.d[3 + a] - n.d[a]);
+                            mb.lo0[a] = c0 - std::fabs(r); mb.hi0[a] = c0 + std::fabs(r);
+                            mb.lo1[a] = c1 - std::fabs(r); mb.hi1[a] = c1 + std::fabs(r);
+                        }
+                    }
+                    mbox[p.type].push_back(mb);
+                }
                 PrimMeta pm; pm.mat_id = p.mat; pm.prim_id = p.prim_id;
                 meta[p.type].push_back(pm);
                 switch (p.type) {
@@ -546,6 +585,57 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
         world_range[wi].second = (uint32_t)instances.size();
     }
     if (max_depth > RT_BVH_MAX_DEPTH) return fail(RT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+    if (!movings.empty()) { // motion-interpolated boxes: refit both shutter ends over the finished topology (post-order)
+        HF.mnodes.assign(2 * nodes.size(), BvhNode32{});
+        std::vector<MotionBox> nb(nodes.size());
+        struct Item { uint32_t node; bool expanded; };
+        for (const Instance& in : std::vector<Instance>(instances)) {
+            std::vector<Item> st;
+            st.push_back({in.root, false});
+            while (!st.empty()) {
+                Item it = st.back();
+                st.pop_back();
+                const BvhNode32& nd = nodes[it.node];
+                MotionBox& b = nb[it.node];
+                if (nd.count & RT_LEAF_FLAG) {
+                    const uint32_t type = (nd.count >> 24) & 0x7fu, cnt = nd.count & 0xffffffu;
+                    b.clear();
+                    for (uint32_t k = 0; k < cnt; ++k) b.merge(mbox[type][nd.first + k]);
+                } else if (!it.expanded) {
+                    st.push_back({it.node, true});
+                    st.push_back({nd.first, false});
+                    st.push_back({nd.first + 1, false});
+                    continue;
+                } else {
+                    b.clear();
+                    b.merge(nb[nd.first]);
+                    b.merge(nb[nd.first + 1]);
+                }
+                BvhNode32 m0 = nd, m1{};
+                const bool empty = !(b.lo0[0] <= b.hi0[0]);
+                for (int a = 0; a < 3; ++a) {
+                    if (empty) { m0.min[a] = 3.0e38f; m0.max[a] = -3.0e38f; continue; } // the root pair's dummy sibling
+                    m0.min[a] = f32_floor(b.lo0[a] - HF.pad); m0.max[a] = f32_ceil(b.hi0[a] + HF.pad);
+                    const float lo1 = f32_floor(b.lo1[a] - HF.pad), hi1 = f32_ceil(b.hi1[a] + HF.pad);
+                    m1.min[a] = f32_floor((double)lo1 - (double)m0.min[a]); // box0 + delta never pokes inside the box at the shutter's end
+                    m1.max[a] = f32_ceil((double)hi1 - (double)m0.max[a]);
+                }
+                HF.mnodes[2 * (size_t)it.node] = m0;
+                HF.mnodes[2 * (size_t)it.node + 1] = m1;
+                if (!empty) { // `nodes`: the union over the shutter (MovingSphere::bounding_box, hit.rs:317-327) = union of the two end boxes
+                    BvhNode32& un = nodes[it.node];
+                    for (int a = 0; a < 3; ++a) {
+                        un.min[a] = f32_floor(std::fmin(b.lo0[a], b.lo1[a]) - HF.pad);
+                        un.max[a] = f32_ceil(std::fmax(b.hi0[a], b.hi1[a]) + HF.pad);
+                    }
+                }
+            }
+            // the root's sibling (empty leaf) keeps its inverted box
+            HF.mnodes[2 * ((size_t)in.root + 1)] = nodes[in.root + 1];
+        }
+        for (Instance& in : instances)
+            for (int a = 0; a < 3; ++a) { in.bmin[a] = nodes[in.root].min[a]; in.bmax[a] = nodes[in.root].max[a]; }
+    }
 
     // materials: user materials first (ids = builder order), the phase functions of media were
     // appended to s->mats at rt_constant_medium time
@@ -640,7 +730,7 @@ int32_t do_commit(rt_scene* s) {
     DeviceScene& D = s->dev.scene;
     std::memset(&D, 0, sizeof D);
     UploadPlan up;
-    up.add(nodes, D.nodes); up.add(spheres, D.spheres); up.add(movings, D.movings); up.add(gravities, D.gravities); up.add(gtable, D.gravity_table);
+    up.add(nodes, D.nodes); up.add(HF.mnodes, D.mnodes); up.add(spheres, D.spheres); up.add(movings, D.movings); up.add(gravities, D.gravities); up.add(gtable, D.gravity_table);
     up.add(rects, D.rects); up.add(boxes, D.boxes); up.add(tris, D.tris);
     for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) up.add(meta[t], D.meta[t]);
     up.add(instances, D.instances); up.add(ops, D.ops); up.add(media, D.media); up.add(dmats, D.materials); up.add(dtex, D.textures);
@@ -649,6 +739,8 @@ int32_t do_commit(rt_scene* s) {
     D.n_main_instances = HF.n_main_instances;
     D.n_media = (uint32_t)media.size();
     D.n_prims = (uint32_t)s->n_prims;
+    D.motion_t0 = s->span0;
+    D.motion_inv_dt = s->span1 > s->span0 ? 1.0 / (s->span1 - s->span0) : 0.0;
     D.prim_mask = (spheres.empty() ? 0u : 1u) | (movings.empty() ? 0u : 2u) | (gravities.empty() ? 0u : 4u) | (rects.empty() ? 0u : 8u) |
                   (boxes.empty() ? 0u : 16u) | (tris.empty() ? 0u : 32u);
     D.flags = (!rects.empty() || !boxes.empty()) ? 1u : 0u;

@@ -120,6 +120,12 @@ struct DeviceScene {
     const DTexture* textures;
     const PerlinTable* perlin;
     const float4* texels; // rgba f32, row 0 = top of file
+    // Motion-interpolated boxes for scenes with MovingSpheres (nullptr otherwise): node i = mnodes[2i] (box at the shutter's start,
+    // same first / count as nodes[i]) and mnodes[2i + 1] (box at the shutter's end minus box at its start).  The box at ray time t
+    // is box0 + s * delta with s = (t - motion_t0) * motion_inv_dt: exact for the reference's linear motion (hit.rs:275-278), so the
+    // spheres-and-moving-spheres kernels walk tight boxes instead of the union over the shutter that `nodes` holds (hit.rs:317-327).
+    const BvhNode32* mnodes;
+    double motion_t0, motion_inv_dt;
     uint32_t prim_mask; // bit t set: primitives of PrimType t exist
     uint32_t pad0_;
     uint32_t n_main_instances;

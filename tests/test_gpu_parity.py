@@ -329,16 +329,18 @@ def test_determinism_wave_size_and_sharding(orc):
     assert not np.array_equal(a1, a4)
 
 
-@pytest.mark.parametrize("scene_id", [13, 5, 6, 14])
+@pytest.mark.parametrize("scene_id", [13, 99, 8, 5, 6, 14])
 def test_fused_mode_is_bit_identical_to_wavefront(scene_id):
     # RT_RENDER_FORCE_FUSED (persistent k_mega) and RT_RENDER_FORCE_WAVEFRONT share device functions, Philox
-    # streams and the integer accumulator: same image bit for bit, same segment count
+    # streams and the integer accumulator: same image bit for bit, same segment count.  Scene 99: the fused kernel walks
+    # motion-interpolated boxes, the wavefront the union-over-the-shutter boxes; scene 8: the GravitySphere variant
     g = rtb.new_scene()
     g.world_build(scene_id, 3, 48 if scene_id == 14 else 0)  # 14: 4608 triangles => the wavefront uses the warp-scheduled k_extend_p
     g.commit()
     res = []
+    aspect = {13: 1.5, 99: 16 / 9, 8: 1.5}.get(scene_id, 1.0)
     for flags in (4, 8, 0):
-        _, acc, st = g.render(capi.make_config(72, 1.0 if scene_id != 13 else 1.5, 6, 50, seed=4, flags=flags), want_accum=True)
+        _, acc, st = g.render(capi.make_config(72, aspect, 6, 50, seed=4, flags=flags), want_accum=True)
         res.append((acc, st["segments"], st["kernel_launches"]))
     assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1]
     assert np.array_equal(res[0][0], res[2][0])  # and so is whatever RT_MODE_AUTO picks
