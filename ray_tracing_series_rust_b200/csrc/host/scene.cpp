@@ -861,6 +861,8 @@ int32_t rt_sphere(rt_scene* s, const double c[3], double r, int32_t mat) {
 }
 int32_t rt_moving_sphere(rt_scene* s, const double c0[3], const double c1[3], double t0, double t1, double r, int32_t mat) {
     CHECK_SCENE(s); CHECK_MAT(s, mat);
+    if (!c0 || !c1) return fail(RT_ERR_INVALID, "null centre");
+    if (!(t0 != t1)) return fail(RT_ERR_INVALID, "MovingSphere with time0 == time1: get_center divides by zero (hit.rs:275-278)");
     Node n; n.kind = N_MOVING; n.mat = mat;
     for (int a = 0; a < 3; ++a) { n.d[a] = c0[a]; n.d[3 + a] = c1[a]; }
     n.d[6] = t0; n.d[7] = t1; n.d[8] = r;

@@ -79,6 +79,15 @@ def test_builder_ids_and_errors(api):
     assert s.tex_solid((0, 0, 0)) == 3 and s.dielectric(1.5) == 3 and med == 2
 
 
+def test_moving_sphere_needs_a_time_interval(api):
+    s = rtb.new_scene()
+    m = s.lambertian((0.5, 0.5, 0.5))
+    assert s.moving_sphere((0, 0, 0), (0, 1, 0), 0.0, 1.0, 0.5, m) == 0
+    with pytest.raises(capi.RtError) as e:
+        s.moving_sphere((0, 0, 0), (0, 1, 0), 2.0, 2.0, 0.5, m)   # get_center would divide by zero (hit.rs:275-278)
+    assert e.value.code == -1
+
+
 def test_config_asserts_and_image_height(api):
     cfg = capi.make_config(800, 1.5, 500, 50)
     assert api.image_height(C.byref(cfg)) == 533  # (800 / 1.5) as i32
