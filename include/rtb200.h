@@ -319,11 +319,21 @@ RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots);
 #define RT_BVH_HOST_SAH 0
 #define RT_BVH_DEVICE_LBVH 1
 RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder);
+/* Branching factor of the tree the fused mesh kernel walks   [ref: src/bvh.rs:97-112, the binary BvhNode::hit].
+ * 2 (default): sibling pairs.  4: rt_scene_commit also collapses the tree of a scene with one wrapper-free instance and
+ * no media into 128-byte 4-wide nodes (csrc/host/bvh_wide.hpp) and the resumable fused kernel walks those; other
+ * scenes ignore the setting.  Results are identical (closest hit is topology independent). */
+RTB_EXPORT int32_t rt_scene_set_bvh_width(rt_scene* s, int32_t width);
 /* Host-only self check of the flattener and BVH builder (needs no GPU): out[0] nodes, [1] max depth,
  * [2] main instances, [3] instances, [4] media, [5..10] primitives per rt_prim_type, [11] leaves,
  * [12] invariant violations (0 = valid), [13] numbered prims, [14] bytes the last commit uploaded,
  * [15] primitives whose BVH the last commit built on the device. */
 RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]);
+/* Test hook (needs no GPU, computes nothing): runs the host half of rt_scene_commit and writes one DeviceScene
+ * (csrc/rt_types.h; out_bytes must equal its size) whose pointers address the flattened HOST arrays, valid until the
+ * next call or rt_scene_destroy.  tests/host_emul compiles csrc/cuda/rt_device.cuh for the host against it, so the
+ * device functions themselves are checked against the oracle on machines without a GPU.  Never used by a render. */
+RTB_EXPORT int32_t rt_debug_host_scene(rt_scene* s, void* out_scene, uint64_t out_bytes);
 #endif
 
 #ifdef __cplusplus

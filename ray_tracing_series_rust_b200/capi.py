@@ -309,6 +309,21 @@ class Scene:
         fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32]
         return self._c(fn(self.h, int(builder)))
 
+    def set_bvh_width(self, width: int):
+        """2 (default) | 4: rt_scene_commit also builds the 4-wide collapse the resumable fused kernel walks (include/rtb200.h)."""
+        fn = self.api.lib.rt_scene_set_bvh_width
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32]
+        return self._c(fn(self.h, int(width)))
+
+    def debug_host_scene(self, nbytes: int):
+        """rt_debug_host_scene: the host-flattened DeviceScene as raw bytes (pointers address host arrays owned by the scene).
+        Test hook for tests/host_emul; `nbytes` must equal sizeof(DeviceScene)."""
+        fn = self.api.lib.rt_debug_host_scene
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64]
+        buf = C.create_string_buffer(int(nbytes))
+        self._c(fn(self.h, buf, int(nbytes)))
+        return buf
+
     def host_check(self):
         """rt_scene_host_check: flattener / BVH invariants + counters of the last commit (include/rtb200.h)."""
         fn = self.api.lib.rt_scene_host_check

@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
 // two modes produce bit-identical images.
 #define RT_MEGA_CHUNK 512u // path indices a warp claims at once; the host lowers it (JobDev.chunk) for short renders, see launch_render
-template <bool MEDIA, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL, bool XF = true>
+// WIDE = true (media-free, wrapper-free, single instance): world.hit walks the 4-wide collapse (DeviceScene::nodes4).
+template <bool MEDIA, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL, bool XF = true, bool WIDE = false>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
@@ -545,7 +546,19 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         if (!alive) continue;
         // ---- one ray_color iteration (world.rs:63-91)
         HitRec h;
-        const bool hit = world_hit<false, 2, MEDIA, GENERAL_MEDIA, PM, XF>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        bool hit;
+        if (WIDE) {
+            BestHit best;
+            best_init(best, RT_INF);
+            unsigned long long wstack[RT_WIDE_STACK];
+            uint32_t cur = S.root4;
+            int sp = 0;
+            trace_wide<PM, false>(S, r, 0.001, best, cur, sp, wstack, 0u);
+            hit = best.type != RT_NONE;
+            if (hit) h = finalize_hit<2, PM, false>(S, r, best);
+        } else {
+            hit = world_hit<false, 2, MEDIA, GENERAL_MEDIA, PM, XF>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, nullptr);
+        }
         ++my_segments;
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
@@ -589,7 +602,8 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
 // idle lanes claim new paths -> every lane with a ray walks the BVH until `wait_thresh` lanes have finished ->
 // the finished lanes shade / scatter / start their next segment, the others keep their traversal state and
 // continue in the next round.  Per-path arithmetic and Philox streams are those of k_mega: bit-identical images.
-template <int MINB, uint32_t PM>
+// WIDE = true walks the 4-wide collapse of the tree (DeviceScene::nodes4, trace_wide) instead of the sibling pairs.
+template <int MINB, uint32_t PM, bool WIDE = false>
 __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                         int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
@@ -602,12 +616,13 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
     uint64_t path_id = 0;
     bool alive = false, exhausted = false;
     uint32_t my_segments = 0;
-    uint32_t stack[RT_STACK];
+    uint32_t stack[WIDE ? 1 : RT_STACK];
+    unsigned long long wstack[WIDE ? RT_WIDE_STACK : 1];
     uint32_t cur = DONE;
     int sp = 0;
     BestHit best;
     best_init(best, RT_INF);
-    const uint32_t root = __ldg(&S.instances[0].root);
+    const uint32_t root = WIDE ? S.root4 : __ldg(&S.instances[0].root);
     for (;;) {
         // ---- refill idle lanes
         const unsigned need = __ballot_sync(full, !alive && !exhausted);
@@ -643,7 +658,8 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
         }
         if (!__any_sync(full, alive)) break;
         // ---- world.hit for every lane that has a ray; returns when enough lanes are ready to shade
-        trace_resume<PM>(S, r, 0.001, best, cur, sp, stack, J.wait_thresh);
+        if (WIDE) trace_wide<PM, true>(S, r, 0.001, best, cur, sp, wstack, J.wait_thresh);
+        else trace_resume<PM>(S, r, 0.001, best, cur, sp, stack, J.wait_thresh);
         if (!alive || cur != DONE) continue;
         // ---- the rest of this ray_color iteration (world.rs:63-91)
         ++my_segments;
@@ -960,7 +976,16 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 // the mesh walk is L2-latency bound (long-scoreboard 3.6 per issue): more resident warps beat fewer spills:
                 // 5 CTAs/SM (96 regs, 132 B spilled) 126, 6 (80 regs) 134.5, 7 (72 regs, 652 B spilled) 139.7, 8 (64 regs) 135 Mpaths/s
-                else k_mega_r<7, 0x28u><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (scene.nodes4 && tune.bvh_wide > 0) {
+                    // 4-wide walk (experimental until measured): resident CTAs per SM by RTB200_WIDE_OCC
+                    if (tune.wide_occ == 5) k_mega_r<5, 0x28u, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                    else if (tune.wide_occ == 6) k_mega_r<6, 0x28u, true><<<148 * 6, 128, 0, stream>>>(scene, J, Q, d_accum);
+                    else k_mega_r<7, 0x28u, true><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
+                } else k_mega_r<7, 0x28u><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
+            } else if (wrapper_free && scene.nodes4 && tune.bvh_wide > 0 && scene.n_main_instances == 1 && (pm == 0x1u || pm == 0x5u || pm == 0x28u)) {
+                if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                else k_mega<false, 5, false, 0x28u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (wrapper_free && pm != RT_PM_ALL) {
                 if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);       // book-1 final
                 else if (pm == 0x3u) k_mega<false, 5, false, 0x3u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);  // book-1 as shipped

@@ -507,6 +507,77 @@ RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestH
     }
 }
 
+// ------------------------------------------------------------------ 4-wide walk (rt_types.h RT_WIDE_EMPTY, host/bvh_wide.hpp)
+// One 128-byte node = four child boxes in SoA form + four references.  The children that the ray's interval reaches are
+// sorted by entry distance (five compare-exchanges on 64-bit keys = distance bits << 32 | reference); the nearest becomes
+// `cur`, the others are pushed far-to-near.  Leaves travel through the stack like nodes, and an entry whose entry distance
+// has fallen behind closest_so_far is dropped when popped, so no primitive of a box that a nearer hit already culled is
+// tested.  Same closest hit as the binary walk (topology independent; ties by depth-first id in consider()).
+// Requires t_min >= 0 (distance bits are compared as unsigned integers).
+RT_DEV unsigned long long wide_key(float lx, float hx, float ly, float hy, float lz, float hz, float ref, const RayF& f, float t_min, float t_max) {
+    const float x0 = fmaf(lx, f.idx, -f.oodx), x1 = fmaf(hx, f.idx, -f.oodx);
+    const float y0 = fmaf(ly, f.idy, -f.oody), y1 = fmaf(hy, f.idy, -f.oody);
+    const float z0 = fmaf(lz, f.idz, -f.oodz), z1 = fmaf(hz, f.idz, -f.oodz);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+    const uint32_t r = __float_as_uint(ref);
+    if (!(tn <= tf) || r == RT_WIDE_EMPTY) return ~0ull;
+    return ((unsigned long long)(__float_as_uint(tn) & 0x7fffffffu) << 32) | (unsigned long long)r;
+}
+RT_DEV void wide_ce(unsigned long long& a, unsigned long long& b) {
+    const bool s = a > b;
+    const unsigned long long lo = s ? b : a, hi = s ? a : b;
+    a = lo; b = hi;
+}
+RT_DEV uint32_t wide_pop(const unsigned long long* stack, int& sp, float tmaxf) {
+    while (sp) {
+        const unsigned long long e = stack[--sp];
+        if ((uint32_t)(e >> 32) <= __float_as_uint(tmaxf)) return (uint32_t)e; // both non-negative floats: integer compare
+    }
+    return 0xffffffffu;
+}
+// RESUME = true: the resumable form used by k_mega_r (see trace_resume below): state (cur, sp, stack, best) lives in the
+// caller, called by all 32 lanes, returns once `wait_thresh` of the lanes that entered with work have finished.
+// RESUME = false: walks until this lane is done.
+template <uint32_t PM, bool RESUME>
+RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack, uint32_t wait_thresh) {
+    const unsigned full = 0xffffffffu;
+    const RayF f = make_rayf(r);
+    const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
+    const float tminf = fmaxf(f32_down(t_min), 0.f);
+    float tmaxf = f32_up(best.t);
+    const float4* __restrict__ nodes4 = S.nodes4;
+    const uint32_t DONE = 0xffffffffu;
+    uint32_t n0 = 0;
+    if (RESUME) n0 = __popc(__ballot_sync(full, cur != DONE));
+    for (;;) {
+        while (cur != DONE && !(cur & RT_LEAF_FLAG)) {
+            const float4* __restrict__ q = nodes4 + 8 * (size_t)cur;
+            const float4 lx = __ldg(q), hx = __ldg(q + 1), ly = __ldg(q + 2), hy = __ldg(q + 3), lz = __ldg(q + 4), hz = __ldg(q + 5), rf = __ldg(q + 6);
+            unsigned long long k0 = wide_key(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, rf.x, f, tminf, tmaxf);
+            unsigned long long k1 = wide_key(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
+            unsigned long long k2 = wide_key(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);
+            unsigned long long k3 = wide_key(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, rf.w, f, tminf, tmaxf);
+            wide_ce(k0, k1); wide_ce(k2, k3); wide_ce(k0, k2); wide_ce(k1, k3); wide_ce(k1, k2);
+            if (k3 != ~0ull) stack[sp++] = k3;
+            if (k2 != ~0ull) stack[sp++] = k2;
+            if (k1 != ~0ull) stack[sp++] = k1;
+            cur = (k0 != ~0ull) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
+        }
+        if (cur != DONE) { // a leaf reference
+            leaf_test<PM>(S, r, pre, t_min, best, (cur >> 28) & 7u, cur & 0x1ffffffu, ((cur >> 25) & 7u) + 1u, 0u);
+            tmaxf = f32_up(best.t);
+            cur = wide_pop(stack, sp, tmaxf);
+        }
+        if (RESUME) {
+            const uint32_t still = __popc(__ballot_sync(full, cur != DONE));
+            if (still == 0 || n0 - still >= wait_thresh) break;
+        } else if (cur == DONE) {
+            break;
+        }
+    }
+}
+
 RT_DEV bool inst_box_hit(const Instance* ip, const Ray& r, double t_min, double t_max) {
     const RayF f = make_rayf(r);
     float tn;

@@ -19,6 +19,7 @@
 #include "../cuda/kernels.h"
 #include "../rt_types.h"
 #include "bvh_build.hpp"
+#include "bvh_wide.hpp"
 #include "io.hpp"
 #include "world.hpp"
 
@@ -109,6 +110,7 @@ struct rt_scene {
     DeviceBuffers dev;
     RenderTuning tuning;
     Workspace* workspace = nullptr;
+    std::shared_ptr<void> debug_flat; // rt_debug_host_scene: the host-flattened arrays handed to the caller
     ~rt_scene() { dev.release(); free_workspace(workspace); }
 };
 
@@ -381,6 +383,9 @@ struct HostFlat {
     uint32_t n_main_instances = 0;
     int max_depth = 0;
     double pad = 0.0;
+    std::vector<float4> nodes4;        // 4-wide collapse of the single main instance's tree (tuning.bvh_wide), else empty
+    uint32_t root4 = RT_WIDE_EMPTY;
+    int wide_depth = 0;
 };
 
 // host half of rt_scene_commit: numbering, flattening, BVH build (no CUDA needed)
@@ -700,7 +705,41 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
     }
 
     HF.n_main_instances = world_range[0].second - world_range[0].first;
+    // 4-wide collapse for the resumable fused kernel: one wrapper-free main instance, no media (k_mega_r's own conditions)
+    if (s->tuning.bvh_wide > 0 && HF.n_main_instances == 1 && media.empty() && instances[world_range[0].first].chain_len == 0) {
+        WideResult wr = collapse_to_wide(nodes, instances[world_range[0].first].root);
+        if (wr.ok) {
+            HF.nodes4.swap(wr.nodes);
+            HF.root4 = wr.root;
+            HF.wide_depth = wr.max_depth;
+        }
+        pt.lap("4-wide collapse");
+    }
     return RT_OK;
+}
+
+// everything in DeviceScene that is not a pointer: counts, masks, kernel-selection flags, camera, background
+void set_scene_scalars(const rt_scene* s, const HostFlat& HF, DeviceScene& D) {
+    D.root4 = HF.root4;
+    D.n_main_instances = HF.n_main_instances;
+    D.n_media = (uint32_t)HF.media.size();
+    D.n_prims = (uint32_t)s->n_prims;
+    D.motion_t0 = s->span0;
+    D.motion_inv_dt = s->span1 > s->span0 ? 1.0 / (s->span1 - s->span0) : 0.0;
+    D.prim_mask = (HF.spheres.empty() ? 0u : 1u) | (HF.movings.empty() ? 0u : 2u) | (HF.gravities.empty() ? 0u : 4u) | (HF.rects.empty() ? 0u : 8u) |
+                  (HF.boxes.empty() ? 0u : 16u) | (HF.tris.empty() ? 0u : 32u);
+    D.flags = (!HF.rects.empty() || !HF.boxes.empty()) ? 1u : 0u;
+    {
+        bool all_fast = true;
+        for (const Medium& m : HF.media) all_fast = all_fast && m.fast_type != 0;
+        if (all_fast) D.flags |= 2u;
+    }
+    if (!HF.perlin.empty()) D.flags |= 8u;     // Perlin-noise textures: expensive, divergent shading
+    if (!HF.texels.empty()) D.flags |= 16u;    // image textures (sphere uv needed)
+    if (!HF.ops.empty()) D.flags |= 32u;       // Translate / RotateY wrappers present
+    if (HF.tris.size() >= 4096) D.flags |= 4u; // deep triangle BVH: prefer the persistent warp-scheduled extend kernel
+    if (s->camera.set) D.cam = s->camera.cam;
+    for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
 }
 
 int32_t do_commit(rt_scene* s) {
@@ -734,27 +773,11 @@ int32_t do_commit(rt_scene* s) {
     up.add(rects, D.rects); up.add(boxes, D.boxes); up.add(tris, D.tris);
     for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) up.add(meta[t], D.meta[t]);
     up.add(instances, D.instances); up.add(ops, D.ops); up.add(media, D.media); up.add(dmats, D.materials); up.add(dtex, D.textures);
-    up.add(perlin, D.perlin); up.add(texels, D.texels);
+    up.add(perlin, D.perlin); up.add(texels, D.texels); up.add(HF.nodes4, D.nodes4);
     if ((ce = up.run(s->dev)) != cudaSuccess) return fail_cuda(ce, "scene upload");
-    D.n_main_instances = HF.n_main_instances;
-    D.n_media = (uint32_t)media.size();
-    D.n_prims = (uint32_t)s->n_prims;
-    D.motion_t0 = s->span0;
-    D.motion_inv_dt = s->span1 > s->span0 ? 1.0 / (s->span1 - s->span0) : 0.0;
-    D.prim_mask = (spheres.empty() ? 0u : 1u) | (movings.empty() ? 0u : 2u) | (gravities.empty() ? 0u : 4u) | (rects.empty() ? 0u : 8u) |
-                  (boxes.empty() ? 0u : 16u) | (tris.empty() ? 0u : 32u);
-    D.flags = (!rects.empty() || !boxes.empty()) ? 1u : 0u;
-    {
-        bool all_fast = true;
-        for (const Medium& m : media) all_fast = all_fast && m.fast_type != 0;
-        if (all_fast) D.flags |= 2u;
-    }
-    if (!perlin.empty()) D.flags |= 8u;     // Perlin-noise textures: expensive, divergent shading
-    if (!texels.empty()) D.flags |= 16u;    // image textures (sphere uv needed)
-    if (!ops.empty()) D.flags |= 32u;       // Translate / RotateY wrappers present
-    if (tris.size() >= 4096) D.flags |= 4u; // deep triangle BVH: prefer the persistent warp-scheduled extend kernel
-    if (s->camera.set) D.cam = s->camera.cam;
-    for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
+    if (HF.nodes4.empty()) D.nodes4 = nullptr;
+    if (HF.mnodes.empty()) D.mnodes = nullptr;
+    set_scene_scalars(s, HF, D);
     s->dev.valid = true;
     s->committed = true;
     return RT_OK;
@@ -775,6 +798,8 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_MEGA_WAIT"))) s->tuning.mega_wait = std::atoi(e);
     if ((e = std::getenv("RTB200_BVH_BUILDER"))) s->tuning.bvh_builder = (std::strcmp(e, "lbvh") == 0 || std::strcmp(e, "1") == 0) ? 1 : 0;
     if ((e = std::getenv("RTB200_BVH_DEVICE_MIN"))) s->tuning.bvh_device_min = std::atoi(e);
+    if ((e = std::getenv("RTB200_BVH_WIDE"))) s->tuning.bvh_wide = std::atoi(e);
+    if ((e = std::getenv("RTB200_WIDE_OCC"))) s->tuning.wide_occ = std::atoi(e);
     return s;
 }
 void rt_scene_destroy(rt_scene* s) { delete s; }
@@ -1241,6 +1266,27 @@ RTB_EXPORT int32_t rt_unit_op(rt_scene* s, int32_t op, uint32_t ia, uint32_t ib,
 // bounds lie inside its leaf box and every node inside its parent, that each typed slot is referenced
 // by exactly one leaf, and returns out[0] nodes, [1] max depth, [2] main instances, [3] all instances,
 // [4] media, [5..10] primitives per type, [11] leaves, [12] violations (0 = valid), [13] prims numbered.
+RTB_EXPORT int32_t rt_debug_host_scene(rt_scene* s, void* out_scene, uint64_t out_bytes) {
+    CHECK_SCENE(s);
+    if (!out_scene || out_bytes != sizeof(DeviceScene)) return fail(RT_ERR_INVALID, "out_scene must hold one DeviceScene (csrc/rt_types.h)");
+    std::shared_ptr<HostFlat> hf = std::make_shared<HostFlat>();
+    const int32_t fr = flatten_host(s, *hf);
+    if (fr != RT_OK) return fr;
+    HostFlat& HF = *hf;
+    DeviceScene D;
+    std::memset(&D, 0, sizeof D);
+    D.nodes = HF.nodes.data(); D.mnodes = HF.mnodes.empty() ? nullptr : HF.mnodes.data(); D.nodes4 = HF.nodes4.empty() ? nullptr : HF.nodes4.data();
+    D.spheres = HF.spheres.data(); D.movings = HF.movings.data(); D.gravities = HF.gravities.data(); D.gravity_table = HF.gtable.data();
+    D.rects = HF.rects.data(); D.boxes = HF.boxes.data(); D.tris = HF.tris.data();
+    for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) D.meta[t] = HF.meta[t].data();
+    D.instances = HF.instances.data(); D.ops = HF.ops.data(); D.media = HF.media.data(); D.materials = HF.dmats.data(); D.textures = HF.dtex.data();
+    D.perlin = HF.perlin.data(); D.texels = HF.texels.data();
+    set_scene_scalars(s, HF, D);
+    std::memcpy(out_scene, &D, sizeof D);
+    s->debug_flat = hf; // the arrays live until the next call or rt_scene_destroy
+    return RT_OK;
+}
+
 RTB_EXPORT int32_t rt_scene_host_check(rt_scene* s, int64_t out[16]) {
     CHECK_SCENE(s);
     if (!out) return fail(RT_ERR_INVALID, "null out");
@@ -1310,6 +1356,14 @@ RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder) {
     CHECK_SCENE(s);
     if (builder != RT_BVH_HOST_SAH && builder != RT_BVH_DEVICE_LBVH) return fail(RT_ERR_INVALID, "unknown BVH builder");
     s->tuning.bvh_builder = builder;
+    return RT_OK;
+}
+
+RTB_EXPORT int32_t rt_scene_set_bvh_width(rt_scene* s, int32_t width) {
+    CHECK_SCENE(s);
+    if (width != 2 && width != 4) return fail(RT_ERR_INVALID, "BVH width must be 2 or 4");
+    s->tuning.bvh_wide = width == 4 ? 1 : 0;
+    s->committed = false;
     return RT_OK;
 }
 

@@ -23,6 +23,15 @@ namespace rtb {
 #define RT_LEAF_FLAG 0x80000000u
 #define RT_BVH_MAX_DEPTH 60 // traversal stack is 64 entries (rt_device.cuh RT_STACK)
 
+// 4-wide BVH node (128 bytes = one cache line, eight float4), the binary tree collapsed by surface area
+// (host/bvh_wide.hpp): q0 = lo.x of the four children, q1 = hi.x, q2 = lo.y, q3 = hi.y, q4 = lo.z, q5 = hi.z,
+// q6 = four child references, q7 unused.  A reference is the index of a 4-wide node (bit 31 clear), a leaf
+// RT_LEAF_FLAG | type << 28 | (n - 1) << 25 | first (n <= 8 primitives of one type, first < 2^25), or
+// RT_WIDE_EMPTY for an unused slot.  Half as many dependent fetches per ray as the sibling-pair walk.
+#define RT_WIDE_EMPTY 0xffffffffu
+#define RT_WIDE_STACK 96 // 64-bit entries (entry distance, reference); a visit pushes at most three
+#define RT_WIDE_MAX_DEPTH 30
+
 enum PrimType : uint32_t {
     PRIM_SPHERE = 0, PRIM_MOVING = 1, PRIM_GRAVITY = 2, PRIM_RECT = 3, PRIM_BOX = 4, PRIM_TRI = 5,
     PRIM_TYPE_COUNT = 6, PRIM_MEDIUM = 6
@@ -125,9 +134,11 @@ struct DeviceScene {
     // is box0 + s * delta with s = (t - motion_t0) * motion_inv_dt: exact for the reference's linear motion (hit.rs:275-278), so the
     // spheres-and-moving-spheres kernels walk tight boxes instead of the union over the shutter that `nodes` holds (hit.rs:317-327).
     const BvhNode32* mnodes;
+    // 4-wide collapse of the main instance's tree (nullptr unless built: single wrapper-free instance, see RT_WIDE_EMPTY above)
+    const float4* nodes4;
     double motion_t0, motion_inv_dt;
     uint32_t prim_mask; // bit t set: primitives of PrimType t exist
-    uint32_t pad0_;
+    uint32_t root4;     // reference of the 4-wide root (valid when nodes4 != nullptr)
     uint32_t n_main_instances;
     uint32_t n_media;
     uint32_t n_prims;

@@ -1,0 +1,76 @@
+"""A/B of the 4-wide BVH walk against the sibling-pair walk (same process, same GPU): bit-identity of the accumulators
+on small renders, then timings on the book-1 final, the bouncing-spheres frame and the 871 200-triangle mesh room."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import ray_tracing_series_rust_b200 as rtb
+from ray_tracing_series_rust_b200 import capi
+
+
+def scene(sid, seed, param, width, env=None):
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = v
+    s = rtb.new_scene()  # tuning knobs are read from the environment here
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    s.world_build(sid, seed, param)
+    s.set_bvh_width(width)
+    t0 = time.time()
+    s.commit()
+    return s, time.time() - t0
+
+
+def timed(s, W, aspect, spp, label, reps=2, seed=1):
+    best = None
+    for _ in range(reps):
+        _, _, st = s.render(capi.make_config(W, aspect, spp, 50, seed=seed))
+        if best is None or st["ms_device"] < best["ms_device"]:
+            best = st
+    print(json.dumps({"label": label, "ms_device": round(best["ms_device"], 3), "Mpaths_s": round(best["paths"] / best["ms_device"] / 1e3, 2),
+                      "seg_per_path": round(best["segments"] / best["paths"], 3)}), flush=True)
+
+
+def main():
+    ok = True
+    for name, sid, seed, param, W, aspect, spp, env in (
+            ("mesh8k k_mega_r", 14, 0xB004, 64, 200, 1.0, 8, None),
+            ("mesh8k k_mega", 14, 0xB004, 64, 200, 1.0, 8, {"RTB200_MEGA_WAIT": "0"}),
+            ("book1 k_mega", 13, 0xB001, 0, 240, 1.5, 8, None),
+            ("bouncing k_mega", 8, 0xB005, 0, 240, 1.5, 8, None)):
+        acc = []
+        for width in (2, 4):
+            s, _ = scene(sid, seed, param, width, env)
+            acc.append(s.render(capi.make_config(W, aspect, spp, 50, seed=3), want_accum=True)[1])
+            s.close()
+        same = bool(np.array_equal(acc[0], acc[1]))
+        ok = ok and same
+        print(json.dumps({"identity": name, "bit_identical": same, "nonzero": int((acc[0] != 0).sum())}), flush=True)
+    for name, sid, seed, W, aspect, spp in (("book1_final", 13, 0xB001, 800, 1.5, 500), ("bouncing_frame", 8, 0xB005, 800, 1.5, 200)):
+        for width in (2, 4, 2, 4):
+            s, c = scene(sid, seed, 0, width)
+            s.render(capi.make_config(W, aspect, 20, 50))
+            timed(s, W, aspect, spp, f"{name} width {width} (commit {c * 1e3:.1f} ms)")
+            s.close()
+    for label, width, env in (("pairs k_mega_r<7>", 2, None), ("wide k_mega_r<7>", 4, {"RTB200_WIDE_OCC": "7"}), ("wide k_mega_r<6>", 4, {"RTB200_WIDE_OCC": "6"}),
+                              ("wide k_mega_r<5>", 4, {"RTB200_WIDE_OCC": "5"}), ("wide k_mega<5>", 4, {"RTB200_MEGA_WAIT": "0"})):
+        s, c = scene(14, 0xB004, 660, width, env)
+        s.render(capi.make_config(1000, 1.0, 4, 50))
+        timed(s, 1000, 1.0, 20, f"mesh871k {label} (commit {c:.2f} s)")
+        s.close()
+    print(json.dumps({"all_bit_identical": ok}), flush=True)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
