@@ -319,10 +319,11 @@ RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots);
 #define RT_BVH_HOST_SAH 0
 #define RT_BVH_DEVICE_LBVH 1
 RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder);
-/* Branching factor of the tree the fused mesh kernel walks   [ref: src/bvh.rs:97-112, the binary BvhNode::hit].
- * 2 (default): sibling pairs.  4: rt_scene_commit also collapses the tree of a scene with one wrapper-free instance and
- * no media into 128-byte 4-wide nodes (csrc/host/bvh_wide.hpp) and the resumable fused kernel walks those; other
- * scenes ignore the setting.  Results are identical (closest hit is topology independent). */
+/* Branching factor of the tree the fused kernels walk   [ref: src/bvh.rs:97-112, the binary BvhNode::hit].
+ * 2: sibling pairs.  4: rt_scene_commit also collapses the tree of a scene with one wrapper-free instance and no media
+ * into 128-byte 4-wide nodes (csrc/host/bvh_wide.hpp) and the fused kernels walk those; other scenes ignore it.
+ * 0 (default): 4 where it measured faster (plain-sphere scenes, meshes of >= 4096 triangles), else 2.
+ * Results are identical (closest hit is topology independent). */
 RTB_EXPORT int32_t rt_scene_set_bvh_width(rt_scene* s, int32_t width);
 /* Host-only self check of the flattener and BVH builder (needs no GPU): out[0] nodes, [1] max depth,
  * [2] main instances, [3] instances, [4] media, [5..10] primitives per rt_prim_type, [11] leaves,

@@ -310,7 +310,7 @@ class Scene:
         return self._c(fn(self.h, int(builder)))
 
     def set_bvh_width(self, width: int):
-        """2 (default) | 4: rt_scene_commit also builds the 4-wide collapse the resumable fused kernel walks (include/rtb200.h)."""
+        """0 (auto, default) | 2 | 4: whether rt_scene_commit also builds the 4-wide collapse the fused kernels walk (include/rtb200.h)."""
         fn = self.api.lib.rt_scene_set_bvh_width
         fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32]
         return self._c(fn(self.h, int(width)))

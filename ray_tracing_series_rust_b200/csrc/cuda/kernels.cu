@@ -976,13 +976,13 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 // the mesh walk is L2-latency bound (long-scoreboard 3.6 per issue): more resident warps beat fewer spills:
                 // 5 CTAs/SM (96 regs, 132 B spilled) 126, 6 (80 regs) 134.5, 7 (72 regs, 652 B spilled) 139.7, 8 (64 regs) 135 Mpaths/s
-                else if (scene.nodes4 && tune.bvh_wide > 0) {
-                    // 4-wide walk (experimental until measured): resident CTAs per SM by RTB200_WIDE_OCC
+                else if (scene.nodes4 && tune.bvh_wide != 0) {
+                    // 4-wide walk: 871k mesh 149.8 -> 179.5 Mpaths/s at 7 CTAs/SM (6: 175.3, 5: 166.7; tools/ab_wide.py); RTB200_WIDE_OCC
                     if (tune.wide_occ == 5) k_mega_r<5, 0x28u, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                     else if (tune.wide_occ == 6) k_mega_r<6, 0x28u, true><<<148 * 6, 128, 0, stream>>>(scene, J, Q, d_accum);
                     else k_mega_r<7, 0x28u, true><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
                 } else k_mega_r<7, 0x28u><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
-            } else if (wrapper_free && scene.nodes4 && tune.bvh_wide > 0 && scene.n_main_instances == 1 && (pm == 0x1u || pm == 0x5u || pm == 0x28u)) {
+            } else if (wrapper_free && scene.nodes4 && tune.bvh_wide != 0 && scene.n_main_instances == 1 && (pm == 0x1u || pm == 0x5u || pm == 0x28u)) {
                 if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega<false, 5, false, 0x28u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);

@@ -705,8 +705,13 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
     }
 
     HF.n_main_instances = world_range[0].second - world_range[0].first;
-    // 4-wide collapse for the resumable fused kernel: one wrapper-free main instance, no media (k_mega_r's own conditions)
-    if (s->tuning.bvh_wide > 0 && HF.n_main_instances == 1 && media.empty() && instances[world_range[0].first].chain_len == 0) {
+    // 4-wide collapse for the fused kernels: one wrapper-free main instance, no media (the conditions of their specialised
+    // variants).  Auto (measured on B200, tools/ab_wide.py): scenes of plain spheres (book-1 final +6 %) and large triangle
+    // meshes (871 200 triangles +20 %); not GravitySphere scenes (-2 %).  rt_scene_set_bvh_width(4) forces it where possible.
+    const bool wide_possible = HF.n_main_instances == 1 && media.empty() && instances[world_range[0].first].chain_len == 0;
+    const bool only_spheres = !spheres.empty() && movings.empty() && gravities.empty() && rects.empty() && boxes.empty() && tris.empty();
+    const bool big_mesh = tris.size() >= 4096 && spheres.empty() && movings.empty() && gravities.empty() && boxes.empty();
+    if (wide_possible && (s->tuning.bvh_wide > 0 || (s->tuning.bvh_wide < 0 && (only_spheres || big_mesh)))) {
         WideResult wr = collapse_to_wide(nodes, instances[world_range[0].first].root);
         if (wr.ok) {
             HF.nodes4.swap(wr.nodes);
@@ -1361,8 +1366,8 @@ RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder) {
 
 RTB_EXPORT int32_t rt_scene_set_bvh_width(rt_scene* s, int32_t width) {
     CHECK_SCENE(s);
-    if (width != 2 && width != 4) return fail(RT_ERR_INVALID, "BVH width must be 2 or 4");
-    s->tuning.bvh_wide = width == 4 ? 1 : 0;
+    if (width != 0 && width != 2 && width != 4) return fail(RT_ERR_INVALID, "BVH width must be 0 (auto), 2 or 4");
+    s->tuning.bvh_wide = width == 4 ? 1 : (width == 2 ? 0 : -1);
     s->committed = false;
     return RT_OK;
 }

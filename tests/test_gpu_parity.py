@@ -375,6 +375,35 @@ def test_device_lbvh_builder_parity(orc, scene_id, param, monkeypatch):
         g.set_bvh_builder(7)
 
 
+@pytest.mark.parametrize("scene_id,param,env", [(13, 0, None), (8, 0, None), (14, 64, None), (14, 64, {"RTB200_MEGA_WAIT": "0"}), (10, 0, None)])
+def test_wide_bvh_walk_is_bit_identical_to_the_pair_walk(orc, scene_id, param, env, monkeypatch):
+    # rt_scene_set_bvh_width: the 4-wide collapse (csrc/host/bvh_wide.hpp) walked by k_mega / k_mega_r (trace_wide) gives, bit for
+    # bit, the image of the sibling-pair walk and the oracle's sums (closest hit is topology independent; ties by depth-first id).
+    # 14/64 = 8192 triangles: the resumable kernel; with RTB200_MEGA_WAIT=0 plain k_mega; 8 = GravitySpheres (wide only when forced)
+    for k, v in (env or {}).items():
+        monkeypatch.setenv(k, v)
+    acc, segs = {}, {}
+    aspect = 1.0 if scene_id == 14 else 1.5
+    cfg = capi.make_config(96, aspect, 6, 50, seed=9)
+    for width in (2, 4, 0):
+        g = rtb.new_scene()
+        g.world_build(scene_id, 0xB001, param)
+        g.set_bvh_width(width)
+        g.commit()
+        _, acc[width], st = g.render(cfg, want_accum=True)
+        segs[width] = st["segments"]
+        assert st["iterations"] == 1  # fused mode
+        g.close()
+    assert np.array_equal(acc[2], acc[4]) and np.array_equal(acc[2], acc[0]) and segs[2] == segs[4] == segs[0]
+    o = orc.new_scene()
+    o.world_build(scene_id, 0xB001, param)
+    o.commit()
+    _, a_o, _ = o.render(cfg, want_accum=True)
+    rel = np.abs(acc[4] - a_o) / np.maximum(np.abs(a_o), 2.0 ** 32 * 1e-3)
+    assert (rel > 1e-5).any(axis=2).mean() < 0.02
+    o.close()
+
+
 def test_tile_sharding_is_bit_identical_and_matches_oracle(orc):
     # SURVEY.md 8(e) tile sharding: 4-row bands dealt round-robin; H = 53 (not a multiple of 4), 3 shards, both render modes
     from ray_tracing_series_rust_b200 import sharding

@@ -41,7 +41,19 @@ def timed(s, W, aspect, spp, label, reps=2, seed=1):
                       "seg_per_path": round(best["segments"] / best["paths"], 3)}), flush=True)
 
 
+def sweep():
+    """RTB200_MEGA_WAIT (lanes that end a k_mega_r round) for the 4-wide walk on the 871 200-triangle mesh room"""
+    for wait in sys.argv[2].split(","):
+        s, c = scene(14, 0xB004, 660, 0, {"RTB200_MEGA_WAIT": wait})
+        s.render(capi.make_config(1000, 1.0, 4, 50))
+        timed(s, 1000, 1.0, 20, f"mesh871k wide k_mega_r<7> wait {wait} (commit {c:.2f} s)")
+        s.close()
+    return 0
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "sweep":
+        return sweep()
     ok = True
     for name, sid, seed, param, W, aspect, spp, env in (
             ("mesh8k k_mega_r", 14, 0xB004, 64, 200, 1.0, 8, None),
