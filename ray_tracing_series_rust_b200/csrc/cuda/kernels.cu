@@ -176,7 +176,8 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
 }
 
 // ------------------------------------------------------------------ k_extend: world.hit(ray, 0.001, inf) for every live slot
-template <bool MEDIA, bool COUNT, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL>
+// WIDE = true: the main world is walked through its 4-wide collapse (DeviceScene::nodes4, Instance::root4)
+template <bool MEDIA, bool COUNT, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL, bool WIDE = false>
 __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, PathState P, Queues Q, int parity) {
     uint32_t* counts = Q.counts + 8 * parity;
     uint32_t my_segments = 0;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(128, MINB) k_extend(const __grid_constant__ De
         uint32_t segment = 0;
         if (MEDIA) { const SlotD d = ld_stream(&P.D[slot]); path_id = d.path_id; segment = d.segment; }
         HitRec h;
-        const bool hit = world_hit<COUNT, 2, MEDIA, GENERAL_MEDIA, PM>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
+        const bool hit = world_hit<COUNT, 2, MEDIA, GENERAL_MEDIA, PM, true, WIDE>(S, r, 0.001, RT_INF, true, J.seed, path_id, segment, h, &tc);
         ++my_segments;
         uint32_t qi = Q_MISS;
         if (hit) {
@@ -875,15 +876,20 @@ static void launch_extend_p(cudaStream_t st, const DeviceScene& scene, const Job
 }
 
 template <bool MEDIA, bool COUNT>
-static void launch_extend(int blocks, bool specialise, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
+static void launch_extend(int blocks, bool specialise, bool wide, cudaStream_t st, const DeviceScene& scene, const JobDev& J, const PathState& P, const Queues& Q, int parity) {
     // MINB = resident 128-thread blocks per SM the kernel is compiled for: 4 (128 registers) with generic media code or event
     // counters, 5 (96 registers) otherwise - also for the two primitive-mask-specialised media kernels, which then spill 56-80
     // bytes but gain 5 % (tools/explore.py ab, Cornell smoke 634 -> 668, book-2 final 325 -> 340 Mpaths/s); 6 CTAs/SM (80
     // registers, 130-340 B spilled) is +1 % on Cornell smoke and -1.4 % on book-2 final.  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
     // the general two-traversal path; the two media scenes of the reference also get their primitive mask compiled in.
+    // wide = the scene carries the 4-wide collapse and the caller forced it (rt_scene_set_bvh_width(4)): not yet measured for these kernels
     if constexpr (MEDIA) {
         if (!(scene.flags & 2u)) {
             k_extend<true, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        } else if (!COUNT && specialise && wide && (scene.prim_mask & ~0x18u) == 0) {
+            k_extend<true, false, 5, false, 0x18u, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        } else if (!COUNT && specialise && wide && (scene.prim_mask & ~0x1bu) == 0) {
+            k_extend<true, false, 5, false, 0x1bu, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
         } else if (!COUNT && specialise && (scene.prim_mask & ~0x18u) == 0) {
             k_extend<true, false, 5, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
         } else if (!COUNT && specialise && (scene.prim_mask & ~0x1bu) == 0) {
@@ -892,9 +898,11 @@ static void launch_extend(int blocks, bool specialise, cudaStream_t st, const De
             k_extend<true, COUNT, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
         }
     } else if constexpr (COUNT) {
-        k_extend<false, true, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        if (wide) k_extend<false, true, 4, false, RT_PM_ALL, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // counts 4 boxes per wide node visited
+        else k_extend<false, true, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
     } else {
-        k_extend<false, false, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        if (wide) k_extend<false, false, 5, false, RT_PM_ALL, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        else k_extend<false, false, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
     }
 }
 
@@ -941,6 +949,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         // measured (profiles/): the warp-scheduled persistent kernel wins on deep triangle BVHs (+22 % on the 871k mesh),
         // the one-ray-per-thread kernel on small scenes and on scenes with media
         const int ext_kind = tune.extend_kind >= 0 ? tune.extend_kind : ((!media && (scene.flags & 4u)) ? 1 : 0);
+        const bool ext_wide = scene.nodes4 != nullptr && tune.bvh_wide > 0; // wavefront: only when forced (unmeasured)
         const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, ext_occ) * (uint32_t)std::max(1, tune.extend_waves));
         CK(cudaEventRecord(w->ev_begin, stream));
         // RT_MODE_AUTO (measured on B200, profiles/README.md): the fused persistent kernel wins where shading is cheap
@@ -1030,9 +1039,9 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 if (ext_kind == 1 && !media) {
                     if (tune.count_events) launch_extend_p<true>(stream, scene, J, P, Q, parity); else launch_extend_p<false>(stream, scene, J, P, Q, parity);
                 } else if (media) {
-                    if (tune.count_events) launch_extend<true, true>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity); else launch_extend<true, false>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity);
+                    if (tune.count_events) launch_extend<true, true>(eblocks, tune.prim_specialise != 0, ext_wide, stream, scene, J, P, Q, parity); else launch_extend<true, false>(eblocks, tune.prim_specialise != 0, ext_wide, stream, scene, J, P, Q, parity);
                 } else {
-                    if (tune.count_events) launch_extend<false, true>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity); else launch_extend<false, false>(eblocks, tune.prim_specialise != 0, stream, scene, J, P, Q, parity);
+                    if (tune.count_events) launch_extend<false, true>(eblocks, tune.prim_specialise != 0, ext_wide, stream, scene, J, P, Q, parity); else launch_extend<false, false>(eblocks, tune.prim_specialise != 0, ext_wide, stream, scene, J, P, Q, parity);
                 }
                 if (tune.timed_extend) {
                     CK(cudaEventRecord(eb, stream));

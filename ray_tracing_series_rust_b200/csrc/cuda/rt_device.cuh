@@ -539,8 +539,9 @@ RT_DEV uint32_t wide_pop(const unsigned long long* stack, int& sp, float tmaxf) 
 // RESUME = true: the resumable form used by k_mega_r (see trace_resume below): state (cur, sp, stack, best) lives in the
 // caller, called by all 32 lanes, returns once `wait_thresh` of the lanes that entered with work have finished.
 // RESUME = false: walks until this lane is done.
-template <uint32_t PM, bool RESUME>
-RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack, uint32_t wait_thresh) {
+template <uint32_t PM, bool RESUME, bool COUNT = false>
+RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack, uint32_t wait_thresh,
+                       uint32_t inst = 0u, TraceCounters* cnt = nullptr) {
     const unsigned full = 0xffffffffu;
     const RayF f = make_rayf(r);
     const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
@@ -554,6 +555,7 @@ RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit
         while (cur != DONE && !(cur & RT_LEAF_FLAG)) {
             const float4* __restrict__ q = nodes4 + 8 * (size_t)cur;
             const float4 lx = __ldg(q), hx = __ldg(q + 1), ly = __ldg(q + 2), hy = __ldg(q + 3), lz = __ldg(q + 4), hz = __ldg(q + 5), rf = __ldg(q + 6);
+            if (COUNT) cnt->nodes += 4;
             unsigned long long k0 = wide_key(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, rf.x, f, tminf, tmaxf);
             unsigned long long k1 = wide_key(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
             unsigned long long k2 = wide_key(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);
@@ -565,7 +567,8 @@ RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit
             cur = (k0 != ~0ull) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
         }
         if (cur != DONE) { // a leaf reference
-            leaf_test<PM>(S, r, pre, t_min, best, (cur >> 28) & 7u, cur & 0x1ffffffu, ((cur >> 25) & 7u) + 1u, 0u);
+            if (COUNT) cnt->prims += ((cur >> 25) & 7u) + 1u;
+            leaf_test<PM>(S, r, pre, t_min, best, (cur >> 28) & 7u, cur & 0x1ffffffu, ((cur >> 25) & 7u) + 1u, inst);
             tmaxf = f32_up(best.t);
             cur = wide_pop(stack, sp, tmaxf);
         }
@@ -589,13 +592,19 @@ RT_DEV bool inst_box_hit(const Instance* ip, const Ray& r, double t_min, double 
 // world.hit restricted to the instances [i0, i1): the main world or one medium's boundary.
 // XF = false: the scene has no Translate / RotateY wrappers (every chain is empty): no ray transform going in,
 // no chain unwinding coming out
-template <bool COUNT, uint32_t PM = RT_PM_ALL, bool XF = true>
+// WIDE = true (main world only, t_min >= 0; the host built Instance::root4 for every instance of the range): the 4-wide walk
+template <bool COUNT, uint32_t PM = RT_PM_ALL, bool XF = true, bool WIDE = false>
 RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, const Ray& world_ray, double t_min, BestHit& best, TraceCounters* cnt) {
     for (uint32_t i = i0; i < i1; ++i) {
         const Instance* ip = &S.instances[i];
         Ray r = world_ray;
         if (XF) xform_ray(S.ops, __ldg(&ip->chain_off), __ldg(&ip->chain_len), r);
-        if (PM == 0x18u) trace_instance_spec<COUNT, PM>(S, i, r, t_min, best, cnt);
+        if (WIDE) {
+            unsigned long long wstack[RT_WIDE_STACK];
+            uint32_t cur = __ldg(&ip->root4);
+            int sp = 0;
+            trace_wide<PM, false, COUNT>(S, r, t_min, best, cur, sp, wstack, 0u, i, cnt);
+        } else if (PM == 0x18u) trace_instance_spec<COUNT, PM>(S, i, r, t_min, best, cnt);
         else trace_instance<COUNT, PM>(S, i, r, t_min, best, cnt);
     }
 }
@@ -771,12 +780,12 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
 
 // world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
 // surface (order independent because medium draws are keyed).
-template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true, uint32_t PM = RT_PM_ALL, bool XF = true>
+template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true, uint32_t PM = RT_PM_ALL, bool XF = true, bool WIDE = false>
 RT_DEV bool world_hit(const DeviceScene& S, const Ray& ray, double t_min, double t_max, bool media, uint64_t seed, uint64_t path_id, uint32_t segment,
                       HitRec& h, TraceCounters* cnt) {
     BestHit best;
     best_init(best, t_max);
-    trace_instances<COUNT, PM, XF>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
+    trace_instances<COUNT, PM, XF, WIDE>(S, 0, S.n_main_instances, ray, t_min, best, cnt);
     if (MEDIA) {
         double closest = best.t;
         int32_t mwin = -1;

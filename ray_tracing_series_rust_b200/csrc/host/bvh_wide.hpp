@@ -21,8 +21,7 @@
 namespace rtb {
 
 struct WideResult {
-    std::vector<float4> nodes; // 8 float4 per wide node
-    uint32_t root = RT_WIDE_EMPTY;
+    uint32_t root = RT_WIDE_EMPTY; // reference of the root in `out` (absolute wide-node index)
     int max_depth = 0;  // wide nodes on the longest root-to-leaf path
     bool ok = false;    // false: a leaf does not fit the reference encoding or the tree is too deep -> keep the binary walk
 };
@@ -43,30 +42,35 @@ inline bool leaf_ref(const BvhNode32& n, uint32_t& ref) {
 }
 } // namespace wide_detail
 
-// `root` = index of the binary root node (first node of its pair; the second is the empty dummy leaf)
-inline WideResult collapse_to_wide(const std::vector<BvhNode32>& bin, uint32_t root) {
+// `root` = index of the binary root node (first node of its pair; the second is the empty dummy leaf).  The wide nodes are
+// appended to `out` (8 float4 each; several instances share one array); on failure `out` is restored.
+inline WideResult collapse_to_wide(const std::vector<BvhNode32>& bin, uint32_t root, std::vector<float4>& out) {
     using namespace wide_detail;
     WideResult R;
     if (root >= bin.size()) return R;
+    const size_t out0 = out.size();
+    struct Restore { std::vector<float4>& v; size_t n; const bool& ok; ~Restore() { if (!ok) v.resize(n); } } restore{out, out0, R.ok};
+    const uint32_t base = (uint32_t)(out0 / 8);
     if (bin[root].count) { // the whole instance is one leaf: a wide node with one child
         uint32_t ref;
         if (!leaf_ref(bin[root], ref)) return R;
-        R.nodes.assign(8, make_float4(0.f, 0.f, 0.f, 0.f));
+        out.resize(out0 + 8, make_float4(0.f, 0.f, 0.f, 0.f));
+        float4* q1 = &out[out0];
         const BvhNode32& n = bin[root];
         const float big = 3.0e38f;
-        R.nodes[0] = make_float4(n.min[0], big, big, big); R.nodes[1] = make_float4(n.max[0], -big, -big, -big);
-        R.nodes[2] = make_float4(n.min[1], big, big, big); R.nodes[3] = make_float4(n.max[1], -big, -big, -big);
-        R.nodes[4] = make_float4(n.min[2], big, big, big); R.nodes[5] = make_float4(n.max[2], -big, -big, -big);
-        R.nodes[6] = make_float4(as_float(ref), as_float(RT_WIDE_EMPTY), as_float(RT_WIDE_EMPTY), as_float(RT_WIDE_EMPTY));
-        R.root = 0;
+        q1[0] = make_float4(n.min[0], big, big, big); q1[1] = make_float4(n.max[0], -big, -big, -big);
+        q1[2] = make_float4(n.min[1], big, big, big); q1[3] = make_float4(n.max[1], -big, -big, -big);
+        q1[4] = make_float4(n.min[2], big, big, big); q1[5] = make_float4(n.max[2], -big, -big, -big);
+        q1[6] = make_float4(as_float(ref), as_float(RT_WIDE_EMPTY), as_float(RT_WIDE_EMPTY), as_float(RT_WIDE_EMPTY));
+        R.root = base;
         R.max_depth = 1;
         R.ok = true;
         return R;
     }
     struct Item { uint32_t bin_node; uint32_t wide; int depth; };
     std::vector<Item> todo;
-    R.nodes.assign(8, make_float4(0.f, 0.f, 0.f, 0.f));
-    todo.push_back({root, 0u, 1});
+    out.resize(out0 + 8, make_float4(0.f, 0.f, 0.f, 0.f));
+    todo.push_back({root, base, 1});
     while (!todo.empty()) {
         const Item it = todo.back();
         todo.pop_back();
@@ -102,22 +106,22 @@ inline WideResult collapse_to_wide(const std::vector<BvhNode32>& bin, uint32_t r
                 if (!leaf_ref(c, ref[k])) return R;
                 if (ref[k] == RT_WIDE_EMPTY) continue;
             } else {
-                const size_t idx = R.nodes.size() / 8;
+                const size_t idx = out.size() / 8;
                 if (idx >= (1u << 31)) return R;
-                R.nodes.resize(R.nodes.size() + 8, make_float4(0.f, 0.f, 0.f, 0.f));
+                out.resize(out.size() + 8, make_float4(0.f, 0.f, 0.f, 0.f));
                 ref[k] = (uint32_t)idx;
                 todo.push_back({kids[k], (uint32_t)idx, it.depth + 1});
             }
             for (int a = 0; a < 3; ++a) { lo[a][k] = c.min[a]; hi[a][k] = c.max[a]; }
         }
-        float4* q = &R.nodes[8 * (size_t)it.wide];
+        float4* q = &out[8 * (size_t)it.wide];
         for (int a = 0; a < 3; ++a) {
             q[2 * a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
             q[2 * a + 1] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
         }
         q[6] = make_float4(as_float(ref[0]), as_float(ref[1]), as_float(ref[2]), as_float(ref[3]));
     }
-    R.root = 0;
+    R.root = base;
     R.ok = true;
     return R;
 }

@@ -582,7 +582,7 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
             in.root = br.root;
             in.chain_off = (uint32_t)ops.size();
             in.chain_len = (uint32_t)ib.chain.size();
-            in.pad_ = 0;
+            in.root4 = RT_WIDE_EMPTY;
             for (int a = 0; a < 3; ++a) { in.bmin[a] = nodes[br.root].min[a]; in.bmax[a] = nodes[br.root].max[a]; }
             ops.insert(ops.end(), ib.chain.begin(), ib.chain.end());
             instances.push_back(in);
@@ -705,19 +705,27 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
     }
 
     HF.n_main_instances = world_range[0].second - world_range[0].first;
-    // 4-wide collapse for the fused kernels: one wrapper-free main instance, no media (the conditions of their specialised
-    // variants).  Auto (measured on B200, tools/ab_wide.py): scenes of plain spheres (book-1 final +6 %) and large triangle
-    // meshes (871 200 triangles +20 %); not GravitySphere scenes (-2 %).  rt_scene_set_bvh_width(4) forces it where possible.
-    const bool wide_possible = HF.n_main_instances == 1 && media.empty() && instances[world_range[0].first].chain_len == 0;
+    // 4-wide collapse of the main world's trees (boundary worlds of media keep the pair walk: their queries start at t_min = -inf).
+    // Auto (measured on B200, tools/ab_wide.py): one wrapper-free instance without media that is plain spheres (book-1 final
+    // +6 %) or a large triangle mesh (871 200 triangles +20 %); not GravitySphere scenes (-2 %).  rt_scene_set_bvh_width(4)
+    // builds it for every main-world instance (the wavefront / generic kernels then walk it too: to be measured).
+    const bool single_plain = HF.n_main_instances == 1 && media.empty() && instances[world_range[0].first].chain_len == 0;
     const bool only_spheres = !spheres.empty() && movings.empty() && gravities.empty() && rects.empty() && boxes.empty() && tris.empty();
     const bool big_mesh = tris.size() >= 4096 && spheres.empty() && movings.empty() && gravities.empty() && boxes.empty();
-    if (wide_possible && (s->tuning.bvh_wide > 0 || (s->tuning.bvh_wide < 0 && (only_spheres || big_mesh)))) {
-        WideResult wr = collapse_to_wide(nodes, instances[world_range[0].first].root);
-        if (wr.ok) {
-            HF.nodes4.swap(wr.nodes);
-            HF.root4 = wr.root;
-            HF.wide_depth = wr.max_depth;
+    if (HF.n_main_instances > 0 && (s->tuning.bvh_wide > 0 || (s->tuning.bvh_wide < 0 && single_plain && (only_spheres || big_mesh)))) {
+        bool all_ok = true;
+        for (uint32_t i = world_range[0].first; i < world_range[0].second && all_ok; ++i) {
+            const WideResult wr = collapse_to_wide(nodes, instances[i].root, HF.nodes4);
+            all_ok = wr.ok;
+            instances[i].root4 = wr.root;
+            HF.wide_depth = std::max(HF.wide_depth, wr.max_depth);
         }
+        if (!all_ok) { // a tree too deep or a leaf that does not fit a reference: the whole scene stays on sibling pairs
+            HF.nodes4.clear();
+            for (Instance& in : instances) in.root4 = RT_WIDE_EMPTY;
+            HF.wide_depth = 0;
+        }
+        HF.root4 = instances[world_range[0].first].root4;
         pt.lap("4-wide collapse");
     }
     return RT_OK;

@@ -69,7 +69,7 @@ struct Instance {
     uint32_t root;      // node index of this instance's BVH root
     uint32_t chain_off; // into ops[]
     uint32_t chain_len;
-    uint32_t pad_;
+    uint32_t root4;     // reference of this instance's 4-wide root in DeviceScene::nodes4, RT_WIDE_EMPTY if it has none
     float bmin[3], bmax[3]; // padded bounds in the instance's own (innermost) space
 };
 
@@ -134,11 +134,11 @@ struct DeviceScene {
     // is box0 + s * delta with s = (t - motion_t0) * motion_inv_dt: exact for the reference's linear motion (hit.rs:275-278), so the
     // spheres-and-moving-spheres kernels walk tight boxes instead of the union over the shutter that `nodes` holds (hit.rs:317-327).
     const BvhNode32* mnodes;
-    // 4-wide collapse of the main instance's tree (nullptr unless built: single wrapper-free instance, see RT_WIDE_EMPTY above)
+    // 4-wide collapse of the main world's trees (nullptr unless built, see RT_WIDE_EMPTY above); per instance: Instance::root4
     const float4* nodes4;
     double motion_t0, motion_inv_dt;
     uint32_t prim_mask; // bit t set: primitives of PrimType t exist
-    uint32_t root4;     // reference of the 4-wide root (valid when nodes4 != nullptr)
+    uint32_t root4;     // = instances[0].root4, for the single-instance fused kernels (valid when nodes4 != nullptr)
     uint32_t n_main_instances;
     uint32_t n_media;
     uint32_t n_prims;

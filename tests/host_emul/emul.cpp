@@ -33,13 +33,23 @@ extern "C" {
 
 uint64_t emul_sizeof_device_scene(void) { return sizeof(DeviceScene); }
 
-int32_t emul_trace_batch(const void* scene, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t flags, uint64_t seed, rt_hit* out) {
+// wide != 0: the main world through Instance::root4 (world_hit<..., WIDE = true>, what k_extend<..., WIDE> runs); needs t_min >= 0.
+// counts (may be null): [0] boxes tested, [1] primitives tested, summed over the batch
+int32_t emul_trace_batch(const void* scene, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t flags, uint64_t seed, int32_t wide,
+                         rt_hit* out, uint64_t* counts) {
     const DeviceScene& S = *static_cast<const DeviceScene*>(scene);
+    if (wide && (!S.nodes4 || !(t_min >= 0.0))) return -1;
+    uint64_t nodes = 0, prims = 0;
     for (int64_t i = 0; i < n; ++i) {
         HitRec h;
-        const bool hit = world_hit<false, 1, true>(S, load_ray(rays[i]), t_min, t_max, (flags & RT_TRACE_SEEDED_MEDIA) != 0, seed, (uint64_t)i, 0u, h, nullptr);
+        TraceCounters tc; tc.nodes = 0; tc.prims = 0;
+        const bool media = (flags & RT_TRACE_SEEDED_MEDIA) != 0;
+        const bool hit = wide ? world_hit<true, 1, true, true, RT_PM_ALL, true, true>(S, load_ray(rays[i]), t_min, t_max, media, seed, (uint64_t)i, 0u, h, &tc)
+                              : world_hit<true, 1, true>(S, load_ray(rays[i]), t_min, t_max, media, seed, (uint64_t)i, 0u, h, &tc);
+        nodes += tc.nodes; prims += tc.prims;
         store_hit(out[i], hit, h);
     }
+    if (counts) { counts[0] = nodes; counts[1] = prims; }
     return 0;
 }
 

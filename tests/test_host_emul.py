@@ -34,7 +34,7 @@ def emul():
     lib = C.CDLL(so)
     lib.emul_sizeof_device_scene.restype = C.c_uint64
     lib.emul_trace_batch.restype = C.c_int32
-    lib.emul_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_uint64, C.c_void_p]
+    lib.emul_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.emul_trace_wide.restype = C.c_int32
     lib.emul_trace_wide.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p]
     if not os.path.exists(rtb.LIB_PATH):
@@ -49,10 +49,13 @@ def host_scene(emul, scene_id, seed=0xB001, param=0, width=2):
     return s, s.debug_host_scene(emul.emul_sizeof_device_scene())
 
 
-def emul_trace(emul, dscene, rays, t_min=0.001, t_max=float("inf"), flags=capi.RT_TRACE_SKIP_MEDIA, seed=0):
+def emul_trace(emul, dscene, rays, t_min=0.001, t_max=float("inf"), flags=capi.RT_TRACE_SKIP_MEDIA, seed=0, wide=0, counts=None):
     rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
     out = np.zeros(rays.shape[0], dtype=capi.HIT_DTYPE)
-    assert emul.emul_trace_batch(dscene, rays.ctypes.data, rays.shape[0], t_min, t_max, flags, seed, out.ctypes.data) == 0
+    cnt = (C.c_uint64 * 2)()
+    assert emul.emul_trace_batch(dscene, rays.ctypes.data, rays.shape[0], t_min, t_max, flags, seed, wide, out.ctypes.data, cnt) == 0
+    if counts is not None:
+        counts.update(boxes=int(cnt[0]), prims=int(cnt[1]))
     return out
 
 
@@ -125,11 +128,34 @@ def test_wide_walk_equals_pair_walk(orc, emul, scene_id, param):
         x.close()
 
 
-def test_wide_collapse_is_skipped_where_the_kernel_cannot_use_it(emul):
+@pytest.mark.parametrize("scene_id", [4, 5, 6, 8, 13, 14, 99])
+def test_wide_world_hit_equals_pair_world_hit(orc, emul, scene_id):
+    """world_hit<..., WIDE> (what k_extend<..., WIDE> runs when rt_scene_set_bvh_width(4) forces it): every main-world instance
+    through its own 4-wide root, wrappers and media (pair-walked boundaries, seeded draws) included: identical hit records."""
+    param = 32 if scene_id == 14 else 0
+    s2, d2 = host_scene(emul, scene_id, param=param, width=2)
+    s4, d4 = host_scene(emul, scene_id, param=param, width=4)
+    o = oracle_scene(orc, scene_id, param=param)
+    cam = pu.camera_fields(orc, o)
+    lo, hi = SCENES[scene_id][:2]
+    prim = pu.primary_rays(cam, 120, 68)
+    batches = [prim, pu.random_rays(15000, lo, hi, seed=5, time_range=(cam["time1"], cam["time2"])), pu.secondary_rays(o.trace_batch(prim), seed=3, time=cam["time1"])]
+    for rays in batches:
+        for flags in (capi.RT_TRACE_SKIP_MEDIA, capi.RT_TRACE_SEEDED_MEDIA):
+            c2, c4 = {}, {}
+            ref = emul_trace(emul, d2, rays, flags=flags, seed=17, counts=c2)
+            w = emul_trace(emul, d4, rays, flags=flags, seed=17, wide=1, counts=c4)
+            assert w.tobytes() == ref.tobytes(), (scene_id, flags, int((w["prim_id"] != ref["prim_id"]).sum()))
+            assert c4["prims"] <= c2["prims"]  # queued leaves behind closest_so_far are dropped
+    for x in (s2, s4, o):
+        x.close()
+
+
+def test_wide_collapse_is_built_only_where_asked_or_measured(emul):
     nbytes = emul.emul_sizeof_device_scene()
-    for scene_id in (5, 6):  # media / several instances: the resumable fused kernel never runs, no 4-wide tree is built
-        s, ds = host_scene(emul, scene_id, width=4)
-        assert emul.emul_trace_wide(ds, None, 0, 0.001, 1.0, 0, None) == -1
+    for scene_id, width, built in ((5, 0, False), (6, 0, False), (8, 0, False), (13, 0, True), (13, 2, False), (6, 4, True), (5, 4, True)):
+        s, ds = host_scene(emul, scene_id, width=width)
+        assert (emul.emul_trace_batch(ds, None, 0, 0.001, 1.0, 0, 0, 1, None, None) == 0) == built, (scene_id, width)
         s.close()
     s = rtb.new_scene()
     with pytest.raises(Exception):

@@ -51,9 +51,33 @@ def sweep():
     return 0
 
 
+def wave():
+    """NOT YET MEASURED (round-1 GPU budget ran out): the wavefront kernels k_extend<..., WIDE> on the media scenes, forced with
+    rt_scene_set_bvh_width(4).  CPU emulation (tests/test_host_emul.py): identical hits; book-2 final 12.9-15.2 pair fetches ->
+    6.2-6.9 wide fetches per segment, Cornell smoke 4.7-5.3 -> 2.0-2.3."""
+    ok = True
+    for name, sid, seed, W, spp_id, spp in (("cornell_smoke", 5, 0xB002, 600, 4, 200), ("book2_final", 6, 0xB002, 1000, 2, 50)):
+        acc = []
+        for width in (2, 4):
+            s, _ = scene(sid, seed, 0, width)
+            acc.append(s.render(capi.make_config(160, 1.0, spp_id, 50, seed=3), want_accum=True)[1])
+            s.close()
+        same = bool(np.array_equal(acc[0], acc[1]))
+        ok = ok and same
+        print(json.dumps({"identity": name, "bit_identical": same}), flush=True)
+        for width in (2, 4, 2, 4):
+            s, c = scene(sid, seed, 0, width)
+            s.render(capi.make_config(W, 1.0, 4, 50))
+            timed(s, W, 1.0, spp, f"{name} wavefront width {width} (commit {c * 1e3:.1f} ms)")
+            s.close()
+    return 0 if ok else 1
+
+
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "sweep":
         return sweep()
+    if len(sys.argv) > 1 and sys.argv[1] == "wave":
+        return wave()
     ok = True
     for name, sid, seed, param, W, aspect, spp, env in (
             ("mesh8k k_mega_r", 14, 0xB004, 64, 200, 1.0, 8, None),
