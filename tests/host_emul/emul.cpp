@@ -77,4 +77,58 @@ int32_t emul_trace_wide(const void* scene, const rt_ray* rays, int64_t n, double
     return 0;
 }
 
+// One path of k_mega / k_shade_all + k_extend, lane by lane: camera_first_ray -> (world_hit -> emitted / scatter)* -> fixed-point
+// accumulate (kernels.cu accumulate()).  Same device functions, same Philox streams as the kernels; wide != 0 walks Instance::root4.
+int32_t emul_render(const void* scene, int32_t W, int32_t H, int32_t spp_total, int32_t sample_begin, int32_t sample_end, int32_t max_depth, uint64_t seed,
+                    int32_t wide, int64_t* accum, uint64_t* segments_out) {
+    const DeviceScene& S = *static_cast<const DeviceScene*>(scene);
+    if (wide && !S.nodes4) return -1;
+    uint64_t segments = 0;
+    for (int32_t j = 0; j < H; ++j)
+        for (int32_t ii = 0; ii < W; ++ii)
+            for (int32_t sl = sample_begin; sl < sample_end; ++sl) {
+                const uint32_t pixel = (uint32_t)j * (uint32_t)W + (uint32_t)ii;
+                const uint64_t path_id = (uint64_t)pixel * (uint64_t)spp_total + (uint64_t)sl;
+                uint32_t draw = 0;
+                Ray r = camera_first_ray<PathRng>(S.cam, ii, j, W, H, seed, path_id, draw);
+                float tr = 1.f, tg = 1.f, tb = 1.f;
+                F3 contrib = mkf3(0.f, 0.f, 0.f);
+                for (uint32_t segment = 0;; ++segment) {
+                    HitRec h;
+                    const bool hit = wide ? world_hit<false, 2, true, true, RT_PM_ALL, true, true>(S, r, 0.001, RT_INF, true, seed, path_id, segment, h, nullptr)
+                                          : world_hit<false, 2, true>(S, r, 0.001, RT_INF, true, seed, path_id, segment, h, nullptr);
+                    ++segments;
+                    if (!hit) { contrib = mkf3(tr * S.background[0], tg * S.background[1], tb * S.background[2]); break; }
+                    const DMaterial m = S.materials[h.mat];
+                    if (m.type == MAT_LIGHT) {
+                        const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
+                        contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
+                        break;
+                    }
+                    PathRng g;
+                    g.init(seed, path_id, draw);
+                    D3 dir = mk3(0, 0, 0);
+                    F3 att = mkf3(0.f, 0.f, 0.f);
+                    bool scattered;
+                    if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                    else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
+                    else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
+                    else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                    if (!(scattered && (int32_t)(segment + 1) < max_depth)) break;
+                    tr *= att.x; tg *= att.y; tb *= att.z;
+                    r.o = h.p; r.d = dir;
+                    draw = g.draw;
+                }
+                const double v[3] = {(double)contrib.x, (double)contrib.y, (double)contrib.z};
+                for (int c = 0; c < 3; ++c) { // kernels.cu accumulate(): 2^32 fixed point, one sample clamped to [0, 2^20]
+                    double x = v[c];
+                    if (!(x > 0.0)) continue;
+                    x = x > 1048576.0 ? 1048576.0 : x;
+                    accum[(size_t)pixel * 3 + c] += (int64_t)(x * 4294967296.0 + 0.5);
+                }
+            }
+    if (segments_out) *segments_out = segments;
+    return 0;
+}
+
 } // extern "C"

@@ -37,6 +37,8 @@ def emul():
     lib.emul_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.emul_trace_wide.restype = C.c_int32
     lib.emul_trace_wide.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p]
+    lib.emul_render.restype = C.c_int32
+    lib.emul_render.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
     if not os.path.exists(rtb.LIB_PATH):
         rtb.build()
     return lib
@@ -163,3 +165,79 @@ def test_wide_collapse_is_built_only_where_asked_or_measured(emul):
     with pytest.raises(Exception):
         s.debug_host_scene(nbytes - 8)
     s.close()
+
+
+def test_wide_collapse_edge_cases(orc, emul, monkeypatch):
+    """Root that is a single leaf, two primitives, a degenerate (empty) world, leaves too large for a wide reference."""
+    nbytes = emul.emul_sizeof_device_scene()
+
+    def build(s, n):
+        m = s.lambertian((0.5, 0.5, 0.5))
+        objs = [s.sphere((2.5 * i, 0.3 * i, -1.0 * i), 1.0, m) for i in range(n)]
+        s.set_root(s.bvh(objs, 0, 1) if n else s.list([]))
+        s.set_camera((0, 1, 12), (0, 0, 0), (0, 1, 0), 40, 1.5, 0.0, 10, 0, 1)
+
+    for n in (1, 2, 3, 5, 9):
+        g, o = rtb.new_scene(), orc.new_scene()
+        build(g, n); build(o, n)
+        o.commit()
+        g.set_bvh_width(4)
+        ds = g.debug_host_scene(nbytes)
+        rays = np.concatenate([pu.random_rays(8000, -3.0, 3.0 * n, seed=n), pu.primary_rays(pu.camera_fields(orc, o), 150, 100)])
+        ho = o.trace_batch(rays)
+        assert (ho["prim_id"] >= 0).sum() > 100
+        pu.assert_parity(emul_trace(emul, ds, rays, wide=1), ho, f"{n} spheres wide")
+        assert emul_trace_wide(emul, ds, rays, 0).tobytes() == emul_trace(emul, ds, rays).tobytes()
+        g.close(); o.close()
+    g = rtb.new_scene()
+    build(g, 0)
+    g.set_bvh_width(4)
+    ds = g.debug_host_scene(nbytes)  # no instances: nothing to collapse, pair and wide entry both see an empty world
+    rays = pu.random_rays(16, -1.0, 1.0, seed=1)
+    assert (emul_trace(emul, ds, rays)["prim_id"] == -1).all()
+    g.close()
+    monkeypatch.setenv("RTB200_MAX_LEAF", "16")  # larger leaves: a leaf of > 8 primitives would not fit a wide reference (the scene then stays on pairs)
+    g = rtb.new_scene()
+    g.world_build(13, 0xB001, 0)
+    g.set_bvh_width(4)
+    ds = g.debug_host_scene(nbytes)
+    rays = pu.random_rays(6000, -15.0, 15.0, seed=2)
+    ref = emul_trace(emul, ds, rays)
+    if emul.emul_trace_batch(ds, None, 0, 0.001, 1.0, 0, 0, 1, None, None) == 0:
+        assert emul_trace(emul, ds, rays, wide=1).tobytes() == ref.tobytes()
+    assert (ref["prim_id"] >= 0).sum() > 500
+    g.close()
+
+
+def emul_render(emul, dscene, W, H, spp, depth, seed, wide=0, sample_begin=0, sample_end=None):
+    acc = np.zeros((H, W, 3), dtype=np.int64)
+    seg = C.c_uint64(0)
+    assert emul.emul_render(dscene, W, H, spp, sample_begin, spp if sample_end is None else sample_end, depth, seed, wide, acc.ctypes.data, C.byref(seg)) == 0
+    return acc, int(seg.value)
+
+
+@pytest.mark.parametrize("scene_id,W,aspect,spp", [(13, 60, 1.5, 6), (99, 60, 16 / 9, 6), (4, 40, 1.0, 8), (5, 40, 1.0, 8), (6, 40, 1.0, 6), (8, 60, 1.5, 4), (14, 40, 1.0, 6),
+                                                   (1, 40, 1.5, 4), (2, 40, 1.5, 4), (3, 40, 1.5, 6)])
+def test_device_path_loop_on_host_matches_the_oracle_sample_by_sample(orc, emul, scene_id, W, aspect, spp):
+    """E2 without a GPU: camera_first_ray, world_hit, every Material::scatter / Texture::value / Perlin and the fixed-point
+    accumulation of the DEVICE header, run path by path on the host with the kernels' Philox streams, against the oracle's
+    int64 sums (same bars as tests/test_gpu_parity.py::test_E2_render_matches_oracle_sample_by_sample)."""
+    param = 32 if scene_id == 14 else 0
+    s, ds = host_scene(emul, scene_id, param=param, width=4 if scene_id in (6, 13) else 2)
+    o = oracle_scene(orc, scene_id, param=param)
+    cfg = capi.make_config(W, aspect, spp, 50, seed=21)
+    so, ao, sto = o.render(cfg, want_accum=True)
+    H = ao.shape[0]
+    ae, seg = emul_render(emul, ds, W, H, spp, 50, 21, wide=1 if scene_id in (6, 13) else 0)
+    fe, fo = ae / capi.ACCUM_SCALE, ao / capi.ACCUM_SCALE
+    rel = np.abs(fe - fo) / np.maximum(1e-3, np.abs(fo))
+    pix_bad = (rel > 1e-5).any(axis=2)
+    assert pix_bad.mean() < 0.02, (pix_bad.mean(), seg, sto["segments"])
+    assert abs(fe.mean() - fo.mean()) <= 0.01 * max(fo.mean(), 1e-3)
+    assert abs(seg - sto["segments"]) <= 0.005 * sto["segments"]
+    # sample ranges add up exactly (integer sums, streams keyed by the global sample index): the sharding contract
+    a0, _ = emul_render(emul, ds, W, H, spp, 50, 21, wide=1 if scene_id in (6, 13) else 0, sample_begin=0, sample_end=spp // 2)
+    a1, _ = emul_render(emul, ds, W, H, spp, 50, 21, wide=1 if scene_id in (6, 13) else 0, sample_begin=spp // 2, sample_end=spp)
+    assert np.array_equal(a0 + a1, ae)
+    s.close()
+    o.close()
