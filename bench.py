@@ -372,12 +372,16 @@ def main():
         "kernel_share_of_step": ext_share,
         "note": "the scene (<64 KB) is L1/L2 resident, so DRAM traffic is far below the algorithmic bytes; the kernel is issue/latency bound, see profiles/",
     }
-    if fused and sid in (13, 14):
+    try:
+        wide = fused and scene.bvh_width() == 4
+    except Exception:
+        wide = False
+    if wide:
+        # the counting pass walks the same 4-wide collapse as the timed fused kernel (kernels.cu count_wide): box_tests = 4 per node
+        # visited, so 32 B x box_tests = 128 B per visit = the bytes of the nodes the kernel fetches
         roofline["kernel"] = ("k_mega" if sid == 13 else "k_mega_r (resumable)") + " (fused persistent: generate + world.hit + scatter; 4-wide BVH walk)"
-        roofline["note"] += ("; the box / primitive counts come from the counting wavefront pass, which walks sibling pairs (32 B per box): the fused kernel walks the "
-                             "4-wide collapse of the same tree (128 B per visit; host emulation on camera + bounce rays: book-1 4.6-4.9 visits = 590-630 B instead of "
-                             "23.9 boxes = 765 B per segment, 871k mesh 13.5-16.6 visits instead of 30.7-35.8 pair fetches) and culls queued leaves, so `achieved` "
-                             "overstates the bytes this kernel touches by up to ~25 %")
+        roofline["bytes_per_segment_source"] = "device event counters on the 4-wide tree the kernel walks: node visits x 128 B (= boxes tested x 32 B) + primitive tests x B_type"
+        roofline["wide_node_visits_per_segment"] = st_c["box_tests"] / own_seg / 4.0
     if fused and sid == 99:
         roofline["note"] += "; the box / primitive counts come from the counting wavefront pass, which walks union-over-the-shutter boxes: the fused kernel walks motion-interpolated boxes and tests fewer, so `achieved` is an upper bound for this workload"
     if algo:

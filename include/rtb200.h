@@ -325,6 +325,8 @@ RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder);
  * 0 (default): 4 where it measured faster (plain-sphere scenes, meshes of >= 4096 triangles), else 2.
  * Results are identical (closest hit is topology independent). */
 RTB_EXPORT int32_t rt_scene_set_bvh_width(rt_scene* s, int32_t width);
+/* 4 if the last rt_scene_commit built the 4-wide collapse (the fused kernels then walk it), else 2; < 0 if not committed. */
+RTB_EXPORT int32_t rt_scene_bvh_width(rt_scene* s);
 /* Host-only self check of the flattener and BVH builder (needs no GPU): out[0] nodes, [1] max depth,
  * [2] main instances, [3] instances, [4] media, [5..10] primitives per rt_prim_type, [11] leaves,
  * [12] invariant violations (0 = valid), [13] numbered prims, [14] bytes the last commit uploaded,

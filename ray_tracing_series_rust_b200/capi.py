@@ -315,6 +315,12 @@ class Scene:
         fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32]
         return self._c(fn(self.h, int(width)))
 
+    def bvh_width(self) -> int:
+        """rt_scene_bvh_width: 4 if the committed scene carries the 4-wide collapse, else 2."""
+        fn = self.api.lib.rt_scene_bvh_width
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p]
+        return self._c(fn(self.h))
+
     def debug_host_scene(self, nbytes: int):
         """rt_debug_host_scene: the host-flattened DeviceScene as raw bytes (pointers address host arrays owned by the scene).
         Test hook for tests/host_emul; `nbytes` must equal sizeof(DeviceScene)."""

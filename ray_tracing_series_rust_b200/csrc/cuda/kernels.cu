@@ -948,8 +948,12 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         const int ext_occ = ((media && !media_specialised) || tune.count_events) ? 4 : 5;
         // measured (profiles/): the warp-scheduled persistent kernel wins on deep triangle BVHs (+22 % on the 871k mesh),
         // the one-ray-per-thread kernel on small scenes and on scenes with media
-        const int ext_kind = tune.extend_kind >= 0 ? tune.extend_kind : ((!media && (scene.flags & 4u)) ? 1 : 0);
-        const bool ext_wide = scene.nodes4 != nullptr && tune.bvh_wide > 0; // wavefront: only when forced (unmeasured)
+        const int ext_kind_auto = tune.extend_kind >= 0 ? tune.extend_kind : ((!media && (scene.flags & 4u)) ? 1 : 0);
+        // wavefront kernels walk the 4-wide collapse only when it was forced (unmeasured for them) - and in the counting pass of a
+        // scene whose fused kernel walks it, so that the device counters describe the tree the timed kernel walks (4 boxes per visit)
+        const bool count_wide = tune.count_events && !media && scene.nodes4 != nullptr && tune.bvh_wide != 0;
+        const bool ext_wide = (scene.nodes4 != nullptr && tune.bvh_wide > 0) || count_wide;
+        const int ext_kind = count_wide ? 0 : ext_kind_auto; // k_extend_p has no wide form
         const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, ext_occ) * (uint32_t)std::max(1, tune.extend_waves));
         CK(cudaEventRecord(w->ev_begin, stream));
         // RT_MODE_AUTO (measured on B200, profiles/README.md): the fused persistent kernel wins where shading is cheap

@@ -1380,6 +1380,12 @@ RTB_EXPORT int32_t rt_scene_set_bvh_width(rt_scene* s, int32_t width) {
     return RT_OK;
 }
 
+RTB_EXPORT int32_t rt_scene_bvh_width(rt_scene* s) {
+    CHECK_SCENE(s);
+    if (!s->committed || !s->dev.valid) return fail(RT_ERR_STATE, "scene not committed");
+    return s->dev.scene.nodes4 ? 4 : 2;
+}
+
 RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots) {
     CHECK_SCENE(s);
     if (wave_slots) s->tuning.wave_slots = wave_slots < 128 ? 128 : wave_slots;

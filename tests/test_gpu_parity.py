@@ -395,6 +395,20 @@ def test_wide_bvh_walk_is_bit_identical_to_the_pair_walk(orc, scene_id, param, e
         assert st["iterations"] == 1  # fused mode
         g.close()
     assert np.array_equal(acc[2], acc[4]) and np.array_equal(acc[2], acc[0]) and segs[2] == segs[4] == segs[0]
+    if scene_id == 13 and env is None:
+        # the counting pass (RT_RENDER_COUNT_EVENTS, bench.py's roofline) walks the tree the fused kernel walks: 4 boxes per visit
+        g = rtb.new_scene()
+        g.world_build(scene_id, 0xB001, param)
+        g.commit()
+        assert g.bvh_width() == 4
+        _, a_cnt, st_cnt = g.render(capi.make_config(96, aspect, 6, 50, seed=9, flags=2), want_accum=True)
+        assert np.array_equal(a_cnt, acc[2]) and st_cnt["box_tests"] % 4 == 0 and 0 < st_cnt["box_tests"] < 40 * st_cnt["segments"]
+        g.set_bvh_width(2)
+        g.commit()
+        assert g.bvh_width() == 2
+        _, _, st_pairs = g.render(capi.make_config(96, aspect, 6, 50, seed=9, flags=2), want_accum=True)
+        assert st_cnt["prim_tests"][0] <= st_pairs["prim_tests"][0]  # queued leaves behind closest_so_far are dropped
+        g.close()
     o = orc.new_scene()
     o.world_build(scene_id, 0xB001, param)
     o.commit()
