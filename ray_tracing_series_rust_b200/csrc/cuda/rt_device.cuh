@@ -560,10 +560,21 @@ RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit
             unsigned long long k1 = wide_key(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
             unsigned long long k2 = wide_key(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);
             unsigned long long k3 = wide_key(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, rf.w, f, tminf, tmaxf);
+#ifdef RT_WIDE_NEAREST_ONLY // experiment (make EXTRA=-DRT_WIDE_NEAREST_ONLY, tools/ab_libs.sh): only the nearest child is found, the others are pushed unordered
+            wide_ce(k0, k1); wide_ce(k2, k3); wide_ce(k0, k2);
+#else
             wide_ce(k0, k1); wide_ce(k2, k3); wide_ce(k0, k2); wide_ce(k1, k3); wide_ce(k1, k2);
+#endif
             if (k3 != ~0ull) stack[sp++] = k3;
             if (k2 != ~0ull) stack[sp++] = k2;
             if (k1 != ~0ull) stack[sp++] = k1;
+#if defined(RT_WIDE_PREFETCH) && defined(__CUDA_ARCH__) // experiment: warm L1 with the node that is visited after the nearest child's subtree (1) / all queued nodes (2)
+            if (k1 != ~0ull && !((uint32_t)k1 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k1));
+#if RT_WIDE_PREFETCH > 1
+            if (k2 != ~0ull && !((uint32_t)k2 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k2));
+            if (k3 != ~0ull && !((uint32_t)k3 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k3));
+#endif
+#endif
             cur = (k0 != ~0ull) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
         }
         if (cur != DONE) { // a leaf reference

@@ -22,14 +22,13 @@ HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def emul():
-    so = os.path.join(HERE, "libemul.so")
+def _build_emul(name, extra=()):
+    so = os.path.join(HERE, name)
     srcs = [os.path.join(HERE, "emul.cpp"), os.path.join(HERE, "cuda_shim.h"),
             os.path.join(ROOT, "ray_tracing_series_rust_b200", "csrc", "cuda", "rt_device.cuh"),
             os.path.join(ROOT, "ray_tracing_series_rust_b200", "csrc", "rt_types.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas", *extra,
                                "-I/usr/local/cuda/include", srcs[0], "-o", so])
     lib = C.CDLL(so)
     lib.emul_sizeof_device_scene.restype = C.c_uint64
@@ -42,6 +41,11 @@ def emul():
     if not os.path.exists(rtb.LIB_PATH):
         rtb.build()
     return lib
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return _build_emul("libemul.so")
 
 
 def host_scene(emul, scene_id, seed=0xB001, param=0, width=2):
@@ -241,3 +245,21 @@ def test_device_path_loop_on_host_matches_the_oracle_sample_by_sample(orc, emul,
     assert np.array_equal(a0 + a1, ae)
     s.close()
     o.close()
+
+
+def test_compile_time_walk_experiments_keep_the_result(orc):
+    """The -D variants of trace_wide kept for A/B on the GPU (tools/ab_libs.sh) return the same hits: nearest child only +
+    unordered pushes (RT_WIDE_NEAREST_ONLY); the prefetch variant only adds prefetch instructions on the device."""
+    alt = _build_emul("libemul_nearest.so", ("-DRT_WIDE_NEAREST_ONLY", "-DRT_WIDE_PREFETCH=2"))
+    ref = _build_emul("libemul.so")
+    for scene_id, param in ((13, 0), (14, 48), (6, 0)):
+        s4, d4 = host_scene(ref, scene_id, param=param, width=4)
+        o = oracle_scene(orc, scene_id, param=param)
+        cam = pu.camera_fields(orc, o)
+        lo, hi = SCENES[scene_id][:2]
+        for rays in (pu.primary_rays(cam, 100, 60), pu.random_rays(10000, lo, hi, seed=4, time_range=(cam["time1"], cam["time2"]))):
+            a = emul_trace(alt, d4, rays, wide=1)
+            b = emul_trace(ref, d4, rays, wide=1)
+            assert a.tobytes() == b.tobytes() and (a["prim_id"] >= 0).sum() > 100
+        s4.close()
+        o.close()
