@@ -111,7 +111,7 @@ def test_device_functions_on_host_match_the_oracle(orc, emul, scene_id):
     o.close()
 
 
-@pytest.mark.parametrize("scene_id,param", [(14, 32), (14, 96), (13, 0), (10, 0)])
+@pytest.mark.parametrize("scene_id,param", [(14, 32), (14, 96), (14, 260), (13, 0), (10, 0)])  # 14/260: 135 200 triangles, the parallel collapse
 def test_wide_walk_equals_pair_walk(orc, emul, scene_id, param):
     """The 4-wide collapse (bvh_wide.hpp) + trace_wide return the SAME hit records, bit for bit, as the sibling-pair walk:
     closest hit is topology independent and exact ties are decided by depth-first id, not by visiting order."""
