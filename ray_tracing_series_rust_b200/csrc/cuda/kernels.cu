@@ -66,6 +66,7 @@ struct JobDev {
     uint32_t wait_thresh; // k_mega_r: finished lanes that end a traversal round
     uint32_t tile_rank, tile_count; // RT_RENDER_TILE_SHARD: npix_rendered counts this shard's pixels only
     uint32_t chunk;                 // fused kernels: consecutive path indices a warp claims per atomic
+    uint32_t tile_order;            // 1: path indices enumerate the pixels tile by tile (tile_order_pixel), single-shard renders only
 };
 
 // Path-state chunks are streamed (read once / written once per kernel): evict-first hints keep them from
@@ -131,7 +132,7 @@ __global__ void k_init(PathState P, Queues Q, uint32_t n) {
 // Tile sharding: the shard's pixels are enumerated densely (local row lr = band lr / 4 of this rank, line lr % 4);
 // the global pixel index (accumulator address, Philox path id) is that of the unsharded image.
 RT_DEV uint32_t shard_pixel(const JobDev& J, uint32_t q) {
-    if (J.tile_count <= 1u) return q;
+    if (J.tile_count <= 1u) return J.tile_order ? tile_order_pixel(q, (uint32_t)J.W, (uint32_t)J.rows) : q;
     const uint32_t W = (uint32_t)J.W, lr = q / W, x = q - lr * W;
     const uint32_t band = (lr / RT_TILE_ROWS) * J.tile_count + J.tile_rank;
     return (band * RT_TILE_ROWS + lr % RT_TILE_ROWS) * W + x;
@@ -923,6 +924,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
     J.total_paths = (unsigned long long)J.npix_rendered * (unsigned long long)(job.sample_end - job.sample_begin);
     J.seed = job.seed;
     J.count_events = tune.count_events;
+    J.tile_order = (tune.tile_order > 0 && J.tile_count <= 1u) ? 1u : 0u;
     uint32_t N = tune.wave_slots;
     if ((unsigned long long)N > J.total_paths) N = (uint32_t)std::max<unsigned long long>(J.total_paths, 1ull);
     N = (N + 127u) & ~127u;

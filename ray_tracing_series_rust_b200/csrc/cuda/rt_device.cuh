@@ -620,6 +620,30 @@ RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, cons
     }
 }
 
+// ------------------------------------------------------------------ path index -> pixel, tile order (experiment, RTB200_TILE_ORDER=1)
+// The default enumerates the rendered pixels row by row, so the ~100 consecutive path indices a warp works on at any time are a
+// 100 x 1 strip of one sample; in tile order they fall into one 32 x 16 tile (bands of 16 rows, cut into 32-pixel columns, a narrower
+// last column, a lower last band): a bijection of [0, W * rows) onto itself.  Path ids (Philox streams) are keyed by the pixel, so the
+// image does not depend on the order.
+RT_DEV uint32_t tile_order_pixel(uint32_t p, uint32_t W, uint32_t rows) {
+    const uint32_t TW = 32u, TH = 16u;
+    const uint32_t y0 = (p / (W * TH)) * TH;
+    const uint32_t hb = rows - y0 < TH ? rows - y0 : TH;
+    const uint32_t q = p - y0 * W; // inside the band: [0, hb * W)
+    const uint32_t wfull = (W / TW) * TW, full = wfull * hb;
+    uint32_t x, y;
+    if (q < full) {
+        const uint32_t tx = q / (TW * hb), r = q - tx * TW * hb;
+        y = r / TW;
+        x = tx * TW + (r - y * TW);
+    } else {
+        const uint32_t rw = W - wfull, r = q - full;
+        y = r / rw;
+        x = wfull + (r - y * rw);
+    }
+    return (y0 + y) * W + x;
+}
+
 // ------------------------------------------------------------------ hit record (hit.rs:9-18)
 struct HitRec {
     D3 p, n;

@@ -813,6 +813,7 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_BVH_DEVICE_MIN"))) s->tuning.bvh_device_min = std::atoi(e);
     if ((e = std::getenv("RTB200_BVH_WIDE"))) s->tuning.bvh_wide = std::atoi(e);
     if ((e = std::getenv("RTB200_WIDE_OCC"))) s->tuning.wide_occ = std::atoi(e);
+    if ((e = std::getenv("RTB200_TILE_ORDER"))) s->tuning.tile_order = std::atoi(e);
     return s;
 }
 void rt_scene_destroy(rt_scene* s) { delete s; }

@@ -263,3 +263,16 @@ def test_compile_time_walk_experiments_keep_the_result(orc):
             assert a.tobytes() == b.tobytes() and (a["prim_id"] >= 0).sum() > 100
         s4.close()
         o.close()
+
+
+def test_tile_order_is_a_bijection_of_the_pixels(emul):
+    """RTB200_TILE_ORDER=1 (experiment): path indices enumerate 32 x 16 tiles; every pixel exactly once, for any image shape;
+    the first 512 indices of an aligned image are one tile."""
+    for W, rows in ((800, 533), (600, 600), (1000, 1000), (31, 7), (32, 16), (33, 17), (1, 1), (5, 40), (64, 15), (95, 33)):
+        out = np.zeros(W * rows, dtype=np.uint32)
+        emul.emul_tile_order(C.c_uint32(W), C.c_uint32(rows), out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(np.sort(out), np.arange(W * rows, dtype=np.uint32)), (W, rows)
+    out = np.zeros(800 * 533, dtype=np.uint32)
+    emul.emul_tile_order(C.c_uint32(800), C.c_uint32(533), out.ctypes.data_as(C.c_void_p))
+    ys, xs = out[:512] // 800, out[:512] % 800
+    assert ys.max() == 15 and xs.max() == 31 and list(out[:3]) == [0, 1, 2] and out[32] == 800
