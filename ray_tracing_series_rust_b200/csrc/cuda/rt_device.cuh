@@ -548,13 +548,31 @@ RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit
     const float tminf = fmaxf(f32_down(t_min), 0.f);
     float tmaxf = f32_up(best.t);
     const float4* __restrict__ nodes4 = S.nodes4;
+    // spheres + moving spheres: motion-interpolated child boxes (DeviceScene::mnodes4), as trace_instance does with mnodes
+    const float4* __restrict__ mnodes4 = S.mnodes4;
+    const bool MOTION = PM == 0x3u && mnodes4 != nullptr;
+    float ms = 0.f;
+    if (MOTION) { const double sd = (r.time - S.motion_t0) * S.motion_inv_dt; ms = (float)(sd < 0.0 ? 0.0 : (sd > 1.0 ? 1.0 : sd)); }
     const uint32_t DONE = 0xffffffffu;
     uint32_t n0 = 0;
     if (RESUME) n0 = __popc(__ballot_sync(full, cur != DONE));
     for (;;) {
         while (cur != DONE && !(cur & RT_LEAF_FLAG)) {
-            const float4* __restrict__ q = nodes4 + 8 * (size_t)cur;
-            const float4 lx = __ldg(q), hx = __ldg(q + 1), ly = __ldg(q + 2), hy = __ldg(q + 3), lz = __ldg(q + 4), hz = __ldg(q + 5), rf = __ldg(q + 6);
+            float4 lx, hx, ly, hy, lz, hz, rf;
+            if (MOTION) { // box(t) = box at the shutter's start + s * delta: 256 bytes per node
+                const float4* __restrict__ q = mnodes4 + 16 * (size_t)cur;
+                lx = __ldg(q); hx = __ldg(q + 1); ly = __ldg(q + 2); hy = __ldg(q + 3); lz = __ldg(q + 4); hz = __ldg(q + 5); rf = __ldg(q + 6);
+                const float4 dlx = __ldg(q + 8), dhx = __ldg(q + 9), dly = __ldg(q + 10), dhy = __ldg(q + 11), dlz = __ldg(q + 12), dhz = __ldg(q + 13);
+                lx.x = fmaf(dlx.x, ms, lx.x); lx.y = fmaf(dlx.y, ms, lx.y); lx.z = fmaf(dlx.z, ms, lx.z); lx.w = fmaf(dlx.w, ms, lx.w);
+                hx.x = fmaf(dhx.x, ms, hx.x); hx.y = fmaf(dhx.y, ms, hx.y); hx.z = fmaf(dhx.z, ms, hx.z); hx.w = fmaf(dhx.w, ms, hx.w);
+                ly.x = fmaf(dly.x, ms, ly.x); ly.y = fmaf(dly.y, ms, ly.y); ly.z = fmaf(dly.z, ms, ly.z); ly.w = fmaf(dly.w, ms, ly.w);
+                hy.x = fmaf(dhy.x, ms, hy.x); hy.y = fmaf(dhy.y, ms, hy.y); hy.z = fmaf(dhy.z, ms, hy.z); hy.w = fmaf(dhy.w, ms, hy.w);
+                lz.x = fmaf(dlz.x, ms, lz.x); lz.y = fmaf(dlz.y, ms, lz.y); lz.z = fmaf(dlz.z, ms, lz.z); lz.w = fmaf(dlz.w, ms, lz.w);
+                hz.x = fmaf(dhz.x, ms, hz.x); hz.y = fmaf(dhz.y, ms, hz.y); hz.z = fmaf(dhz.z, ms, hz.z); hz.w = fmaf(dhz.w, ms, hz.w);
+            } else {
+                const float4* __restrict__ q = nodes4 + 8 * (size_t)cur;
+                lx = __ldg(q); hx = __ldg(q + 1); ly = __ldg(q + 2); hy = __ldg(q + 3); lz = __ldg(q + 4); hz = __ldg(q + 5); rf = __ldg(q + 6);
+            }
             if (COUNT) cnt->nodes += 4;
             unsigned long long k0 = wide_key(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, rf.x, f, tminf, tmaxf);
             unsigned long long k1 = wide_key(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
@@ -569,7 +587,7 @@ RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit
             if (k2 != ~0ull) stack[sp++] = k2;
             if (k1 != ~0ull) stack[sp++] = k1;
 #if defined(RT_WIDE_PREFETCH) && defined(__CUDA_ARCH__) // experiment: warm L1 with the node that is visited after the nearest child's subtree (1) / all queued nodes (2)
-            if (k1 != ~0ull && !((uint32_t)k1 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k1));
+            if (k1 != ~0ull && !((uint32_t)k1 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(MOTION ? mnodes4 + 16 * (size_t)(uint32_t)k1 : nodes4 + 8 * (size_t)(uint32_t)k1));
 #if RT_WIDE_PREFETCH > 1
             if (k2 != ~0ull && !((uint32_t)k2 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k2));
             if (k3 != ~0ull && !((uint32_t)k3 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k3));

@@ -112,6 +112,9 @@ inline bool collapse_range(const std::vector<BvhNode32>& bin, uint32_t bin_root,
             q[2 * a + 1] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
         }
         q[6] = make_float4(as_float(ref[0]), as_float(ref[1]), as_float(ref[2]), as_float(ref[3]));
+        uint32_t kid4[4] = {RT_WIDE_EMPTY, RT_WIDE_EMPTY, RT_WIDE_EMPTY, RT_WIDE_EMPTY}; // binary node behind every slot (for build_motion_wide)
+        for (int k = 0; k < nk; ++k) kid4[k] = kids[k];
+        std::memcpy(&q[7], kid4, 16);
     }
     return true;
 }
@@ -137,6 +140,8 @@ inline WideResult collapse_to_wide(const std::vector<BvhNode32>& bin, uint32_t r
         q1[2] = make_float4(n.min[1], big, big, big); q1[3] = make_float4(n.max[1], -big, -big, -big);
         q1[4] = make_float4(n.min[2], big, big, big); q1[5] = make_float4(n.max[2], -big, -big, -big);
         q1[6] = make_float4(as_float(ref), as_float(RT_WIDE_EMPTY), as_float(RT_WIDE_EMPTY), as_float(RT_WIDE_EMPTY));
+        const uint32_t kid4[4] = {root, RT_WIDE_EMPTY, RT_WIDE_EMPTY, RT_WIDE_EMPTY};
+        std::memcpy(&q1[7], kid4, 16);
         R.root = base;
         R.max_depth = 1;
         R.ok = true;
@@ -196,6 +201,34 @@ inline WideResult collapse_to_wide(const std::vector<BvhNode32>& bin, uint32_t r
     R.root = base;
     R.ok = true;
     return R;
+}
+
+// Motion form of the wide nodes (DeviceScene::mnodes4) from the binary motion nodes (`mbin`: node i = box at the shutter's start
+// mbin[2i] and end-minus-start deltas mbin[2i + 1], scene.cpp): the same f32 values the pair walk interpolates, regrouped per wide node.
+inline void build_motion_wide(const std::vector<float4>& wide, const std::vector<BvhNode32>& mbin, std::vector<float4>& out) {
+    const size_t n = wide.size() / 8;
+    out.assign(16 * n, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (size_t w = 0; w < n; ++w) {
+        uint32_t kid4[4], ref4[4];
+        std::memcpy(kid4, &wide[8 * w + 7], 16);
+        std::memcpy(ref4, &wide[8 * w + 6], 16);
+        float rows[12][4];
+        for (int k = 0; k < 4; ++k) {
+            const bool used = kid4[k] != RT_WIDE_EMPTY && ref4[k] != RT_WIDE_EMPTY;
+            for (int a = 0; a < 3; ++a) {
+                rows[2 * a][k] = used ? mbin[2 * (size_t)kid4[k]].min[a] : 3.0e38f;
+                rows[2 * a + 1][k] = used ? mbin[2 * (size_t)kid4[k]].max[a] : -3.0e38f;
+                rows[6 + 2 * a][k] = used ? mbin[2 * (size_t)kid4[k] + 1].min[a] : 0.f;
+                rows[6 + 2 * a + 1][k] = used ? mbin[2 * (size_t)kid4[k] + 1].max[a] : 0.f;
+            }
+        }
+        float4* q = &out[16 * w];
+        for (int r = 0; r < 6; ++r) {
+            q[r] = make_float4(rows[r][0], rows[r][1], rows[r][2], rows[r][3]);
+            q[8 + r] = make_float4(rows[6 + r][0], rows[6 + r][1], rows[6 + r][2], rows[6 + r][3]);
+        }
+        q[6] = wide[8 * w + 6];
+    }
 }
 
 } // namespace rtb

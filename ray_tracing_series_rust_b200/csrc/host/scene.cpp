@@ -383,6 +383,7 @@ struct HostFlat {
     uint32_t n_main_instances = 0;
     int max_depth = 0;
     double pad = 0.0;
+    std::vector<float4> mnodes4;       // motion form of nodes4 (MovingSphere scenes with a 4-wide collapse)
     std::vector<float4> nodes4;        // 4-wide collapse of the single main instance's tree (tuning.bvh_wide), else empty
     uint32_t root4 = RT_WIDE_EMPTY;
     int wide_depth = 0;
@@ -726,6 +727,7 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
             HF.wide_depth = 0;
         }
         HF.root4 = instances[world_range[0].first].root4;
+        if (!HF.nodes4.empty() && !HF.mnodes.empty()) build_motion_wide(HF.nodes4, HF.mnodes, HF.mnodes4);
         pt.lap("4-wide collapse");
     }
     return RT_OK;
@@ -786,9 +788,10 @@ int32_t do_commit(rt_scene* s) {
     up.add(rects, D.rects); up.add(boxes, D.boxes); up.add(tris, D.tris);
     for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) up.add(meta[t], D.meta[t]);
     up.add(instances, D.instances); up.add(ops, D.ops); up.add(media, D.media); up.add(dmats, D.materials); up.add(dtex, D.textures);
-    up.add(perlin, D.perlin); up.add(texels, D.texels); up.add(HF.nodes4, D.nodes4);
+    up.add(perlin, D.perlin); up.add(texels, D.texels); up.add(HF.nodes4, D.nodes4); up.add(HF.mnodes4, D.mnodes4);
     if ((ce = up.run(s->dev)) != cudaSuccess) return fail_cuda(ce, "scene upload");
     if (HF.nodes4.empty()) D.nodes4 = nullptr;
+    if (HF.mnodes4.empty()) D.mnodes4 = nullptr;
     if (HF.mnodes.empty()) D.mnodes = nullptr;
     set_scene_scalars(s, HF, D);
     s->dev.valid = true;
@@ -1289,7 +1292,7 @@ RTB_EXPORT int32_t rt_debug_host_scene(rt_scene* s, void* out_scene, uint64_t ou
     HostFlat& HF = *hf;
     DeviceScene D;
     std::memset(&D, 0, sizeof D);
-    D.nodes = HF.nodes.data(); D.mnodes = HF.mnodes.empty() ? nullptr : HF.mnodes.data(); D.nodes4 = HF.nodes4.empty() ? nullptr : HF.nodes4.data();
+    D.nodes = HF.nodes.data(); D.mnodes = HF.mnodes.empty() ? nullptr : HF.mnodes.data(); D.nodes4 = HF.nodes4.empty() ? nullptr : HF.nodes4.data(); D.mnodes4 = HF.mnodes4.empty() ? nullptr : HF.mnodes4.data();
     D.spheres = HF.spheres.data(); D.movings = HF.movings.data(); D.gravities = HF.gravities.data(); D.gravity_table = HF.gtable.data();
     D.rects = HF.rects.data(); D.boxes = HF.boxes.data(); D.tris = HF.tris.data();
     for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) D.meta[t] = HF.meta[t].data();

@@ -25,7 +25,7 @@ namespace rtb {
 
 // 4-wide BVH node (128 bytes = one cache line, eight float4), the binary tree collapsed by surface area
 // (host/bvh_wide.hpp): q0 = lo.x of the four children, q1 = hi.x, q2 = lo.y, q3 = hi.y, q4 = lo.z, q5 = hi.z,
-// q6 = four child references, q7 unused.  A reference is the index of a 4-wide node (bit 31 clear), a leaf
+// q6 = four child references, q7 = the four binary child node indices (host bookkeeping, never read on the device).  A reference is the index of a 4-wide node (bit 31 clear), a leaf
 // RT_LEAF_FLAG | type << 28 | (n - 1) << 25 | first (n <= 8 primitives of one type, first < 2^25), or
 // RT_WIDE_EMPTY for an unused slot.  Half as many dependent fetches per ray as the sibling-pair walk.
 #define RT_WIDE_EMPTY 0xffffffffu
@@ -136,6 +136,9 @@ struct DeviceScene {
     const BvhNode32* mnodes;
     // 4-wide collapse of the main world's trees (nullptr unless built, see RT_WIDE_EMPTY above); per instance: Instance::root4
     const float4* nodes4;
+    // motion form of nodes4 for MovingSphere scenes (nullptr otherwise): 16 float4 per wide node = the six box rows of the children at the
+    // shutter's start, the references, one unused row, then the six rows of (box at the shutter's end - box at its start) and two unused rows
+    const float4* mnodes4;
     double motion_t0, motion_inv_dt;
     uint32_t prim_mask; // bit t set: primitives of PrimType t exist
     uint32_t root4;     // = instances[0].root4, for the single-instance fused kernels (valid when nodes4 != nullptr)

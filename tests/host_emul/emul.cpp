@@ -29,6 +29,28 @@ static Ray load_ray(const rt_ray& q) {
     return r;
 }
 
+// Closest hit through trace_wide as the fused kernels call it (single main instance).  pm3 != 0: the spheres + moving-spheres
+// instantiation, which walks the motion form of the wide nodes (DeviceScene::mnodes4) when the scene has it.
+template <uint32_t PM>
+static void wide_batch(const DeviceScene& S, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t resume, rt_hit* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        const Ray r = load_ray(rays[i]);
+        BestHit best;
+        best_init(best, t_max);
+        unsigned long long stack[RT_WIDE_STACK];
+        uint32_t cur = S.root4;
+        int sp = 0;
+        if (resume) { // one lane: every call returns after the lane finishes; wait_thresh 1 exercises the state hand-over
+            while (cur != 0xffffffffu) trace_wide<PM, true>(S, r, t_min, best, cur, sp, stack, 1u);
+        } else {
+            trace_wide<PM, false>(S, r, t_min, best, cur, sp, stack, 0u);
+        }
+        HitRec h;
+        const bool hit = best.type != RT_NONE;
+        if (hit) h = finalize_hit<1, PM, false>(S, r, best);
+        store_hit(out[i], hit, h);
+    }
+}
 extern "C" {
 
 uint64_t emul_sizeof_device_scene(void) { return sizeof(DeviceScene); }
@@ -57,26 +79,14 @@ int32_t emul_trace_batch(const void* scene, const rt_ray* rays, int64_t n, doubl
     return 0;
 }
 
-// stats[0] = wide nodes visited, [1] = leaves tested, [2] = deepest stack (only meaningful for resume_rounds == 0)
-int32_t emul_trace_wide(const void* scene, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t resume, rt_hit* out) {
+int32_t emul_trace_wide(const void* scene, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t resume, int32_t pm3, rt_hit* out) {
     const DeviceScene& S = *static_cast<const DeviceScene*>(scene);
     if (!S.nodes4) return -1;
-    for (int64_t i = 0; i < n; ++i) {
-        const Ray r = load_ray(rays[i]);
-        BestHit best;
-        best_init(best, t_max);
-        unsigned long long stack[RT_WIDE_STACK];
-        uint32_t cur = S.root4;
-        int sp = 0;
-        if (resume) { // one lane: every call returns after the lane finishes; wait_thresh 1 exercises the state hand-over
-            while (cur != 0xffffffffu) trace_wide<RT_PM_ALL, true>(S, r, t_min, best, cur, sp, stack, 1u);
-        } else {
-            trace_wide<RT_PM_ALL, false>(S, r, t_min, best, cur, sp, stack, 0u);
-        }
-        HitRec h;
-        const bool hit = best.type != RT_NONE;
-        if (hit) h = finalize_hit<1, RT_PM_ALL, false>(S, r, best);
-        store_hit(out[i], hit, h);
+    if (pm3) {
+        if (!S.mnodes4) return -2;
+        wide_batch<0x3u>(S, rays, n, t_min, t_max, resume, out);
+    } else {
+        wide_batch<RT_PM_ALL>(S, rays, n, t_min, t_max, resume, out);
     }
     return 0;
 }

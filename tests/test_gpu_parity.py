@@ -375,15 +375,17 @@ def test_device_lbvh_builder_parity(orc, scene_id, param, monkeypatch):
         g.set_bvh_builder(7)
 
 
-@pytest.mark.parametrize("scene_id,param,env", [(13, 0, None), (8, 0, None), (14, 64, None), (14, 64, {"RTB200_MEGA_WAIT": "0"}), (10, 0, None)])
+@pytest.mark.parametrize("scene_id,param,env", [(13, 0, None), (8, 0, None), (14, 64, None), (14, 64, {"RTB200_MEGA_WAIT": "0"}), (10, 0, None),
+                                                (99, 0, None), (7, 0, None)])
 def test_wide_bvh_walk_is_bit_identical_to_the_pair_walk(orc, scene_id, param, env, monkeypatch):
     # rt_scene_set_bvh_width: the 4-wide collapse (csrc/host/bvh_wide.hpp) walked by k_mega / k_mega_r (trace_wide) gives, bit for
     # bit, the image of the sibling-pair walk and the oracle's sums (closest hit is topology independent; ties by depth-first id).
-    # 14/64 = 8192 triangles: the resumable kernel; with RTB200_MEGA_WAIT=0 plain k_mega; 8 = GravitySpheres (wide only when forced)
+    # 14/64 = 8192 triangles: the resumable kernel; with RTB200_MEGA_WAIT=0 plain k_mega; 8 = GravitySpheres (wide only when forced);
+    # 99 / 7 = MovingSpheres: the motion form of the wide nodes (mnodes4), only when forced
     for k, v in (env or {}).items():
         monkeypatch.setenv(k, v)
     acc, segs = {}, {}
-    aspect = 1.0 if scene_id == 14 else 1.5
+    aspect = 1.0 if scene_id == 14 else (16 / 9 if scene_id == 99 else 1.5)
     cfg = capi.make_config(96, aspect, 6, 50, seed=9)
     for width in (2, 4, 0):
         g = rtb.new_scene()

@@ -35,7 +35,7 @@ def _build_emul(name, extra=()):
     lib.emul_trace_batch.restype = C.c_int32
     lib.emul_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.emul_trace_wide.restype = C.c_int32
-    lib.emul_trace_wide.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p]
+    lib.emul_trace_wide.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_void_p]
     lib.emul_render.restype = C.c_int32
     lib.emul_render.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
     if not os.path.exists(rtb.LIB_PATH):
@@ -65,10 +65,10 @@ def emul_trace(emul, dscene, rays, t_min=0.001, t_max=float("inf"), flags=capi.R
     return out
 
 
-def emul_trace_wide(emul, dscene, rays, resume, t_min=0.001, t_max=float("inf")):
+def emul_trace_wide(emul, dscene, rays, resume, t_min=0.001, t_max=float("inf"), pm3=0):
     rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
     out = np.zeros(rays.shape[0], dtype=capi.HIT_DTYPE)
-    assert emul.emul_trace_wide(dscene, rays.ctypes.data, rays.shape[0], t_min, t_max, resume, out.ctypes.data) == 0
+    assert emul.emul_trace_wide(dscene, rays.ctypes.data, rays.shape[0], t_min, t_max, resume, pm3, out.ctypes.data) == 0
     return out
 
 
@@ -276,3 +276,32 @@ def test_tile_order_is_a_bijection_of_the_pixels(emul):
     emul.emul_tile_order(C.c_uint32(800), C.c_uint32(533), out.ctypes.data_as(C.c_void_p))
     ys, xs = out[:512] // 800, out[:512] % 800
     assert ys.max() == 15 and xs.max() == 31 and list(out[:3]) == [0, 1, 2] and out[32] == 800
+
+
+@pytest.mark.parametrize("scene_id", [99, 7])
+def test_motion_form_of_the_wide_walk(orc, emul, scene_id):
+    """MovingSphere scenes (book-1 as shipped, the moving-sphere test scene): trace_wide<spheres + moving spheres> interpolates
+    the child boxes of DeviceScene::mnodes4 at the ray's time; hits equal the pair walk over union boxes, bit for bit, at
+    shutter start, end, in between and (clamped) outside."""
+    s2, d2 = host_scene(emul, scene_id, width=2)
+    s4, d4 = host_scene(emul, scene_id, width=4)
+    o = oracle_scene(orc, scene_id)
+    cam = pu.camera_fields(orc, o)
+    t1, t2 = cam["time1"], cam["time2"]
+    n_hits = 0
+    for time in (t1, t2, 0.5 * (t1 + t2), t1 + 0.123 * (t2 - t1)):
+        prim = pu.primary_rays(cam, 120, 68, time=time)
+        for rays in (prim, pu.secondary_rays(o.trace_batch(prim), seed=9, time=time)):
+            ref = emul_trace(emul, d2, rays)
+            pu.assert_parity(ref, o.trace_batch(rays), f"scene {scene_id} t={time}", require_hits=False)
+            for resume in (0, 1):
+                w = emul_trace_wide(emul, d4, rays, resume, pm3=1)
+                assert w.tobytes() == ref.tobytes(), (scene_id, time, resume, int((w["prim_id"] != ref["prim_id"]).sum()))
+            n_hits += int((ref["prim_id"] >= 0).sum())
+    rnd = pu.random_rays(8000, -15.0, 15.0, seed=6, time_range=(t1, t2))
+    assert emul_trace_wide(emul, d4, rnd, 0, pm3=1).tobytes() == emul_trace(emul, d2, rnd).tobytes()
+    assert n_hits > 5000
+    s13, d13 = host_scene(emul, 13, width=4)  # no moving spheres: no motion form
+    assert emul.emul_trace_wide(d13, None, 0, 0.001, 1.0, 0, 1, None) == -2
+    for x in (s2, s4, o, s13):
+        x.close()

@@ -73,7 +73,26 @@ def wave():
     return 0 if ok else 1
 
 
+def moving():
+    """NOT YET MEASURED: the motion form of the wide nodes (mnodes4) on book-1 as shipped (MovingSpheres), forced with width 4."""
+    acc = []
+    for width in (2, 4):
+        s, _ = scene(99, 0xB001, 0, width)
+        acc.append(s.render(capi.make_config(240, 16 / 9, 8, 50, seed=3), want_accum=True)[1])
+        s.close()
+    same = bool(np.array_equal(acc[0], acc[1]))
+    print(json.dumps({"identity": "book1_shipped", "bit_identical": same}), flush=True)
+    for width in (2, 4, 2, 4):
+        s, c = scene(99, 0xB001, 0, width)
+        s.render(capi.make_config(800, 1.5, 20, 50))
+        timed(s, 800, 1.5, 500, f"book1_shipped width {width} (commit {c * 1e3:.1f} ms)")
+        s.close()
+    return 0 if same else 1
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "moving":
+        return moving()
     if len(sys.argv) > 2 and sys.argv[1] == "sweep":
         return sweep()
     if len(sys.argv) > 1 and sys.argv[1] == "wave":
