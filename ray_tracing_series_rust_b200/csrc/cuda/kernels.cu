@@ -132,7 +132,11 @@ __global__ void k_init(PathState P, Queues Q, uint32_t n) {
 // Tile sharding: the shard's pixels are enumerated densely (local row lr = band lr / 4 of this rank, line lr % 4);
 // the global pixel index (accumulator address, Philox path id) is that of the unsharded image.
 RT_DEV uint32_t shard_pixel(const JobDev& J, uint32_t q) {
+#ifdef RT_TILE_ORDER // experiment (make EXTRA=-DRT_TILE_ORDER + RTB200_TILE_ORDER=1): compiled out of the default build, whose refill code is the measured one
     if (J.tile_count <= 1u) return J.tile_order ? tile_order_pixel(q, (uint32_t)J.W, (uint32_t)J.rows) : q;
+#else
+    if (J.tile_count <= 1u) return q;
+#endif
     const uint32_t W = (uint32_t)J.W, lr = q / W, x = q - lr * W;
     const uint32_t band = (lr / RT_TILE_ROWS) * J.tile_count + J.tile_rank;
     return (band * RT_TILE_ROWS + lr % RT_TILE_ROWS) * W + x;

@@ -35,7 +35,7 @@ struct RenderTuning {
     int prim_specialise = 2;        // 1: kernel variants compiled for the primitive types the scene contains; 2: also without wrapper handling for wrapper-free scenes; 0: generic
     int bvh_wide = -1;              // 4-wide collapse of a single wrapper-free instance's tree for the fused kernels: 1 build it where possible, 0 never, -1 auto (plain-sphere scenes and large meshes; RTB200_BVH_WIDE)
     int wide_occ = 7;               // resident CTAs per SM of the 4-wide k_mega_r (5, 6 or 7; RTB200_WIDE_OCC)
-    int tile_order = 0;             // 1: path indices enumerate pixels in 32 x 16 tiles instead of rows (RTB200_TILE_ORDER; unmeasured experiment, same image)
+    int tile_order = 0;             // 1: path indices enumerate pixels in 32 x 16 tiles instead of rows (RTB200_TILE_ORDER, builds with -DRT_TILE_ORDER only; unmeasured experiment, same image)
     int extend_waves = 4;           // k_extend grid = 148 SMs * resident CTAs * extend_waves blocks (grid-stride over the slots)
 };
 

@@ -638,7 +638,7 @@ RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, cons
     }
 }
 
-// ------------------------------------------------------------------ path index -> pixel, tile order (experiment, RTB200_TILE_ORDER=1)
+// ------------------------------------------------------------------ path index -> pixel, tile order (experiment: -DRT_TILE_ORDER builds, RTB200_TILE_ORDER=1)
 // The default enumerates the rendered pixels row by row, so the ~100 consecutive path indices a warp works on at any time are a
 // 100 x 1 strip of one sample; in tile order they fall into one 32 x 16 tile (bands of 16 rows, cut into 32-pixel columns, a narrower
 // last column, a lower last band): a bijection of [0, W * rows) onto itself.  Path ids (Philox streams) are keyed by the pixel, so the

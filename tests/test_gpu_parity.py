@@ -438,22 +438,6 @@ def test_wide_bvh_walk_in_the_wavefront_kernels(scene_id, flags):
     assert np.array_equal(acc[2], acc[4]) and acc[2].any()
 
 
-@pytest.mark.parametrize("scene_id,W,aspect,compat", [(13, 100, 1.5, 0), (13, 70, 1.5, 11), (5, 72, 1.0, 0), (14, 50, 1.0, 0)])
-def test_tile_order_experiment_renders_the_same_image(scene_id, W, aspect, compat, monkeypatch):
-    # RTB200_TILE_ORDER=1: path indices enumerate 32 x 16 pixel tiles instead of rows (tile_order_pixel, a bijection checked on the CPU
-    # in tests/test_host_emul.py); Philox streams are keyed by the pixel, so the image is the same bit for bit (fused and wavefront)
-    acc = []
-    for order in ("0", "1"):
-        monkeypatch.setenv("RTB200_TILE_ORDER", order)
-        g = rtb.new_scene()
-        g.world_build(scene_id, 0xB001, 64 if scene_id == 14 else 0)
-        g.commit()
-        _, a, st = g.render(capi.make_config(W, aspect, 5, 50, seed=15, compat_threads=compat), want_accum=True)
-        acc.append(a)
-        g.close()
-    assert np.array_equal(acc[0], acc[1]) and acc[0].any()
-
-
 def test_tile_sharding_is_bit_identical_and_matches_oracle(orc):
     # SURVEY.md 8(e) tile sharding: 4-row bands dealt round-robin; H = 53 (not a multiple of 4), 3 shards, both render modes
     from ray_tracing_series_rust_b200 import sharding
