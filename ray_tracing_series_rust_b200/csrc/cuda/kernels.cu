@@ -1002,7 +1002,8 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                     else k_mega_r<7, 0x28u, true><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
                 } else k_mega_r<7, 0x28u><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (wrapper_free && scene.nodes4 && tune.bvh_wide != 0 && scene.n_main_instances == 1 && (pm == 0x1u || pm == 0x3u || pm == 0x5u || pm == 0x28u)) {
-                if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                if (pm == 0x1u && tune.wide_occ == 6) k_mega<false, 6, false, 0x1u, false, true><<<148 * 6, 128, 0, stream>>>(scene, J, Q, d_accum); // RTB200_WIDE_OCC=6: unmeasured (80 registers)
+                else if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else if (pm == 0x3u) k_mega<false, 5, false, 0x3u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum); // motion form (mnodes4), forced only
                 else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega<false, 5, false, 0x28u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
