@@ -735,6 +735,9 @@ __global__ void k_resolve(const int64_t* __restrict__ accum, double* __restrict_
 }
 
 // ------------------------------------------------------------------ trace_batch (parity hook)
+// WIDE = true: the main world through its 4-wide collapse (scenes that carry one, t_min >= 0), so the parity hook checks the walk the
+// render kernels of such a scene use
+template <bool WIDE>
 __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ DeviceScene S, const rt_ray* __restrict__ rays, int64_t n, double t_min,
                                                      double t_max, int32_t flags, uint64_t seed, rt_hit* __restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -743,7 +746,7 @@ __global__ void __launch_bounds__(128) k_trace_batch(const __grid_constant__ Dev
         r.d = mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
         r.time = rays[i].time;
         HitRec h;
-        const bool hit = world_hit<false, 1, true>(S, r, t_min, t_max, (flags & RT_TRACE_SEEDED_MEDIA) != 0, seed, (uint64_t)i, 0u, h, nullptr);
+        const bool hit = world_hit<false, 1, true, true, RT_PM_ALL, true, WIDE>(S, r, t_min, t_max, (flags & RT_TRACE_SEEDED_MEDIA) != 0, seed, (uint64_t)i, 0u, h, nullptr);
         rt_hit o;
         if (hit) {
             o.prim_id = (int32_t)h.prim_id; o.mat_id = (int32_t)h.mat; o.t = h.t;
@@ -799,7 +802,8 @@ cudaError_t launch_trace_batch(const DeviceScene& scene, const rt_ray* d_rays, i
                                rt_hit* d_out, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const int blocks = (int)std::min<int64_t>((n + 127) / 128, 148 * 32);
-    k_trace_batch<<<blocks, 128, 0, stream>>>(scene, d_rays, n, t_min, t_max, flags, seed, d_out);
+    if (scene.nodes4 != nullptr && t_min >= 0.0) k_trace_batch<true><<<blocks, 128, 0, stream>>>(scene, d_rays, n, t_min, t_max, flags, seed, d_out);
+    else k_trace_batch<false><<<blocks, 128, 0, stream>>>(scene, d_rays, n, t_min, t_max, flags, seed, d_out);
     return cudaGetLastError();
 }
 
