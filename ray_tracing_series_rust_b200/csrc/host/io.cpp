@@ -1,12 +1,16 @@
-// io.cpp — see io.hpp.  Whole-file reads + hand-rolled token scanners: the 871 k-triangle ASCII PLY
-// of the dragon-scale config (~40 MB of text) parses in well under a second.
+// io.cpp — see io.hpp.  Whole-file reads + hand-rolled token scanners (std::from_chars, body lines parsed on all cores): the
+// 871 k-triangle ASCII PLY of the dragon-scale config (~37 MB of text) parses in well under 0.1 s.
 #include "io.hpp"
 
+#include <algorithm>
 #include <cctype>
+#include <charconv>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace rtb {
 
@@ -101,9 +105,33 @@ bool read_ppm_p3(const char* path, int32_t& W, int32_t& H, std::vector<double>& 
     return true;
 }
 
-bool read_ply_ascii(const char* path, double scale, std::vector<double>& verts, std::vector<uint32_t>& faces, std::string& err) {
-    std::string s;
-    if (!slurp(path, s, err)) return false;
+// One decimal number at p (leading blanks and an optional '+' skipped, as Rust's str::parse::<f64> accepts them after
+// split_whitespace, model.rs:44-48): std::from_chars is correctly rounded like strtod and several times faster; anything it does
+// not take (hex floats, "infinity" spellings) goes through strtod, so the accepted language is the old one.
+inline bool parse_double(const char*& p, const char* end, double& v) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    const char* q = (p < end && *p == '+') ? p + 1 : p;
+    const std::from_chars_result r = std::from_chars(q, end, v);
+    if (r.ec == std::errc() && r.ptr != q) { p = r.ptr; return true; }
+    char* e;
+    v = std::strtod(p, &e);
+    if (e == p) return false;
+    p = e;
+    return true;
+}
+inline bool parse_ulong(const char*& p, const char* end, unsigned long& v) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    const char* q = (p < end && *p == '+') ? p + 1 : p;
+    const std::from_chars_result r = std::from_chars(q, end, v);
+    if (r.ec != std::errc() || r.ptr == q) return false;
+    p = r.ptr;
+    return true;
+}
+
+// ASCII PLY subset of TriangleModel::load_from_file (model.rs:13-62): "element vertex N" / "element face M" / "end_header",
+// then N lines "x y z ..." (scaled) and M lines "3 a b c".  Lines are located with memchr, then parsed on all cores (each line is
+// independent); errors are reported for the first bad line, as the serial reader did.
+bool parse_ply_ascii(const std::string& s, double scale, std::vector<double>& verts, std::vector<uint32_t>& faces, std::string& err) {
     const char* p = s.c_str();
     const char* end = p + s.size();
     long nv = 0, nf = 0;
@@ -119,39 +147,72 @@ bool read_ply_ascii(const char* path, double scale, std::vector<double>& verts, 
     }
     if (!header_done) { err = "ply: no end_header line"; return false; }
     if (nv < 0 || nf < 0) { err = "ply: negative counts"; return false; }
-    verts.clear();
-    verts.reserve((size_t)nv * 3);
-    for (long i = 0; i < nv; ++i) {
-        if (p >= end) { err = "ply: truncated vertex list"; return false; }
+    // line starts of the nv + nf body lines
+    const size_t n_lines = (size_t)nv + (size_t)nf;
+    std::vector<const char*> line(n_lines + 1, end);
+    size_t found = 0;
+    while (found < n_lines && p < end) {
+        line[found++] = p;
         const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
-        char* e;
-        for (int k = 0; k < 3; ++k) {
-            const double v = std::strtod(p, &e);
-            if (e == p) { err = "ply: bad vertex line"; return false; }
-            verts.push_back(v * scale);
-            p = e;
-        }
         p = nl ? nl + 1 : end;
     }
-    faces.clear();
-    faces.reserve((size_t)nf * 3);
-    for (long i = 0; i < nf; ++i) {
-        if (p >= end) { err = "ply: truncated face list"; return false; }
-        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
-        char* e;
-        (void)std::strtoul(p, &e, 10); // the leading count is ignored (model.rs:53-57)
-        if (e == p) { err = "ply: bad face line"; return false; }
-        p = e;
-        for (int k = 0; k < 3; ++k) {
-            const unsigned long v = std::strtoul(p, &e, 10);
-            if (e == p) { err = "ply: bad face line"; return false; }
-            if (v >= (unsigned long)nv) { err = "ply: vertex index out of range"; return false; }
-            faces.push_back((uint32_t)v);
-            p = e;
+    if (found < (size_t)nv) { err = "ply: truncated vertex list"; return false; }
+    if (found < n_lines) { err = "ply: truncated face list"; return false; }
+    line[n_lines] = p;
+    verts.assign((size_t)nv * 3, 0.0);
+    faces.assign((size_t)nf * 3, 0u);
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned threads = n_lines >= 65536 ? std::min(16u, std::max(1u, hw)) : 1u;
+    // first failing line per kind (0 = bad vertex line, 1 = bad face line, 2 = index out of range); SIZE_MAX = none
+    std::vector<size_t> bad(3 * (size_t)threads, SIZE_MAX);
+    auto work = [&](unsigned t) {
+        // every thread takes an equal share of the vertex lines AND of the face lines (vertex lines cost ~3x a face line)
+        const size_t v_lo = (size_t)nv * t / threads, v_hi = (size_t)nv * (t + 1) / threads;
+        const size_t f_lo = (size_t)nv + (size_t)nf * t / threads, f_hi = (size_t)nv + (size_t)nf * (t + 1) / threads;
+        for (size_t i = v_lo; i < f_hi; i = (i + 1 == v_hi ? f_lo : i + 1)) {
+            if (i >= v_hi && i < f_lo) { i = f_lo; if (i >= f_hi) break; }
+            const char* q = line[i];
+            const char* le = line[i + 1];
+            if (i < (size_t)nv) {
+                for (int k = 0; k < 3; ++k) {
+                    double v;
+                    if (!parse_double(q, le, v)) { bad[3 * t] = std::min(bad[3 * t], i); break; }
+                    verts[3 * i + k] = v * scale;
+                }
+            } else {
+                const size_t fi = i - (size_t)nv;
+                unsigned long v;
+                if (!parse_ulong(q, le, v)) { bad[3 * t + 1] = std::min(bad[3 * t + 1], i); continue; } // the leading count is ignored (model.rs:53-57)
+                for (int k = 0; k < 3; ++k) {
+                    if (!parse_ulong(q, le, v)) { bad[3 * t + 1] = std::min(bad[3 * t + 1], i); break; }
+                    if (v >= (unsigned long)nv) { bad[3 * t + 2] = std::min(bad[3 * t + 2], i); break; }
+                    faces[3 * fi + k] = (uint32_t)v;
+                }
+            }
         }
-        p = nl ? nl + 1 : end;
+    };
+    if (threads <= 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (std::thread& th : pool) th.join();
     }
+    size_t first = SIZE_MAX;
+    int kind = -1;
+    for (unsigned t = 0; t < threads; ++t)
+        for (int k = 0; k < 3; ++k)
+            if (bad[3 * t + k] < first) { first = bad[3 * t + k]; kind = k; }
+    if (kind == 0) { err = "ply: bad vertex line"; return false; }
+    if (kind == 1) { err = "ply: bad face line"; return false; }
+    if (kind == 2) { err = "ply: vertex index out of range"; return false; }
     return true;
+}
+
+bool read_ply_ascii(const char* path, double scale, std::vector<double>& verts, std::vector<uint32_t>& faces, std::string& err) {
+    std::string s;
+    if (!slurp(path, s, err)) return false;
+    return parse_ply_ascii(s, scale, verts, faces, err);
 }
 
 // ------------------------------------------------------------------ binary fast paths
@@ -276,7 +337,7 @@ bool read_ply_any(const char* path, double scale, std::vector<double>& verts, st
         }
     }
     if (!header_done) { err = "ply: no end_header line"; return false; }
-    if (!binary) return read_ply_ascii(path, scale, verts, faces, err);
+    if (!binary) return parse_ply_ascii(s, scale, verts, faces, err); // the buffer is already in memory
     if (nv < 0 || nf < 0) { err = "ply: negative counts"; return false; }
     if (vprops.size() < 3 || !ply_is_float(vprops[0].first) || !ply_is_float(vprops[1].first) || !ply_is_float(vprops[2].first)) {
         err = "ply: binary vertices need three leading float/double properties"; return false;

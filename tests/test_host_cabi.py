@@ -198,6 +198,56 @@ def test_ply_and_ppm_io_roundtrip(api, orc, tmp_path):
     assert tuple(out) == tuple(scr[4, 0] / 255.0)
 
 
+def test_ascii_ply_number_formats_and_errors(api, tmp_path):
+    # the ASCII reader (std::from_chars, body lines parsed on all cores) accepts what Rust's str::parse accepts after split_whitespace
+    # (model.rs:44-57: signs, exponents, extra columns, CRLF), gives the binary reader's values bit for bit, and names the first bad line
+    hdr = "ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+    body = "+1.5 -2.5e-1 3E2\r\n\t0.1  1e-320   -0.0 7 7\r\n 12345678.901234567 .5 5.\n1 1 1\n3 0 1 2\n 3  +1 2 3 \n"
+    ply = tmp_path / "fmt.ply"
+    ply.write_text(hdr % (4, 2) + body)
+    binp = tmp_path / "fmt.bin.ply"
+    capi.ply_convert_binary(api, ply, binp)
+    raw = binp.read_bytes()
+    assert b"property float x" in raw  # the binary twin stores f32 vertices (as the device does)
+    vals = np.frombuffer(raw[raw.index(b"end_header\n") + 11:], dtype="<f4", count=12)
+    want = np.array([1.5, -0.25, 300.0, 0.1, 1e-320, -0.0, 12345678.901234567, 0.5, 5.0, 1.0, 1.0, 1.0]).astype("<f4")
+    assert vals.tobytes() == want.tobytes()
+    s = rtb.new_scene()
+    m = s.lambertian((0.2, 0.2, 0.2))
+    s.ply_load(ply, 2.0, m)
+    cases = {
+        "short vertex line": (hdr % (2, 0) + "0 0 0\n1 1\n", "bad vertex line"),
+        "not a number": (hdr % (1, 0) + "0 zero 0\n", "bad vertex line"),
+        "short face line": (hdr % (3, 1) + "0 0 0\n1 0 0\n0 1 0\n3 0 1\n", "bad face line"),
+        "index out of range": (hdr % (3, 1) + "0 0 0\n1 0 0\n0 1 0\n3 0 1 3\n", "out of range"),
+        "truncated vertices": (hdr % (3, 1) + "0 0 0\n1 0 0\n", "truncated vertex list"),
+        "truncated faces": (hdr % (3, 2) + "0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n", "truncated face list"),
+    }
+    for name, (text, msg) in cases.items():
+        f = tmp_path / "bad.ply"
+        f.write_text(text)
+        with pytest.raises(capi.RtError) as e:
+            s.ply_load(f, 1.0, m)
+        assert msg in str(e.value), (name, str(e.value))
+    # a body large enough for the parallel path: same arrays as the serial reader's would be (checked through the binary twin)
+    rng = np.random.default_rng(3)
+    nv, nf = 50000, 40000
+    v = rng.normal(size=(nv, 3)) * 10.0 ** rng.integers(-8, 8, size=(nv, 1))
+    fidx = rng.integers(0, nv, size=(nf, 3))
+    big = tmp_path / "big.ply"
+    with open(big, "w") as fh:
+        fh.write(hdr % (nv, nf))
+        fh.write("".join("%r %r %r\n" % (a, b, c) for a, b, c in v.tolist()))
+        fh.write("".join("3 %d %d %d\n" % (a, b, c) for a, b, c in fidx.tolist()))
+    bigb = tmp_path / "big.bin.ply"
+    capi.ply_convert_binary(api, big, bigb)
+    raw = bigb.read_bytes()
+    off = raw.index(b"end_header\n") + 11
+    assert np.frombuffer(raw[off:], dtype="<f4", count=3 * nv).tobytes() == v.astype("<f4").tobytes()  # repr round-trips: correctly rounded parse
+    idx = np.frombuffer(raw[off + 12 * nv:], dtype=np.uint8).reshape(nf, 13)
+    assert (idx[:, 0] == 3).all() and np.array_equal(np.ascontiguousarray(idx[:, 1:]).view("<u4").reshape(nf, 3), fidx.astype("<u4"))
+
+
 def test_binary_io_fast_paths(api, tmp_path):
     # P6 out/in and binary_little_endian PLY in, next to the byte-compatible text formats
     rng = np.random.default_rng(1)
