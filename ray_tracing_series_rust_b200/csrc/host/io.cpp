@@ -69,6 +69,29 @@ bool write_ppm_p3(const char* path, const double* screen, int32_t W, int32_t H, 
     return ok;
 }
 
+// One decimal number at p (leading blanks and an optional '+' skipped, as Rust's str::parse::<f64> accepts them after
+// split_whitespace, model.rs:44-48): std::from_chars is correctly rounded like strtod and several times faster; anything it does
+// not take (hex floats, "infinity" spellings) goes through strtod, so the accepted language is the old one.
+inline bool parse_double(const char*& p, const char* end, double& v) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    const char* q = (p < end && *p == '+') ? p + 1 : p;
+    const std::from_chars_result r = std::from_chars(q, end, v);
+    if (r.ec == std::errc() && r.ptr != q) { p = r.ptr; return true; }
+    char* e;
+    v = std::strtod(p, &e);
+    if (e == p) return false;
+    p = e;
+    return true;
+}
+inline bool parse_ulong(const char*& p, const char* end, unsigned long& v) {
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    const char* q = (p < end && *p == '+') ? p + 1 : p;
+    const std::from_chars_result r = std::from_chars(q, end, v);
+    if (r.ec != std::errc() || r.ptr == q) return false;
+    p = r.ptr;
+    return true;
+}
+
 bool read_ppm_p3(const char* path, int32_t& W, int32_t& H, std::vector<double>& rgb, std::string& err) {
     std::string s;
     if (!slurp(path, s, err)) return false;
@@ -95,36 +118,11 @@ bool read_ppm_p3(const char* path, int32_t& W, int32_t& H, std::vector<double>& 
     while (rgb.size() < want) {
         while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r' || *p == '\f' || *p == '\v')) ++p;
         if (p >= end) break;
-        char* e;
-        const double v = std::strtod(p, &e);
-        if (e == p) { err = "ppm: bad sample"; return false; }
+        double v;
+        if (!parse_double(p, end, v)) { err = "ppm: bad sample"; return false; }
         rgb.push_back(v);
-        p = e;
     }
     if (rgb.size() < want) { err = "ppm: not enough samples"; return false; }
-    return true;
-}
-
-// One decimal number at p (leading blanks and an optional '+' skipped, as Rust's str::parse::<f64> accepts them after
-// split_whitespace, model.rs:44-48): std::from_chars is correctly rounded like strtod and several times faster; anything it does
-// not take (hex floats, "infinity" spellings) goes through strtod, so the accepted language is the old one.
-inline bool parse_double(const char*& p, const char* end, double& v) {
-    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
-    const char* q = (p < end && *p == '+') ? p + 1 : p;
-    const std::from_chars_result r = std::from_chars(q, end, v);
-    if (r.ec == std::errc() && r.ptr != q) { p = r.ptr; return true; }
-    char* e;
-    v = std::strtod(p, &e);
-    if (e == p) return false;
-    p = e;
-    return true;
-}
-inline bool parse_ulong(const char*& p, const char* end, unsigned long& v) {
-    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
-    const char* q = (p < end && *p == '+') ? p + 1 : p;
-    const std::from_chars_result r = std::from_chars(q, end, v);
-    if (r.ec != std::errc() || r.ptr == q) return false;
-    p = r.ptr;
     return true;
 }
 
