@@ -161,6 +161,13 @@ RTB_EXPORT int32_t RTB_FN(scene_set_camera)(rt_scene* s, const double lookfrom[3
  * its flatten() makes; rt_scene_set_camera derives the same block from Camera::new's arguments. */
 RTB_EXPORT int32_t RTB_FN(scene_set_camera_fields)(rt_scene* s, const double fields[24]);
 RTB_EXPORT int32_t RTB_FN(scene_set_background)(rt_scene* s, const double rgb[3]);
+/* Book-1 sky: a miss contributes (1 - t) * horizon + t * zenith with t = 0.5 * (unit(direction).y + 1) instead of the
+ * constant background.  HEAD of the reference only has the constant (src/world.rs:86-89); the revision that rendered the
+ * shipped images/book1.png (README.md:18) used this sky with horizon (1,1,1), zenith (0.5,0.7,1.0), so the option
+ * exists to check renders against that reference-held image (tests/test_reference_images.py).
+ * rt_scene_set_background switches back to the constant. */
+RTB_EXPORT int32_t RTB_FN(scene_set_background_gradient)(rt_scene* s, const double horizon_rgb[3],
+                                                         const double zenith_rgb[3]);
 /* Freeze the scene: number the leaves depth-first, flatten, build the device BVH, upload to the
  * current CUDA device.  Replaces "Arc::new(world)" hand-off at src/world.rs:1181-1186. */
 RTB_EXPORT int32_t RTB_FN(scene_commit)(rt_scene* s);

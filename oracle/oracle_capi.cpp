@@ -36,7 +36,7 @@ struct rt_scene {
     HittablePtr root;
     Camera cam;
     bool has_cam = false;
-    Color background = Color(0, 0, 0);
+    Background background;
     int32_t n_prims = 0;
     bool committed = false;
     uint64_t bvh_seed = 0x0B5EEDull;
@@ -344,7 +344,16 @@ int32_t orc_scene_set_camera_fields(rt_scene* s, const double f[24]) {
 }
 int32_t orc_scene_set_background(rt_scene* s, const double rgb[3]) {
     CHECK_SCENE(s);
-    s->background = Color(rgb[0], rgb[1], rgb[2]);
+    s->background = Background();
+    s->background.c0 = Color(rgb[0], rgb[1], rgb[2]);
+    return RT_OK;
+}
+int32_t orc_scene_set_background_gradient(rt_scene* s, const double horizon_rgb[3], const double zenith_rgb[3]) {
+    CHECK_SCENE(s);
+    if (!horizon_rgb || !zenith_rgb) return fail(RT_ERR_INVALID, "null colour");
+    s->background.c0 = Color(horizon_rgb[0], horizon_rgb[1], horizon_rgb[2]);
+    s->background.c1 = Color(zenith_rgb[0], zenith_rgb[1], zenith_rgb[2]);
+    s->background.gradient = true;
     return RT_OK;
 }
 int32_t orc_scene_commit(rt_scene* s) {
@@ -398,7 +407,7 @@ int32_t orc_render(rt_scene* s, const rt_render_config* cfg, double* out_screen,
     std::vector<Counters> cnts((size_t)threads);
     const Hittable& world = *s->root;
     const Camera& cam = s->cam;
-    const Color background = s->background;
+    const Background background = s->background;
     const int32_t max_depth = cfg->max_depth;
     const uint64_t seed = cfg->seed;
     const int32_t tile_count = RT_RENDER_TILE_COUNT(cfg->flags) > 1 ? RT_RENDER_TILE_COUNT(cfg->flags) : 1;

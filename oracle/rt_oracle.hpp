@@ -964,7 +964,18 @@ struct Camera {
 };
 
 // ------------------------------------------------------------------ world.rs:52-93 ray_color
-inline Color ray_color(const Ray& r, const Color& background, const Hittable& world, int32_t depth) {
+// Background of a miss.  world.rs:86-89 multiplies by one constant `background`; the earlier revision that rendered the shipped
+// images/book1.png used the book-1 sky instead (unit(d).y blended white -> blue), kept here as an option so that image can pin the port.
+struct Background {
+    Color c0 = Color(0, 0, 0), c1 = Color(0, 0, 0);
+    bool gradient = false;
+    Color at(const Ray& r) const {
+        if (!gradient) return c0;
+        const double t = 0.5 * (r.direction.unit().y + 1.0);
+        return (1.0 - t) * c0 + t * c1;
+    }
+};
+inline Color ray_color(const Ray& r, const Background& background, const Hittable& world, int32_t depth) {
     Vec3 product(1, 1, 1), output(0, 0, 0);
     Ray current_ray = r;
     PathCtx& c = ctx();
@@ -988,7 +999,7 @@ inline Color ray_color(const Ray& r, const Color& background, const Hittable& wo
                 break;
             }
         } else {
-            output += product * background;
+            output += product * background.at(current_ray);
             break;
         }
     }

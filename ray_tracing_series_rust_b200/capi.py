@@ -101,6 +101,7 @@ SIGNATURES = {
     "scene_set_camera": (C.c_int32, [_P, c_d3, c_d3, c_d3] + [C.c_double] * 6),
     "scene_set_camera_fields": (C.c_int32, [_P, c_d3]),
     "scene_set_background": (C.c_int32, [_P, c_d3]),
+    "scene_set_background_gradient": (C.c_int32, [_P, c_d3, c_d3]),
     "scene_commit": (C.c_int32, [_P]),
     "world_build": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_int32]),
     "scene_num_prims": (C.c_int32, [_P]),
@@ -292,6 +293,10 @@ class Scene:
 
     def set_background(self, rgb):
         return self._c(self.api.scene_set_background(self.h, _d3(rgb)))
+
+    def set_background_gradient(self, horizon_rgb=(1.0, 1.0, 1.0), zenith_rgb=(0.5, 0.7, 1.0)):
+        """book-1 sky (the revision of the reference that rendered images/book1.png)"""
+        return self._c(self.api.scene_set_background_gradient(self.h, _d3(horizon_rgb), _d3(zenith_rgb)))
 
     def commit(self):
         return self._c(self.api.scene_commit(self.h))

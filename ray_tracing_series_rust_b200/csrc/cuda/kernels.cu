@@ -445,7 +445,9 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
         bool ended = true;
         if (q == Q_MISS) {
             // world.rs:86-89: output += product * background
-            contrib = mkf3(sd.tr * S.background[0], sd.tg * S.background[1], sd.tb * S.background[2]);
+            F3 bg = mkf3(S.background[0], S.background[1], S.background[2]);
+            if (S.bg_gradient) { const SlotB sb = P.B[slot]; bg = miss_color(S, mk3(sb.dx, sb.dy, sb.dz)); } // a miss leaves the ray direction in B
+            contrib = mkf3(sd.tr * bg.x, sd.tg * bg.y, sd.tb * bg.z);
         } else {
             const SlotA sa = P.A[slot];
             const SlotC sc = P.C[slot];
@@ -569,7 +571,8 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
         if (!hit) {
-            contrib = mkf3(tr * S.background[0], tg * S.background[1], tb * S.background[2]);
+            const F3 bg = miss_color(S, r.d);
+            contrib = mkf3(tr * bg.x, tg * bg.y, tb * bg.z);
         } else {
             const DMaterial m = S.materials[h.mat];
             if (m.type == MAT_LIGHT) {
@@ -672,7 +675,8 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
         F3 contrib = mkf3(0.f, 0.f, 0.f);
         bool ended = true;
         if (best.type == RT_NONE) {
-            contrib = mkf3(tr * S.background[0], tg * S.background[1], tb * S.background[2]);
+            const F3 bg = miss_color(S, r.d);
+            contrib = mkf3(tr * bg.x, tg * bg.y, tb * bg.z);
         } else {
             const HitRec h = finalize_hit<2, PM, false>(S, r, best);
             const DMaterial m = S.materials[h.mat];

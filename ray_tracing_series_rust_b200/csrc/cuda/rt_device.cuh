@@ -927,6 +927,14 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
     return mkf3(0.f, 0.f, 0.f);
 }
 
+// world.rs:86-89: what a miss contributes per unit of throughput.  Constant `background`, or the book-1 sky of the revision that
+// rendered images/book1.png (rt_scene_set_background_gradient): (1 - t) * horizon + t * zenith, t = 0.5 * (unit(d).y + 1).
+RT_DEV F3 miss_color(const DeviceScene& S, D3 d) {
+    if (!S.bg_gradient) return mkf3(S.background[0], S.background[1], S.background[2]);
+    const float t = (float)(0.5 * (unit(d).y + 1.0)), w = 1.0f - t;
+    return mkf3(w * S.background[0] + t * S.background_top[0], w * S.background[1] + t * S.background_top[1], w * S.background[2] + t * S.background_top[2]);
+}
+
 // ------------------------------------------------------------------ Material::scatter (hit.rs:1004-1152)
 // Returns true when the path continues; `dir` = scattered direction, `att` = attenuation.
 template <bool FULLTEX = true, class G>

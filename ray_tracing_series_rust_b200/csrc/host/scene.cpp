@@ -103,6 +103,8 @@ struct rt_scene {
     int32_t root = -1;
     CameraDesc camera;
     double background[3] = {0, 0, 0};
+    double background_top[3] = {0, 0, 0};
+    bool bg_gradient = false;
     int32_t n_prims = 0;
     bool committed = false;
     double span0 = 0.0, span1 = 1.0; // time span the moving-primitive bounds cover
@@ -754,7 +756,8 @@ void set_scene_scalars(const rt_scene* s, const HostFlat& HF, DeviceScene& D) {
     if (!HF.ops.empty()) D.flags |= 32u;       // Translate / RotateY wrappers present
     if (HF.tris.size() >= 4096) D.flags |= 4u; // deep triangle BVH: prefer the persistent warp-scheduled extend kernel
     if (s->camera.set) D.cam = s->camera.cam;
-    for (int a = 0; a < 3; ++a) D.background[a] = (float)s->background[a];
+    for (int a = 0; a < 3; ++a) { D.background[a] = (float)s->background[a]; D.background_top[a] = (float)s->background_top[a]; }
+    D.bg_gradient = s->bg_gradient ? 1u : 0u;
 }
 
 int32_t do_commit(rt_scene* s) {
@@ -1071,8 +1074,22 @@ int32_t rt_scene_set_background(rt_scene* s, const double rgb[3]) {
     CHECK_SCENE(s);
     if (!rgb) return fail(RT_ERR_INVALID, "null colour");
     for (int a = 0; a < 3; ++a) s->background[a] = rgb[a];
-    if (s->dev.valid)
+    s->bg_gradient = false;
+    if (s->dev.valid) {
         for (int a = 0; a < 3; ++a) s->dev.scene.background[a] = (float)rgb[a];
+        s->dev.scene.bg_gradient = 0u;
+    }
+    return RT_OK;
+}
+int32_t rt_scene_set_background_gradient(rt_scene* s, const double horizon[3], const double zenith[3]) {
+    CHECK_SCENE(s);
+    if (!horizon || !zenith) return fail(RT_ERR_INVALID, "null colour");
+    for (int a = 0; a < 3; ++a) { s->background[a] = horizon[a]; s->background_top[a] = zenith[a]; }
+    s->bg_gradient = true;
+    if (s->dev.valid) {
+        for (int a = 0; a < 3; ++a) { s->dev.scene.background[a] = (float)horizon[a]; s->dev.scene.background_top[a] = (float)zenith[a]; }
+        s->dev.scene.bg_gradient = 1u;
+    }
     return RT_OK;
 }
 int32_t rt_scene_commit(rt_scene* s) {

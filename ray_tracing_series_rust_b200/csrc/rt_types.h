@@ -147,7 +147,9 @@ struct DeviceScene {
     uint32_t n_prims;
     uint32_t flags; // bit 0: the scene has axis rects / boxes (per-ray inverse directions are needed); bit 1: every medium has the fast path; bit 2: large triangle mesh; bit 3: Perlin-noise textures; bit 4: image textures; bit 5: Translate / RotateY wrappers present
     DCamera cam;
-    float background[3];
+    float background[3];    // world.rs:86-89 constant background (gradient sky: colour at the horizon side, t = 0)
+    uint32_t bg_gradient;   // 1: book-1 sky, (1 - t) * background + t * background_top, t = 0.5 * (unit(d).y + 1)  (rt_scene_set_background_gradient)
+    float background_top[3];
     float pad2_;
 };
 

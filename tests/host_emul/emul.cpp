@@ -112,7 +112,7 @@ int32_t emul_render(const void* scene, int32_t W, int32_t H, int32_t spp_total, 
                     const bool hit = wide ? world_hit<false, 2, true, true, RT_PM_ALL, true, true>(S, r, 0.001, RT_INF, true, seed, path_id, segment, h, nullptr)
                                           : world_hit<false, 2, true>(S, r, 0.001, RT_INF, true, seed, path_id, segment, h, nullptr);
                     ++segments;
-                    if (!hit) { contrib = mkf3(tr * S.background[0], tg * S.background[1], tb * S.background[2]); break; }
+                    if (!hit) { const F3 bg = miss_color(S, r.d); contrib = mkf3(tr * bg.x, tg * bg.y, tb * bg.z); break; }
                     const DMaterial m = S.materials[h.mat];
                     if (m.type == MAT_LIGHT) {
                         const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
