@@ -244,6 +244,24 @@ typedef enum rt_mat_type {
  *                                   [ref: src/world.rs:1181-1247, src/vec3.rs:89-107] */
 RTB_EXPORT int32_t RTB_FN(render)(rt_scene* s, const rt_render_config* cfg, double* out_screen,
                                   int64_t* out_accum, rt_stats* stats);
+/* The same render spread over n_gpus GPUs of this box by ONE host thread of ONE process (what a Rust render_scene_gpu calls to
+ * use the whole 8 x B200 node; SURVEY.md 8(b) n_gpus / shard_mode, 8(e)).  GPU 0 is the device the scene was committed on, GPUs
+ * 1..n-1 are the next visible devices; each gets the committed scene's flattened bytes (uploaded once per commit, or ahead of time
+ * by rt_scene_commit_multi) and renders one shard: RT_SHARD_SAMPLES = a contiguous range of the samples of every pixel (perfect
+ * balance), RT_SHARD_TILES = every sample of the RT_TILE_ROWS-row bands b with b % n_gpus == g (the reference's row bands,
+ * world.rs:1198-1227).  The shards' int64 accumulators are summed and resolved by one kernel on GPU 0 that reads the peers'
+ * accumulators in place over NVLink (P2P-mapped pointers; a staged peer copy only where no P2P route exists).  Integer sums and
+ * Philox streams keyed by the global pixel / sample index make the image bit-identical to rt_render for every n_gpus and either
+ * mode.  cfg->sample_begin / sample_end select the range that is split; RT_RENDER_TILE_SHARD must not be set.  stats: counters
+ * summed over the shards, ms_device = the slowest shard.                      [ref: src/world.rs:1181-1247, 1198-1240] */
+#define RT_SHARD_SAMPLES 0
+#define RT_SHARD_TILES 1
+#ifndef RTB_PREFIX_ORC
+RTB_EXPORT int32_t rt_render_multi(rt_scene* s, const rt_render_config* cfg, int32_t n_gpus, int32_t shard_mode,
+                                   double* out_screen, int64_t* out_accum, rt_stats* stats);
+/* rt_scene_commit + upload of the flattened scene to GPUs 1..n_gpus-1 (otherwise the first rt_render_multi does it). */
+RTB_EXPORT int32_t rt_scene_commit_multi(rt_scene* s, int32_t n_gpus);
+#endif
 /* image height the config implies: (image_width as f64 / aspect_ratio) as i32 */
 RTB_EXPORT int32_t RTB_FN(image_height)(const rt_render_config* cfg);
 

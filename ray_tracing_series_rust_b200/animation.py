@@ -8,7 +8,7 @@ not the loop around it (its `/video_testing/` driver is absent from the repo), a
                       `rt_scene_set_camera` + `rt_scene_commit` (GravitySphere windows, BVH) -> render -> PPM
                       (P3 as the reference, or P6).  Finished frames are skipped on restart.
 * `ProgressiveRender` one still rendered as sample ranges `[s0, s1)` (rt_render_config.sample_begin / sample_end)
-                      summed into the int64 accumulator, with an atomic checkpoint every few chunks.  Philox
+                      summed into the int64 accumulator, with an atomic single-file checkpoint every few chunks.  Philox
                       streams are keyed by the global sample index and the sum is integer, so a render that
                       was interrupted and resumed is bit-identical to the one-shot render.
 * `resolve_accumulator`  host mirror of `k_resolve` (Vec3::get_normalized_color, src/vec3.rs:89-107).
@@ -53,33 +53,37 @@ class ProgressiveRender:
         self.meta = dict(meta or {})
         self.accum = np.zeros(self.shape, dtype=np.int64)
         self.done = 0
-        if checkpoint and os.path.exists(checkpoint + ".json"):
+        if checkpoint and os.path.exists(self._file()):
             self._load()
 
-    # ---- checkpoint = <path>.npy (accumulator) + <path>.json (samples done, identity of the render); written to
-    # temporaries and renamed, the json last: a crash leaves either the old or the new pair
+    # ---- checkpoint = ONE file <path>.npz holding the accumulator, the number of samples it contains and the identity of the
+    # render; written to a temporary and renamed, so a crash at any point leaves either the old or the new checkpoint, never an
+    # accumulator paired with another checkpoint's sample count (which would add a sample range twice on resume)
+    def _file(self):
+        return self.checkpoint + ".npz"
+
     def _identity(self):
         return {"shape": list(self.shape), "spp_total": self.spp_total, "meta": self.meta}
 
     def _load(self):
-        j = json.load(open(self.checkpoint + ".json"))
-        if j.get("identity") != self._identity():
-            raise ValueError("checkpoint belongs to a different render: %r" % (j.get("identity"),))
-        a = np.load(self.checkpoint + ".npy")
-        if a.shape != self.shape or a.dtype != np.int64 or not (0 <= int(j["samples_done"]) <= self.spp_total):
+        with np.load(self._file(), allow_pickle=False) as z:
+            ident = json.loads(str(z["identity"]))
+            a, done = z["accum"], int(z["samples_done"])
+        if ident != self._identity():
+            raise ValueError("checkpoint belongs to a different render: %r" % (ident,))
+        if a.shape != self.shape or a.dtype != np.int64 or not (0 <= done <= self.spp_total):
             raise ValueError("corrupt checkpoint")
-        self.accum, self.done = a, int(j["samples_done"])
+        self.accum, self.done = a, done
 
     def save(self):
         if not self.checkpoint:
             return
-        tmp = self.checkpoint + ".tmp.npy"
-        np.save(tmp, self.accum)
-        os.replace(tmp, self.checkpoint + ".npy")
-        tmpj = self.checkpoint + ".tmp.json"
-        with open(tmpj, "w") as f:
-            json.dump({"samples_done": self.done, "identity": self._identity()}, f)
-        os.replace(tmpj, self.checkpoint + ".json")
+        tmp = self.checkpoint + ".tmp.npz"
+        with open(tmp, "wb") as f:
+            np.savez(f, accum=self.accum, samples_done=np.int64(self.done), identity=np.array(json.dumps(self._identity(), sort_keys=True)))
+            f.flush()
+            os.fsync(f.fileno())
+        os.replace(tmp, self._file())
 
     def run(self, max_chunks: Optional[int] = None) -> np.ndarray:
         """Renders until spp_total (or for `max_chunks` chunks); returns the accumulator so far."""

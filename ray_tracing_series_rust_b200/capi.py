@@ -115,7 +115,12 @@ SIGNATURES = {
 DEVICE_SIGNATURES = {
     "render_device": (C.c_int32, [_P, C.POINTER(RenderConfig), _P, _P, C.POINTER(Stats)]),
     "resolve_device": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    # one process, N GPUs: shards rendered per device, accumulators summed + resolved over NVLink peer memory
+    "render_multi": (C.c_int32, [_P, C.POINTER(RenderConfig), C.c_int32, C.c_int32, c_d3, C.POINTER(C.c_int64), C.POINTER(Stats)]),
+    "scene_commit_multi": (C.c_int32, [_P, C.c_int32]),
 }
+RT_SHARD_SAMPLES = 0
+RT_SHARD_TILES = 1
 
 
 class RtError(RuntimeError):
@@ -359,6 +364,20 @@ class Scene:
         self._c(self.api.render(self.h, C.byref(cfg), screen.ctypes.data_as(c_d3),
                                 accum.ctypes.data_as(C.POINTER(C.c_int64)) if want_accum else None, C.byref(st)))
         return screen, accum, st.as_dict()
+
+    def render_multi(self, cfg: RenderConfig, n_gpus: int, shard_mode: int = RT_SHARD_SAMPLES, want_accum=False):
+        """rt_render_multi: the same render sharded over n_gpus GPUs by this one process; same return as render()"""
+        H = self.image_height(cfg)
+        W = cfg.image_width
+        screen = np.zeros((H, W, 3), dtype=np.float64)
+        accum = np.zeros((H, W, 3), dtype=np.int64) if want_accum else None
+        st = Stats()
+        self._c(self.api.render_multi(self.h, C.byref(cfg), int(n_gpus), int(shard_mode), screen.ctypes.data_as(c_d3),
+                                      accum.ctypes.data_as(C.POINTER(C.c_int64)) if want_accum else None, C.byref(st)))
+        return screen, accum, st.as_dict()
+
+    def commit_multi(self, n_gpus: int):
+        return self._c(self.api.scene_commit_multi(self.h, int(n_gpus)))
 
     def render_scene_with_time(self, t0, t1, path=None, cfg: RenderConfig = None):
         """render_scene_with_time(t0, t1, path, world)  [ref: world.rs:1249]; cfg None = the reference's 500x500x500spp frame"""

@@ -66,7 +66,6 @@ struct JobDev {
     uint32_t wait_thresh; // k_mega_r: finished lanes that end a traversal round
     uint32_t tile_rank, tile_count; // RT_RENDER_TILE_SHARD: npix_rendered counts this shard's pixels only
     uint32_t chunk;                 // fused kernels: consecutive path indices a warp claims per atomic
-    uint32_t tile_order;            // 1: path indices enumerate the pixels tile by tile (tile_order_pixel), single-shard renders only
 };
 
 // Path-state chunks are streamed (read once / written once per kernel): evict-first hints keep them from
@@ -132,11 +131,7 @@ __global__ void k_init(PathState P, Queues Q, uint32_t n) {
 // Tile sharding: the shard's pixels are enumerated densely (local row lr = band lr / 4 of this rank, line lr % 4);
 // the global pixel index (accumulator address, Philox path id) is that of the unsharded image.
 RT_DEV uint32_t shard_pixel(const JobDev& J, uint32_t q) {
-#ifdef RT_TILE_ORDER // experiment (make EXTRA=-DRT_TILE_ORDER + RTB200_TILE_ORDER=1): compiled out of the default build, whose refill code is the measured one
-    if (J.tile_count <= 1u) return J.tile_order ? tile_order_pixel(q, (uint32_t)J.W, (uint32_t)J.rows) : q;
-#else
     if (J.tile_count <= 1u) return q;
-#endif
     const uint32_t W = (uint32_t)J.W, lr = q / W, x = q - lr * W;
     const uint32_t band = (lr / RT_TILE_ROWS) * J.tile_count + J.tile_rank;
     return (band * RT_TILE_ROWS + lr % RT_TILE_ROWS) * W + x;
@@ -738,6 +733,53 @@ __global__ void k_resolve(const int64_t* __restrict__ accum, double* __restrict_
     }
 }
 
+// ------------------------------------------------------------------ reduce + resolve over peer memory (multi-GPU inside the library)
+// The one exchange of a sharded render fused with get_normalized_color: this kernel runs on the gathering GPU and reads
+// every shard's int64 accumulator where it lies - its own HBM or a peer's, through NVLink / NVSwitch P2P-mapped pointers - adds them
+// (integer: order independent, so the image is bit-identical for any shard count) and writes the quantised Screen.  There is no staging
+// copy and no separate reduce pass: 24 B per pixel per shard cross the links once, 128 bits per load.
+//   sum_out    nullable: the reduced int64 accumulator (rt_render's out_accum)
+//   screen_u8  nullable: Screen as bytes, same layout as the f64 Screen (row 0 = bottom, rgb); every value is an integer in 0..255
+//   screen_f64 nullable: Screen as the reference's f64 Colors (vec3.rs:89-107)
+__global__ void __launch_bounds__(256) k_reduce_resolve(const AccumShards A, int64_t* sum_out /* may alias A.p[0] */, uint8_t* __restrict__ screen_u8,
+                                                        double* __restrict__ screen_f64, int32_t W, int32_t H, int32_t spp, int32_t rows) {
+    const int64_t n = (int64_t)W * H * 3, n2 = n >> 1; // pairs of channels: 16-byte loads
+    const int64_t rendered = (int64_t)W * rows * 3;
+    const double scale = 1.0 / (double)spp;
+    for (int64_t i2 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i2 < n2 + (n & 1); i2 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = 2 * i2;
+        const bool pair = i + 1 < n;
+        long long s0 = 0, s1 = 0;
+        for (int g = 0; g < A.n; ++g) {
+            if (pair) {
+                const longlong2 v = *reinterpret_cast<const longlong2*>(A.p[g] + i);
+                s0 += v.x; s1 += v.y;
+            } else {
+                s0 += A.p[g][i];
+            }
+        }
+        if (sum_out) {
+            if (pair) *reinterpret_cast<longlong2*>(sum_out + i) = make_longlong2(s0, s1);
+            else sum_out[i] = s0;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1 && !pair) break;
+            const int64_t e = i + k;
+            double out = 0.0;
+            if (e < rendered) { // rows >= `rows` stay (0,0,0): world.rs:1198-1202
+                const double sum = (double)(k ? s1 : s0) * (1.0 / 4294967296.0);
+                double c = sqrt(sum * scale);
+                c = c < 0.0 ? 0.0 : (c > 1.0 ? 1.0 : c);     // mutil.rs:1-9 (NaN passes through)
+                const double q = 255.9 * c;
+                out = (q != q) ? 0.0 : (double)(int32_t)q;    // `as i32`: truncation, NaN -> 0
+            }
+            if (screen_u8) screen_u8[e] = (uint8_t)out;
+            if (screen_f64) screen_f64[e] = out;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ trace_batch (parity hook)
 // WIDE = true: the main world through its 4-wide collapse (scenes that carry one, t_min >= 0), so the parity hook checks the walk the
 // render kernels of such a scene use
@@ -799,6 +841,14 @@ cudaError_t launch_resolve(const int64_t* d_accum, double* d_screen, int32_t W, 
     const int64_t n = (int64_t)W * H * 3;
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
     k_resolve<<<blocks, 256, 0, stream>>>(d_accum, d_screen, W, H, spp, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_resolve(const AccumShards& shards, int64_t* d_sum_out, uint8_t* d_screen_u8, double* d_screen_f64, int32_t W, int32_t H, int32_t spp,
+                                  int32_t rows, cudaStream_t stream) {
+    const int64_t n2 = ((int64_t)W * H * 3 + 1) / 2;
+    const int blocks = (int)std::min<int64_t>((n2 + 255) / 256, 148 * 8);
+    k_reduce_resolve<<<blocks, 256, 0, stream>>>(shards, d_sum_out, d_screen_u8, d_screen_f64, W, H, spp, rows);
     return cudaGetLastError();
 }
 
@@ -895,14 +945,11 @@ static void launch_extend(int blocks, bool specialise, bool wide, cudaStream_t s
     // bytes but gain 5 % (tools/explore.py ab, Cornell smoke 634 -> 668, book-2 final 325 -> 340 Mpaths/s); 6 CTAs/SM (80
     // registers, 130-340 B spilled) is +1 % on Cornell smoke and -1.4 % on book-2 final.  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
     // the general two-traversal path; the two media scenes of the reference also get their primitive mask compiled in.
-    // wide = the scene carries the 4-wide collapse and the caller forced it (rt_scene_set_bvh_width(4)): not yet measured for these kernels
+    // wide: only the counting pass of a scene whose fused kernel walks the 4-wide collapse.  The wavefront kernels themselves stay on
+    // sibling pairs: forced onto the wide tree they measured 718.7 vs 719.2 (Cornell smoke) and 341.3 vs 341.9 Mpaths/s (book-2 final)
     if constexpr (MEDIA) {
         if (!(scene.flags & 2u)) {
             k_extend<true, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-        } else if (!COUNT && specialise && wide && (scene.prim_mask & ~0x18u) == 0) {
-            k_extend<true, false, 5, false, 0x18u, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-        } else if (!COUNT && specialise && wide && (scene.prim_mask & ~0x1bu) == 0) {
-            k_extend<true, false, 5, false, 0x1bu, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
         } else if (!COUNT && specialise && (scene.prim_mask & ~0x18u) == 0) {
             k_extend<true, false, 5, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
         } else if (!COUNT && specialise && (scene.prim_mask & ~0x1bu) == 0) {
@@ -914,8 +961,7 @@ static void launch_extend(int blocks, bool specialise, bool wide, cudaStream_t s
         if (wide) k_extend<false, true, 4, false, RT_PM_ALL, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // counts 4 boxes per wide node visited
         else k_extend<false, true, 4, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
     } else {
-        if (wide) k_extend<false, false, 5, false, RT_PM_ALL, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
-        else k_extend<false, false, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        k_extend<false, false, 5, false><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
     }
 }
 
@@ -936,7 +982,6 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
     J.total_paths = (unsigned long long)J.npix_rendered * (unsigned long long)(job.sample_end - job.sample_begin);
     J.seed = job.seed;
     J.count_events = tune.count_events;
-    J.tile_order = (tune.tile_order > 0 && J.tile_count <= 1u) ? 1u : 0u;
     uint32_t N = tune.wave_slots;
     if ((unsigned long long)N > J.total_paths) N = (uint32_t)std::max<unsigned long long>(J.total_paths, 1ull);
     N = (N + 127u) & ~127u;
@@ -966,7 +1011,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         // wavefront kernels walk the 4-wide collapse only when it was forced (unmeasured for them) - and in the counting pass of a
         // scene whose fused kernel walks it, so that the device counters describe the tree the timed kernel walks (4 boxes per visit)
         const bool count_wide = tune.count_events && !media && scene.nodes4 != nullptr && tune.bvh_wide != 0;
-        const bool ext_wide = (scene.nodes4 != nullptr && tune.bvh_wide > 0) || count_wide;
+        const bool ext_wide = count_wide;
         const int ext_kind = count_wide ? 0 : ext_kind_auto; // k_extend_p has no wide form
         const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, ext_occ) * (uint32_t)std::max(1, tune.extend_waves));
         CK(cudaEventRecord(w->ev_begin, stream));
@@ -1004,14 +1049,11 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 // the mesh walk is L2-latency bound (long-scoreboard 3.6 per issue): more resident warps beat fewer spills:
                 // 5 CTAs/SM (96 regs, 132 B spilled) 126, 6 (80 regs) 134.5, 7 (72 regs, 652 B spilled) 139.7, 8 (64 regs) 135 Mpaths/s
                 else if (scene.nodes4 && tune.bvh_wide != 0) {
-                    // 4-wide walk: 871k mesh 149.8 -> 179.5 Mpaths/s at 7 CTAs/SM (6: 175.3, 5: 166.7; tools/ab_wide.py); RTB200_WIDE_OCC
-                    if (tune.wide_occ == 5) k_mega_r<5, 0x28u, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
-                    else if (tune.wide_occ == 6) k_mega_r<6, 0x28u, true><<<148 * 6, 128, 0, stream>>>(scene, J, Q, d_accum);
-                    else k_mega_r<7, 0x28u, true><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
+                    // 4-wide walk: 871k mesh 149.8 -> 179.5 Mpaths/s at 7 CTAs/SM (6: 175.5, 5: 165.9; profiles/r2_00_ab.log)
+                    k_mega_r<7, 0x28u, true><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
                 } else k_mega_r<7, 0x28u><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (wrapper_free && scene.nodes4 && tune.bvh_wide != 0 && scene.n_main_instances == 1 && (pm == 0x1u || pm == 0x3u || pm == 0x5u || pm == 0x28u)) {
-                if (pm == 0x1u && tune.wide_occ == 6) k_mega<false, 6, false, 0x1u, false, true><<<148 * 6, 128, 0, stream>>>(scene, J, Q, d_accum); // RTB200_WIDE_OCC=6: unmeasured (80 registers)
-                else if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
+                if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else if (pm == 0x3u) k_mega<false, 5, false, 0x3u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum); // motion form (mnodes4), forced only
                 else if (pm == 0x5u) k_mega<false, 5, false, 0x5u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);
                 else k_mega<false, 5, false, 0x28u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);

@@ -34,8 +34,6 @@ struct RenderTuning {
     int extend_kind = -1;           // 0: one ray per thread (while-while), 1: persistent warp-scheduled k_extend_p, -1: auto (1 for big meshes without media)
     int prim_specialise = 2;        // 1: kernel variants compiled for the primitive types the scene contains; 2: also without wrapper handling for wrapper-free scenes; 0: generic
     int bvh_wide = -1;              // 4-wide collapse of a single wrapper-free instance's tree for the fused kernels: 1 build it where possible, 0 never, -1 auto (plain-sphere scenes and large meshes; RTB200_BVH_WIDE)
-    int wide_occ = 7;               // resident CTAs per SM of the 4-wide k_mega_r (5, 6 or 7; RTB200_WIDE_OCC)
-    int tile_order = 0;             // 1: path indices enumerate pixels in 32 x 16 tiles instead of rows (RTB200_TILE_ORDER, builds with -DRT_TILE_ORDER only; unmeasured experiment, same image)
     int extend_waves = 4;           // k_extend grid = 148 SMs * resident CTAs * extend_waves blocks (grid-stride over the slots)
 };
 
@@ -49,6 +47,15 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
 // accum -> Screen-layout doubles (vec3.rs:89-107), rows >= rendered_rows stay 0
 cudaError_t launch_resolve(const int64_t* d_accum, double* d_screen, int32_t width, int32_t height, int32_t spp, int32_t rendered_rows,
                            cudaStream_t stream);
+
+// Sum of the shards' accumulators + resolve in one pass; the pointers may address peer GPUs' memory (P2P over NVLink).
+#define RT_MAX_GPUS 16
+struct AccumShards {
+    const int64_t* p[RT_MAX_GPUS];
+    int32_t n;
+};
+cudaError_t launch_reduce_resolve(const AccumShards& shards, int64_t* d_sum_out, uint8_t* d_screen_u8, double* d_screen_f64, int32_t W, int32_t H, int32_t spp,
+                                  int32_t rows, cudaStream_t stream);
 
 // world.hit for n rays (device pointers)
 cudaError_t launch_trace_batch(const DeviceScene& scene, const rt_ray* d_rays, int64_t n, double t_min, double t_max, int32_t flags, uint64_t seed,

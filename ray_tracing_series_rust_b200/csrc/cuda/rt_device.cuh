@@ -250,7 +250,7 @@ RT_DEV double tri_t(const Ray& r, const DTri* __restrict__ tp, double t_min, dou
     const D3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q0.w, q1.x, q1.y), v2 = mk3(q1.z, q1.w, q2.x), n = mk3(q2.y, q2.z, q2.w);
     const double nd = dot(n, r.d);
     if (fabs(nd) < 0.0001) return RT_INF;
-    const double dd = -dot(n, v0);
+    const double dd = __ldg(&tp->dd); // -(n . v0) with the exact f64 vertex (rt_types.h DTri)
     const double t = -(dot(n, r.o) + dd) / nd;
     if (t < t_min || t > t_max) return RT_INF;
     const D3 p = ray_at(r, t);
@@ -509,8 +509,8 @@ RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestH
 
 // ------------------------------------------------------------------ 4-wide walk (rt_types.h RT_WIDE_EMPTY, host/bvh_wide.hpp)
 // One 128-byte node = four child boxes in SoA form + four references.  The children that the ray's interval reaches are
-// sorted by entry distance (five compare-exchanges on 64-bit keys = distance bits << 32 | reference); the nearest becomes
-// `cur`, the others are pushed far-to-near.  Leaves travel through the stack like nodes, and an entry whose entry distance
+// keyed by entry distance (64-bit keys = distance bits << 32 | reference); three compare-exchanges find the nearest, which becomes
+// `cur`, the others are pushed.  Leaves travel through the stack like nodes, and an entry whose entry distance
 // has fallen behind closest_so_far is dropped when popped, so no primitive of a box that a nearer hit already culled is
 // tested.  Same closest hit as the binary walk (topology independent; ties by depth-first id in consider()).
 // Requires t_min >= 0 (distance bits are compared as unsigned integers).
@@ -578,21 +578,13 @@ RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit
             unsigned long long k1 = wide_key(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
             unsigned long long k2 = wide_key(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);
             unsigned long long k3 = wide_key(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, rf.w, f, tminf, tmaxf);
-#ifdef RT_WIDE_NEAREST_ONLY // experiment (make EXTRA=-DRT_WIDE_NEAREST_ONLY, tools/ab_libs.sh): only the nearest child is found, the others are pushed unordered
+            // Only the nearest child is found exactly (three compare-exchanges); k1..k3 are pushed as they are.  The full five-exchange
+            // sort (far-to-near pushes) measured 2.7 % slower on book-1 final and 3 % on the 871 200-triangle mesh (profiles/r2_00_ab.log):
+            // an entry that a nearer hit has culled is dropped when popped, so the order of the queued ones matters little.
             wide_ce(k0, k1); wide_ce(k2, k3); wide_ce(k0, k2);
-#else
-            wide_ce(k0, k1); wide_ce(k2, k3); wide_ce(k0, k2); wide_ce(k1, k3); wide_ce(k1, k2);
-#endif
             if (k3 != ~0ull) stack[sp++] = k3;
             if (k2 != ~0ull) stack[sp++] = k2;
             if (k1 != ~0ull) stack[sp++] = k1;
-#if defined(RT_WIDE_PREFETCH) && defined(__CUDA_ARCH__) // experiment: warm L1 with the node that is visited after the nearest child's subtree (1) / all queued nodes (2)
-            if (k1 != ~0ull && !((uint32_t)k1 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(MOTION ? mnodes4 + 16 * (size_t)(uint32_t)k1 : nodes4 + 8 * (size_t)(uint32_t)k1));
-#if RT_WIDE_PREFETCH > 1
-            if (k2 != ~0ull && !((uint32_t)k2 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k2));
-            if (k3 != ~0ull && !((uint32_t)k3 & RT_LEAF_FLAG)) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes4 + 8 * (size_t)(uint32_t)k3));
-#endif
-#endif
             cur = (k0 != ~0ull) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
         }
         if (cur != DONE) { // a leaf reference
@@ -636,30 +628,6 @@ RT_DEV void trace_instances(const DeviceScene& S, uint32_t i0, uint32_t i1, cons
         } else if (PM == 0x18u) trace_instance_spec<COUNT, PM>(S, i, r, t_min, best, cnt);
         else trace_instance<COUNT, PM>(S, i, r, t_min, best, cnt);
     }
-}
-
-// ------------------------------------------------------------------ path index -> pixel, tile order (experiment: -DRT_TILE_ORDER builds, RTB200_TILE_ORDER=1)
-// The default enumerates the rendered pixels row by row, so the ~100 consecutive path indices a warp works on at any time are a
-// 100 x 1 strip of one sample; in tile order they fall into one 32 x 16 tile (bands of 16 rows, cut into 32-pixel columns, a narrower
-// last column, a lower last band): a bijection of [0, W * rows) onto itself.  Path ids (Philox streams) are keyed by the pixel, so the
-// image does not depend on the order.
-RT_DEV uint32_t tile_order_pixel(uint32_t p, uint32_t W, uint32_t rows) {
-    const uint32_t TW = 32u, TH = 16u;
-    const uint32_t y0 = (p / (W * TH)) * TH;
-    const uint32_t hb = rows - y0 < TH ? rows - y0 : TH;
-    const uint32_t q = p - y0 * W; // inside the band: [0, hb * W)
-    const uint32_t wfull = (W / TW) * TW, full = wfull * hb;
-    uint32_t x, y;
-    if (q < full) {
-        const uint32_t tx = q / (TW * hb), r = q - tx * TW * hb;
-        y = r / TW;
-        x = tx * TW + (r - y * TW);
-    } else {
-        const uint32_t rw = W - wfull, r = q - full;
-        y = r / rw;
-        x = wfull + (r - y * rw);
-    }
-    return (y0 + y) * W + x;
 }
 
 // ------------------------------------------------------------------ hit record (hit.rs:9-18)

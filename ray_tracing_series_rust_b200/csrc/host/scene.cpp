@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/rtb200.h"
@@ -83,7 +84,12 @@ struct DeviceBuffers { // one grow-only device arena + one pinned staging buffer
     size_t staging_capacity = 0;
     DeviceScene scene;
     bool valid = false;
+    int device = 0;   // CUDA device the arena lives on (the device current at rt_scene_commit)
     size_t bytes = 0; // bytes uploaded by the last commit
+    uint64_t generation = 0; // bumped by every commit: replicas on other GPUs (rt_render_multi) compare it
+    // (offset of a pointer field inside DeviceScene, offset of its array inside the arena / staging buffer): lets a replica on
+    // another GPU re-base the same flattened bytes without running the flattener again
+    std::vector<std::pair<size_t, size_t>> layout;
     int64_t device_built_prims = 0; // primitives whose BVH the last commit built on the device (lbvh.cu)
     float device_build_ms = 0.f;
     void release() {
@@ -91,6 +97,51 @@ struct DeviceBuffers { // one grow-only device arena + one pinned staging buffer
         if (staging) cudaFreeHost(staging);
         arena = nullptr; staging = nullptr; capacity = 0; staging_capacity = 0;
         valid = false;
+    }
+};
+
+// Output side of rt_render / rt_render_multi, kept between calls (no cudaMalloc / cudaFree / pageable staging per render):
+// the accumulator and the byte Screen on the gathering GPU, one pinned host mirror of the byte Screen.
+struct RenderBuffers {
+    int64_t* d_accum = nullptr;
+    uint8_t* d_u8 = nullptr;
+    uint8_t* h_u8 = nullptr; // pinned
+    size_t cap = 0;          // elements (W * H * 3)
+    cudaStream_t stream = nullptr;
+    void release() {
+        if (d_accum) cudaFree(d_accum);
+        if (d_u8) cudaFree(d_u8);
+        if (h_u8) cudaFreeHost(h_u8);
+        if (stream) cudaStreamDestroy(stream);
+        d_accum = nullptr; d_u8 = nullptr; h_u8 = nullptr; stream = nullptr; cap = 0;
+    }
+};
+
+// The committed scene on one more GPU (rt_render_multi): same flattened bytes, pointers re-based into this GPU's arena.
+struct Replica {
+    int device = -1;
+    char* arena = nullptr;
+    size_t capacity = 0;
+    uint64_t generation = ~0ull;
+    DeviceScene scene;
+    Workspace* workspace = nullptr;
+    int64_t* d_accum = nullptr;
+    size_t accum_cap = 0;
+    cudaStream_t stream = nullptr;
+    bool peer_ok = false; // the gathering GPU can read this arena's accumulator directly
+    int64_t* d_stage = nullptr; // on the gathering GPU, only when peer access is unavailable
+    size_t stage_cap = 0;
+    void release() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (device >= 0) cudaSetDevice(device);
+        if (arena) cudaFree(arena);
+        if (d_accum) cudaFree(d_accum);
+        if (stream) cudaStreamDestroy(stream);
+        free_workspace(workspace);
+        cudaSetDevice(cur);
+        if (d_stage) cudaFree(d_stage);
+        arena = nullptr; d_accum = nullptr; stream = nullptr; workspace = nullptr; d_stage = nullptr;
     }
 };
 
@@ -112,8 +163,15 @@ struct rt_scene {
     DeviceBuffers dev;
     RenderTuning tuning;
     Workspace* workspace = nullptr;
+    RenderBuffers out;
+    std::vector<Replica> replicas; // GPUs 1 .. n-1 of rt_render_multi (GPU 0 is `dev`)
     std::shared_ptr<void> debug_flat; // rt_debug_host_scene: the host-flattened arrays handed to the caller
-    ~rt_scene() { dev.release(); free_workspace(workspace); }
+    ~rt_scene() {
+        for (Replica& r : replicas) r.release();
+        out.release();
+        dev.release();
+        free_workspace(workspace);
+    }
 };
 
 #define CHECK_SCENE(s) \
@@ -349,9 +407,11 @@ struct UploadPlan { // collects the flattened arrays, lays them out 256-byte ali
             if ((e = cudaMallocHost(&dev.staging, cap)) != cudaSuccess) return e;
             dev.staging_capacity = cap;
         }
+        dev.layout.clear();
         for (const Piece& p : pieces) {
             if (p.bytes) std::memcpy(dev.staging + p.offset, p.src, p.bytes);
             *p.dst = dev.arena + p.offset;
+            dev.layout.emplace_back((size_t)(reinterpret_cast<const char*>(p.dst) - reinterpret_cast<const char*>(&dev.scene)), p.offset);
         }
         if ((e = cudaMemcpy(dev.arena, dev.staging, total, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
         dev.bytes = total;
@@ -576,6 +636,8 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
                     DTri q;
                     for (int a = 0; a < 3; ++a) { q.v0[a] = (float)v0[a]; q.v1[a] = (float)v1[a]; q.v2[a] = (float)v2[a]; }
                     q.n[0] = (float)nx; q.n[1] = (float)ny; q.n[2] = (float)nz;
+                    q.dd = -((double)q.n[0] * v0[0] + (double)q.n[1] * v0[1] + (double)q.n[2] * v0[2]); // rounded normal, exact vertex (rt_types.h)
+                    q.pad_ = 0.0;
                     tris.push_back(q);
                 } break;
                 }
@@ -797,6 +859,8 @@ int32_t do_commit(rt_scene* s) {
     if (HF.mnodes4.empty()) D.mnodes4 = nullptr;
     if (HF.mnodes.empty()) D.mnodes = nullptr;
     set_scene_scalars(s, HF, D);
+    cudaGetDevice(&s->dev.device);
+    ++s->dev.generation;
     s->dev.valid = true;
     s->committed = true;
     return RT_OK;
@@ -818,8 +882,6 @@ rt_scene* rt_scene_create(void) {
     if ((e = std::getenv("RTB200_BVH_BUILDER"))) s->tuning.bvh_builder = (std::strcmp(e, "lbvh") == 0 || std::strcmp(e, "1") == 0) ? 1 : 0;
     if ((e = std::getenv("RTB200_BVH_DEVICE_MIN"))) s->tuning.bvh_device_min = std::atoi(e);
     if ((e = std::getenv("RTB200_BVH_WIDE"))) s->tuning.bvh_wide = std::atoi(e);
-    if ((e = std::getenv("RTB200_WIDE_OCC"))) s->tuning.wide_occ = std::atoi(e);
-    if ((e = std::getenv("RTB200_TILE_ORDER"))) s->tuning.tile_order = std::atoi(e);
     return s;
 }
 void rt_scene_destroy(rt_scene* s) { delete s; }
@@ -1164,36 +1226,245 @@ int32_t rt_resolve_device(const int64_t* d_accum, double* d_screen, int32_t widt
     return RT_OK;
 }
 
+// ---- rt_render / rt_render_multi: host-buffer entry points (what a Rust render_scene_gpu calls, world.rs:1181-1247)
+namespace {
+
+int32_t ensure_out_buffers(rt_scene* s, size_t n) {
+    RenderBuffers& o = s->out;
+    cudaError_t e;
+    if (!o.stream && (e = cudaStreamCreateWithFlags(&o.stream, cudaStreamNonBlocking)) != cudaSuccess) return fail_cuda(e, "stream");
+    if (n <= o.cap) return RT_OK;
+    cudaStream_t keep = o.stream;
+    o.stream = nullptr;
+    o.release();
+    o.stream = keep;
+    if ((e = cudaMalloc(&o.d_accum, n * sizeof(int64_t))) != cudaSuccess) return fail_cuda(e, "accumulator allocation");
+    if ((e = cudaMalloc(&o.d_u8, n)) != cudaSuccess) return fail_cuda(e, "screen allocation");
+    if ((e = cudaMallocHost(&o.h_u8, n)) != cudaSuccess) return fail_cuda(e, "pinned screen allocation");
+    o.cap = n;
+    return RT_OK;
+}
+
+// Screen bytes (every value is an integer 0..255, vec3.rs:89-107) -> the reference's f64 Colors
+void widen_screen(const uint8_t* src, double* dst, size_t n) {
+    for (size_t i = 0; i < n; ++i) dst[i] = (double)src[i];
+}
+
+// sum of the shards (own + peers) -> out buffers on the gathering GPU -> host
+int32_t gather_and_copy_out(rt_scene* s, const AccumShards& shards, const RenderJob& job, double* out_screen, int64_t* out_accum) {
+    RenderBuffers& o = s->out;
+    const size_t n = (size_t)job.width * job.height * 3;
+    cudaError_t e;
+    // one shard: its sums already are o.d_accum; several: summed in place over shard 0 (a thread reads element i of every shard before it writes it)
+    int64_t* sum_out = (out_accum && shards.n > 1) ? o.d_accum : nullptr;
+    if ((e = launch_reduce_resolve(shards, sum_out, out_screen ? o.d_u8 : nullptr, nullptr, job.width, job.height, job.spp_total, job.rows, o.stream)) != cudaSuccess)
+        return fail_cuda(e, "reduce + resolve");
+    if (out_screen && (e = cudaMemcpyAsync(o.h_u8, o.d_u8, n, cudaMemcpyDeviceToHost, o.stream)) != cudaSuccess) return fail_cuda(e, "screen copy");
+    if (out_accum && (e = cudaMemcpyAsync(out_accum, o.d_accum, n * sizeof(int64_t), cudaMemcpyDeviceToHost, o.stream)) != cudaSuccess) return fail_cuda(e, "accum copy");
+    if ((e = cudaStreamSynchronize(o.stream)) != cudaSuccess) return fail_cuda(e, "render sync");
+    if (out_screen) widen_screen(o.h_u8, out_screen, n);
+    return RT_OK;
+}
+
+RenderTuning tuning_for(const rt_scene* s, const rt_render_config* cfg) {
+    RenderTuning tune = s->tuning;
+    tune.timed_extend = (cfg->flags & RT_RENDER_TIMED_EXTEND) ? 1 : 0;
+    tune.count_events = (cfg->flags & RT_RENDER_COUNT_EVENTS) ? 1 : 0;
+    if (cfg->flags & RT_RENDER_FORCE_WAVEFRONT) tune.mode = RT_MODE_WAVEFRONT;
+    if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
+    if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
+    return tune;
+}
+
+} // namespace
+
 int32_t rt_render(rt_scene* s, const rt_render_config* cfg, double* out_screen, int64_t* out_accum, rt_stats* stats) {
     CHECK_SCENE(s);
     RenderJob job;
-    const int32_t r = make_job(s, cfg, job);
-    if (r != RT_OK) return r;
+    int32_t rc = make_job(s, cfg, job);
+    if (rc != RT_OK) return rc;
     const auto t0 = std::chrono::steady_clock::now();
     const size_t n = (size_t)job.width * job.height * 3;
-    int64_t* d_accum = nullptr;
-    double* d_screen = nullptr;
-    cudaError_t e = cudaMalloc(&d_accum, n * sizeof(int64_t));
-    if (e != cudaSuccess) return fail_cuda(e, "accumulator allocation");
+    if ((rc = ensure_out_buffers(s, n)) != RT_OK) return rc;
+    RenderBuffers& o = s->out;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(o.d_accum, 0, n * sizeof(int64_t), o.stream)) != cudaSuccess) return fail_cuda(e, "memset");
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if ((e = launch_render(s->dev.scene, job, tuning_for(s, cfg), o.d_accum, o.stream, stats, &s->workspace)) != cudaSuccess) return fail_cuda(e, "render");
+    AccumShards sh;
+    sh.n = 1;
+    sh.p[0] = o.d_accum;
+    if ((rc = gather_and_copy_out(s, sh, job, out_screen, out_accum)) != RT_OK) return rc;
+    if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RT_OK;
+}
+
+// ---- multi-GPU inside the library (SURVEY.md 8(b) n_gpus / shard_mode, 8(e)): one process, N devices
+namespace {
+
+bool multi_alias() { // test hook: every logical GPU is the scene's own device (separate arenas, accumulators and streams): 1-GPU boxes run the N-GPU logic
+    const char* e = std::getenv("RTB200_MULTI_ALIAS");
+    return e && std::atoi(e) != 0;
+}
+
+// logical GPU g (>= 1) -> physical device: the devices after the scene's own, wrapping around
+int32_t replica_device(const rt_scene* s, int g, int dev_count) { return multi_alias() ? s->dev.device : (s->dev.device + g) % dev_count; }
+
+int32_t ensure_replicas(rt_scene* s, int32_t n_gpus, size_t accum_elems) {
+    int dev_count = 0;
+    cudaError_t e = cudaGetDeviceCount(&dev_count);
+    if (e != cudaSuccess || dev_count < 1) return fail(RT_ERR_CUDA, "no CUDA device: librtb200 has no CPU fallback");
+    if (n_gpus > RT_MAX_GPUS) return fail(RT_ERR_INVALID, "n_gpus > 16");
+    if (n_gpus > dev_count && !multi_alias()) return fail(RT_ERR_INVALID, "n_gpus exceeds the visible CUDA devices");
+    if ((int)s->replicas.size() < n_gpus - 1) s->replicas.resize((size_t)n_gpus - 1);
+    int home = 0;
+    cudaGetDevice(&home);
     int32_t rc = RT_OK;
-    do {
-        if ((e = cudaMemset(d_accum, 0, n * sizeof(int64_t))) != cudaSuccess) { rc = fail_cuda(e, "memset"); break; }
-        rc = rt_render_device(s, cfg, d_accum, nullptr, stats);
-        if (rc != RT_OK) break;
-        if (out_screen) {
-            if ((e = cudaMalloc(&d_screen, n * sizeof(double))) != cudaSuccess) { rc = fail_cuda(e, "screen allocation"); break; }
-            rc = rt_resolve_device(d_accum, d_screen, job.width, job.height, job.spp_total, job.rows, nullptr);
-            if (rc != RT_OK) break;
-            if ((e = cudaMemcpy(out_screen, d_screen, n * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = fail_cuda(e, "screen copy"); break; }
+    for (int g = 1; g < n_gpus && rc == RT_OK; ++g) {
+        Replica& r = s->replicas[(size_t)g - 1];
+        const int dev = replica_device(s, g, dev_count);
+        if (r.device != dev) { r.release(); r = Replica(); r.device = dev; }
+        if ((e = cudaSetDevice(dev)) != cudaSuccess) { rc = fail_cuda(e, "cudaSetDevice"); break; }
+        if (!r.stream && (e = cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = fail_cuda(e, "replica stream"); break; }
+        if (r.generation != s->dev.generation) { // upload the committed bytes (still in the pinned staging buffer) to this GPU
+            if (s->dev.bytes > r.capacity) {
+                if (r.arena) cudaFree(r.arena);
+                r.arena = nullptr; r.capacity = 0;
+                const size_t cap = s->dev.bytes + s->dev.bytes / 4 + 4096;
+                if ((e = cudaMalloc(&r.arena, cap)) != cudaSuccess) { rc = fail_cuda(e, "replica arena"); break; }
+                r.capacity = cap;
+            }
+            if ((e = cudaMemcpyAsync(r.arena, s->dev.staging, s->dev.bytes, cudaMemcpyHostToDevice, r.stream)) != cudaSuccess) { rc = fail_cuda(e, "replica upload"); break; }
+            r.generation = s->dev.generation;
         }
-        if (out_accum) {
-            if ((e = cudaMemcpy(out_accum, d_accum, n * sizeof(int64_t), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = fail_cuda(e, "accum copy"); break; }
+        if (accum_elems > r.accum_cap) {
+            if (r.d_accum) cudaFree(r.d_accum);
+            r.d_accum = nullptr; r.accum_cap = 0;
+            if ((e = cudaMalloc(&r.d_accum, accum_elems * sizeof(int64_t))) != cudaSuccess) { rc = fail_cuda(e, "replica accumulator"); break; }
+            r.accum_cap = accum_elems;
         }
-    } while (0);
-    cudaFree(d_accum);
-    if (d_screen) cudaFree(d_screen);
-    if (rc == RT_OK && stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        // scalars (camera, background, flags) follow the primary scene; pointers are re-based into this arena
+        r.scene = s->dev.scene;
+        for (const auto& fo : s->dev.layout) {
+            const char** field = reinterpret_cast<const char**>(reinterpret_cast<char*>(&r.scene) + fo.first);
+            if (*field) *field = r.arena + fo.second;
+        }
+        // peer access: the gathering GPU (the scene's own) reads this accumulator in k_reduce_resolve
+        r.peer_ok = dev == s->dev.device;
+        if (!r.peer_ok) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, s->dev.device, dev);
+            if (can) {
+                cudaSetDevice(s->dev.device);
+                e = cudaDeviceEnablePeerAccess(dev, 0);
+                if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) r.peer_ok = true;
+                (void)cudaGetLastError();
+            }
+            if (!r.peer_ok && accum_elems > r.stage_cap) { // no P2P route: the shard is copied next to the gathering GPU's own first
+                cudaSetDevice(s->dev.device);
+                if (r.d_stage) cudaFree(r.d_stage);
+                r.d_stage = nullptr; r.stage_cap = 0;
+                if ((e = cudaMalloc(&r.d_stage, accum_elems * sizeof(int64_t))) != cudaSuccess) { rc = fail_cuda(e, "gather staging"); break; }
+                r.stage_cap = accum_elems;
+            }
+        }
+    }
+    cudaSetDevice(home);
     return rc;
+}
+
+} // namespace
+
+int32_t rt_scene_commit_multi(rt_scene* s, int32_t n_gpus) {
+    CHECK_SCENE(s);
+    if (n_gpus < 1) return fail(RT_ERR_INVALID, "n_gpus < 1");
+    const int32_t rc = do_commit(s);
+    if (rc != RT_OK) return rc;
+    return ensure_replicas(s, n_gpus, 0);
+}
+
+int32_t rt_render_multi(rt_scene* s, const rt_render_config* cfg, int32_t n_gpus, int32_t shard_mode, double* out_screen, int64_t* out_accum, rt_stats* stats) {
+    CHECK_SCENE(s);
+    if (n_gpus < 1) return fail(RT_ERR_INVALID, "n_gpus < 1");
+    if (shard_mode != RT_SHARD_SAMPLES && shard_mode != RT_SHARD_TILES) return fail(RT_ERR_INVALID, "shard_mode must be RT_SHARD_SAMPLES or RT_SHARD_TILES");
+    if (n_gpus == 1) return rt_render(s, cfg, out_screen, out_accum, stats);
+    RenderJob job;
+    int32_t rc = make_job(s, cfg, job);
+    if (rc != RT_OK) return rc;
+    if (job.tile_count > 1) return fail(RT_ERR_INVALID, "rt_render_multi shards the image itself: RT_RENDER_TILE_SHARD must not be set");
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t n = (size_t)job.width * job.height * 3;
+    if ((rc = ensure_out_buffers(s, n)) != RT_OK) return rc;
+    if ((rc = ensure_replicas(s, n_gpus, n)) != RT_OK) return rc;
+    const RenderTuning tune = tuning_for(s, cfg);
+    // shard g: samples [b + g * S / N, b + (g + 1) * S / N) of every pixel, or every sample of the 4-row bands b with b % N == g
+    std::vector<RenderJob> jobs((size_t)n_gpus, job);
+    const int32_t S = job.sample_end - job.sample_begin;
+    for (int g = 0; g < n_gpus; ++g) {
+        if (shard_mode == RT_SHARD_SAMPLES) {
+            jobs[(size_t)g].sample_begin = job.sample_begin + (int32_t)(((int64_t)S * g) / n_gpus);
+            jobs[(size_t)g].sample_end = job.sample_begin + (int32_t)(((int64_t)S * (g + 1)) / n_gpus);
+        } else {
+            jobs[(size_t)g].tile_rank = g;
+            jobs[(size_t)g].tile_count = n_gpus;
+        }
+    }
+    std::vector<rt_stats> st((size_t)n_gpus);
+    std::vector<cudaError_t> errs((size_t)n_gpus, cudaSuccess);
+    auto run = [&](int g) {
+        rt_stats& out = st[(size_t)g];
+        std::memset(&out, 0, sizeof out);
+        cudaError_t e;
+        if (g == 0) {
+            RenderBuffers& o = s->out;
+            if ((e = cudaSetDevice(s->dev.device)) == cudaSuccess && (e = cudaMemsetAsync(o.d_accum, 0, n * sizeof(int64_t), o.stream)) == cudaSuccess)
+                e = launch_render(s->dev.scene, jobs[0], tune, o.d_accum, o.stream, &out, &s->workspace);
+        } else {
+            Replica& r = s->replicas[(size_t)g - 1];
+            if ((e = cudaSetDevice(r.device)) == cudaSuccess && (e = cudaMemsetAsync(r.d_accum, 0, n * sizeof(int64_t), r.stream)) == cudaSuccess)
+                e = launch_render(r.scene, jobs[(size_t)g], tune, r.d_accum, r.stream, &out, &r.workspace);
+        }
+        errs[(size_t)g] = e;
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int g = 1; g < n_gpus; ++g) pool.emplace_back(run, g);
+        run(0); // launch_render returns after its stream has drained
+        for (std::thread& th : pool) th.join();
+    }
+    cudaSetDevice(s->dev.device);
+    for (int g = 0; g < n_gpus; ++g)
+        if (errs[(size_t)g] != cudaSuccess) return fail_cuda(errs[(size_t)g], "render (multi-GPU shard)");
+    AccumShards sh;
+    sh.n = n_gpus;
+    sh.p[0] = s->out.d_accum;
+    for (int g = 1; g < n_gpus; ++g) {
+        Replica& r = s->replicas[(size_t)g - 1];
+        if (r.peer_ok) {
+            sh.p[g] = r.d_accum;
+        } else {
+            const cudaError_t e = cudaMemcpyPeerAsync(r.d_stage, s->dev.device, r.d_accum, r.device, n * sizeof(int64_t), s->out.stream);
+            if (e != cudaSuccess) return fail_cuda(e, "peer copy");
+            sh.p[g] = r.d_stage;
+        }
+    }
+    if ((rc = gather_and_copy_out(s, sh, job, out_screen, out_accum)) != RT_OK) return rc;
+    if (stats) {
+        *stats = st[0];
+        for (int g = 1; g < n_gpus; ++g) {
+            const rt_stats& a = st[(size_t)g];
+            stats->paths += a.paths; stats->segments += a.segments; stats->box_tests += a.box_tests; stats->medium_queries += a.medium_queries;
+            for (int k = 0; k < 8; ++k) stats->prim_tests[k] += a.prim_tests[k];
+            for (int k = 0; k < 5; ++k) stats->scatters[k] += a.scatters[k];
+            stats->iterations = std::max(stats->iterations, a.iterations);
+            stats->kernel_launches += a.kernel_launches;
+            stats->ms_device = std::max(stats->ms_device, a.ms_device); // the slowest shard
+            stats->ms_extend = std::max(stats->ms_extend, a.ms_extend);
+        }
+        stats->kernel_launches += 1; // k_reduce_resolve
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return RT_OK;
 }
 
 int32_t rt_write_ppm(const char* path, const double* screen, int32_t width, int32_t height) {

@@ -55,7 +55,12 @@ struct alignas(16) DMoving { double c0[3]; double dc[3]; double t0, dt, r, pad_;
 struct alignas(8) DGravity { double x, z, r; int32_t table_off; int32_t idx0; int32_t n; int32_t pad_; }; // hit.rs:330-336, window of `stored`
 struct alignas(16) DRect { double a0, a1, b0, b1, k; int32_t axis; int32_t pad_; };    // hit.rs:446-453 (axis 2 = Xy, 1 = Xz, 0 = Yz)
 struct alignas(16) DBox { double p0[3]; double p1[3]; };                              // hit.rs:713-717
-struct alignas(16) DTri { float v0[3], v1[3], v2[3], n[3]; };                          // hit.rs:87-93 (unit normal precomputed, hit.rs:96-107)
+// hit.rs:87-93.  64 bytes = two whole sectors: f32 vertices and f32 unit normal n (hit.rs:96-107, computed in f64, then rounded), and the
+// plane offset dd = -(n . v0) in f64, evaluated from the ROUNDED normal and the EXACT f64 vertex: the plane n . x + dd = 0 then passes
+// through the reference's v0 exactly and only its tilt (6e-8 rad) differs, so t agrees to ~1e-7 relative for rays of any length (with
+// dd recomputed from the f32 vertex the plane itself was displaced by the vertex rounding, ~1e-6 absolute: 2e-5 relative on t = 0.05).
+// The f32 vertices serve the three edge tests only.
+struct alignas(16) DTri { float v0[3], v1[3], v2[3], n[3]; double dd; double pad_; };
 
 struct PrimMeta { uint32_t mat_id; uint32_t prim_id; }; // per primitive, same order as its typed buffer
 

@@ -55,10 +55,6 @@ extern "C" {
 
 uint64_t emul_sizeof_device_scene(void) { return sizeof(DeviceScene); }
 
-void emul_tile_order(uint32_t W, uint32_t rows, uint32_t* out) {
-    for (uint32_t p = 0; p < W * rows; ++p) out[p] = tile_order_pixel(p, W, rows);
-}
-
 // wide != 0: the main world through Instance::root4 (world_hit<..., WIDE = true>, what k_extend<..., WIDE> runs); needs t_min >= 0.
 // counts (may be null): [0] boxes tested, [1] primitives tested, summed over the batch
 int32_t emul_trace_batch(const void* scene, const rt_ray* rays, int64_t n, double t_min, double t_max, int32_t flags, uint64_t seed, int32_t wide,

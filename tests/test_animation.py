@@ -29,13 +29,26 @@ def test_progressive_resume_is_exact(tmp_path):
     ck = str(tmp_path / "still")
     p = animation.ProgressiveRender(fake_chunk(shape), shape, 23, chunk=4, checkpoint=ck, every=2)
     p.run(max_chunks=3)                         # "crash" after 3 chunks: only the checkpoint of chunk 2 is on disk
-    assert p.done == 12 and json.load(open(ck + ".json"))["samples_done"] == 8
+    assert p.done == 12 and int(np.load(ck + ".npz")["samples_done"]) == 8
     q = animation.ProgressiveRender(fake_chunk(shape), shape, 23, chunk=4, checkpoint=ck, every=2)
     assert q.done == 8 and not q.finished
     acc = q.run()
     assert q.finished and np.array_equal(acc, one_shot)
-    assert json.load(open(ck + ".json"))["samples_done"] == 23 and np.array_equal(np.load(ck + ".npy"), one_shot)
-    assert not [f for f in os.listdir(tmp_path) if ".tmp" in f]
+    z = np.load(ck + ".npz")
+    assert int(z["samples_done"]) == 23 and np.array_equal(z["accum"], one_shot)
+    assert sorted(os.listdir(tmp_path)) == ["still.npz"]  # ONE file: accumulator and sample count cannot be torn apart
+    # a crash while the next checkpoint is being written (temporary present, rename not done) leaves the old pair intact
+    q.done, q.accum = 19, fake_chunk(shape)(0, 19)
+    real_replace = os.replace
+    try:
+        os.replace = lambda a, b: (_ for _ in ()).throw(OSError("crash before rename"))
+        with pytest.raises(OSError):
+            q.save()
+    finally:
+        os.replace = real_replace
+    again = animation.ProgressiveRender(fake_chunk(shape), shape, 23, chunk=4, checkpoint=ck)
+    assert again.done == 23 and np.array_equal(again.accum, one_shot)
+    os.remove(ck + ".tmp.npz")
     # a finished checkpoint resumes to a no-op; another render's checkpoint is refused
     r = animation.ProgressiveRender(lambda a, b: 1 / 0, shape, 23, chunk=4, checkpoint=ck)
     assert r.finished and np.array_equal(r.run(), one_shot)

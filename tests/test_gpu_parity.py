@@ -420,24 +420,6 @@ def test_wide_bvh_walk_is_bit_identical_to_the_pair_walk(orc, scene_id, param, e
     o.close()
 
 
-@pytest.mark.parametrize("scene_id,flags", [(5, 0), (6, 0), (4, 4), (13, 4), (14, 4)])
-def test_wide_bvh_walk_in_the_wavefront_kernels(scene_id, flags):
-    # rt_scene_set_bvh_width(4) forces the 4-wide collapse for every main-world instance; the wavefront kernels
-    # (k_extend<..., WIDE>: media scenes 5 / 6 by RT_MODE_AUTO, the others with flags = 4 = force wavefront) then walk it.
-    # Same image, bit for bit, as the sibling-pair walk (CPU counterpart: tests/test_host_emul.py).
-    acc = {}
-    cfg = capi.make_config(80, 1.0 if scene_id in (4, 5, 6, 14) else 1.5, 5, 50, seed=12, flags=flags)
-    for width in (2, 4):
-        g = rtb.new_scene()
-        g.world_build(scene_id, 0xB001, 40 if scene_id == 14 else 0)
-        g.set_bvh_width(width)
-        g.commit()
-        _, acc[width], st = g.render(cfg, want_accum=True)
-        assert st["iterations"] > 1  # wavefront
-        g.close()
-    assert np.array_equal(acc[2], acc[4]) and acc[2].any()
-
-
 def test_tile_sharding_is_bit_identical_and_matches_oracle(orc):
     # SURVEY.md 8(e) tile sharding: 4-row bands dealt round-robin; H = 53 (not a multiple of 4), 3 shards, both render modes
     from ray_tracing_series_rust_b200 import sharding
