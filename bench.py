@@ -5,14 +5,16 @@
 
 A "step" is one complete render of the workload (every pixel, every sample, depth 50) through
 librtb200.so.  `value` = camera paths per second over all ranks with the scene already resident in
-HBM; `e2e` = the same through the host-buffer C-ABI call a Rust host would make (rt_scene_commit:
-flatten + BVH build + H2D upload, rt_render: kernels + D2H of the Screen), all inside the timed region.
+HBM; `e2e` = the same through the host-buffer plugin call a Rust host would make - rt_scene_commit
+(flatten + BVH build + H2D upload) + rt_render(host Screen buffer) at N = 1, rt_scene_commit_multi +
+rt_render_multi (one process driving all N GPUs, peer-memory reduce + resolve) at N > 1 - with every
+copy inside the timed region.
 
-Multi-GPU (torchrun, one rank per GPU): every rank renders its own sample range of ONE image
-(Philox streams are keyed by the global sample index), then the int64 accumulators are summed with one
-NCCL reduce to rank 0, which resolves the image.  Default scaling is weak (each rank renders the
-workload's full sample count, i.e. the N-GPU image has N x spp samples); --scaling strong splits the
-workload's own spp.
+Multi-GPU (torchrun, one rank per GPU): STRONG scaling by default - the workload's own spp (500 for
+book-1 final) is split into N sample ranges of ONE image (Philox streams are keyed by the global sample
+index), the int64 accumulators are summed with one NCCL reduce to rank 0, which resolves the image; the
+line also carries `also.book2_final_strong`, the full 10 000-spp book-2 final split the same way.
+--scaling weak renders the full spp on every rank (an N x spp image).
 
 --impl reference times the CPU restatement of the reference (oracle/, all host threads) on a bounded
 sample of the same workload: the reference itself is Rust and cannot be built in this image.
@@ -123,11 +125,14 @@ def oracle_counts_per_segment(st):
             "bytes_per_segment": B_NODE * v + prim_bytes + B_STATE}
 
 
-def run_cpu_sample(wl, target_s, threads, seed=1):
-    """Times the oracle (all host threads) on a bounded sample: the full image at a reduced spp."""
+def run_cpu_sample(wl, target_s, threads, seed=1, width=None):
+    """Times the oracle (all host threads) on a bounded sample: the full image (or, with `width`, the same view at a lower
+    resolution) at a reduced spp."""
     import oracle
     from ray_tracing_series_rust_b200 import capi
     sid, sseed, param, W, aspect, spp, depth, cam, desc = wl
+    full_W = W
+    W = width or W
     s = build_scene(oracle, oracle.new_scene, wl)
     s.commit()
     # calibrate with 1 spp, then pick the spp that fills ~target_s
@@ -140,7 +145,7 @@ def run_cpu_sample(wl, target_s, threads, seed=1):
     _, _, st = s.render(capi.make_config(W, aspect, use, depth, seed=seed, threads=threads))
     dt = time.time() - t0
     return {"paths_per_s": st["paths"] / dt, "seconds": dt, "spp": use, "stats": st,
-            "sample": f"full {W}x{H} image at {use} of {spp} spp, depth {depth} ({st['paths']} paths, {dt:.1f} s)"}
+            "sample": f"{'full' if W == full_W else 'same view at'} {W}x{H} image at {use} of {spp} spp, depth {depth} ({st['paths']} paths, {dt:.1f} s)"}
 
 
 def reference_arm(args, wl, name):
@@ -179,7 +184,7 @@ def main():
     ap.add_argument("--impl", default="rtb200", choices=["rtb200", "reference"])
     ap.add_argument("--workload", default="book1_final", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (marks the line as a non-headline configuration)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--sharding", default="samples", choices=["samples", "tiles"],
                     help="N>1: sample ranges of every pixel (default) or 4-row tile bands dealt round-robin (SURVEY 8e alternative)")
     ap.add_argument("--slots", type=int, default=0, help="resident path slots of the wavefront (0 = library default)")
@@ -288,32 +293,11 @@ def main():
     ms_per_step = ms_total / args.steps
     value = paths_all * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host-buffer C-ABI call path, commit (flatten + BVH + H2D) + render + D2H, per step
-    barrier()
-    e2e_ms = []
-    scene_bytes = 0
-    for k in range(max(2, min(args.steps, 3)) + 1):
-        barrier()
-        t0 = time.time()
-        scene.commit()
-        t_commit = time.time()
-        cfg = capi.make_config(W, aspect, spp_total, depth, seed=100 + k, sample_begin=s_begin, sample_end=s_end, flags=shard_flags)
-        accum.zero_()
-        st = capi.Stats()
-        api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
-        sharding.reduce_accumulators(accum, dst=0)
-        if rank == 0:
-            api.check(api.resolve_device(C.c_void_p(accum.data_ptr()), C.c_void_p(screen.data_ptr()), W, H, spp_total, H, C.c_void_p(stream.cuda_stream)))
-            host_screen.copy_(screen, non_blocking=True)
-        barrier()
-        if k > 0:
-            e2e_ms.append(1e3 * (time.time() - t0))
-        if rank == 0 and os.environ.get("RTB200_BENCH_DEBUG"):
-            print(f"[e2e] step {k}: {1e3 * (time.time() - t0):.1f} ms (commit {1e3 * (t_commit - t0):.1f}, render {st.ms_total:.1f} / device {st.ms_device:.1f})", file=sys.stderr)
-    e2e_local = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_local, op=dist.ReduceOp.MAX)
-    e2e_value = paths_all / (float(e2e_local.item()) * 1e-3)
+    # ---- book-2 final, the other north-star render, split the same way (all ranks; one timed render after a short warm-up)
+    book2 = None
+    if not args.no_extra and args.workload == "book1_final" and not args.spp and args.scaling == "strong":
+        book2 = strong_render(api, rtb, capi, sharding, torch, dist, stream, "book2_final", rank, world, barrier)
+
     out_hc = (C.c_int64 * 16)()
     api.lib.rt_scene_host_check.restype = C.c_int32
     api.lib.rt_scene_host_check(C.c_void_p(scene.h), out_hc)
@@ -322,9 +306,37 @@ def main():
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-        dist.destroy_process_group()  # every collective is done; rank 0 continues alone (roofline, CPU baseline)
+        dist.destroy_process_group()  # every collective is done; rank 0 continues alone (e2e, roofline, CPU baseline)
     if rank != 0:
         return 0
+
+    # ---- e2e: the plugin call with HOST buffers, as a Rust render_scene_gpu would make it (world.rs:1181 seam), rank 0 alone:
+    # rt_scene_commit[_multi] (flatten + BVH + H2D of the scene to every GPU) + rt_render[_multi] (kernels on all N GPUs, peer-memory
+    # reduce + resolve, D2H of the Screen into a pageable numpy buffer), wall clock around the calls, same spp as the timed steps
+    n_dev = torch.cuda.device_count()
+    e2e_gpus = world if n_dev >= world else 1
+    e2e_ms, e2e_commit_ms = [], []
+    cfg_e = capi.make_config(W, aspect, spp_total, depth, seed=100)
+    for k in range(args.warmup + args.steps):
+        cfg_e.seed = 100 + k
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if e2e_gpus > 1:
+            scene.commit_multi(e2e_gpus)
+            t1 = time.perf_counter()
+            scr_e, _, st_e = scene.render_multi(cfg_e, e2e_gpus, capi.RT_SHARD_SAMPLES)
+        else:
+            scene.commit()
+            t1 = time.perf_counter()
+            scr_e, _, st_e = scene.render(cfg_e)
+        t2 = time.perf_counter()
+        if k >= args.warmup:
+            e2e_ms.append(1e3 * (t2 - t0))
+            e2e_commit_ms.append(1e3 * (t1 - t0))
+            launches_e2e = st_e["kernel_launches"] + 1
+    e2e_ms_avg = sum(e2e_ms) / len(e2e_ms)
+    e2e_value = W * H * spp_total / (e2e_ms_avg * 1e-3)
 
     # ---- roofline of the dominant kernel, rank 0.  RT_MODE_AUTO picks the fused persistent kernel (k_mega: one launch
     # per render, path state in registers) or the wavefront (k_extend dominant: CUDA events around every launch).
@@ -362,7 +374,10 @@ def main():
     own_bps = B_NODE * st_c["box_tests"] / own_seg + prim_b * st_c["prim_tests"][0] / own_seg + state_b
     achieved = own_bps * seg_per_launch / (ext_ms_avg * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_mega (fused persistent: generate + world.hit + scatter)" if fused else "k_extend",
+        # What binds is SIMT issue (divergent incoherent rays), not DRAM: the scene is L1/L2 resident (`traffic` is a few 1e-5 of the
+        # algorithmic bytes).  achieved / peak / frac stay the SURVEY 8(d) HBM figure (algorithmic bytes over measured copy bandwidth);
+        # `frac_binding` = lane-issue efficiency of the same kernel from the committed ncu capture (issue-active x active threads / 32).
+        "bound": "issue", "kernel": "k_mega (fused persistent: generate + world.hit + scatter)" if fused else "k_extend",
         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
         "peak_source": hbm_src,
         "bytes_per_segment": own_bps,
@@ -401,8 +416,14 @@ def main():
         try:
             pj = json.load(open(prof)).get(args.workload, {}).get("fused" if fused else "wavefront", {})
             roofline["traffic"] = pj.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = f"profiles/extend_traffic.json (ncu --set full capture {pj.get('capture', '?')}, kernel {pj.get('kernel', '?')}); not re-measured by this run"
             if "ncu" in pj:
                 roofline["ncu"] = pj["ncu"]  # issue-slot utilisation, active threads per instruction, stalls: what actually bounds the kernel
+                ia, th = pj["ncu"].get("issue_active_pct"), pj["ncu"].get("threads_per_inst")
+                if ia and th:
+                    roofline["frac_binding"] = (ia / 100.0) * (th / 32.0)
+                    roofline["binding"] = {"roof": "SIMT lane-issue slots (4 schedulers x 32 lanes per SM per cycle)", "issue_active": ia / 100.0, "active_threads_per_instruction": th,
+                                           "frac": (ia / 100.0) * (th / 32.0)}
         except Exception:
             pass
 
@@ -410,7 +431,7 @@ def main():
         "metric": "paths/s", "value": value, "unit": "paths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": (value / README_BOOK1_10T_PATHS_PER_S) if (args.workload == "book1_final" and not args.spp) else None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64 geometry / f32 slabs+colour", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "image": [W, H], "spp_per_gpu": s_end - s_begin, "spp_total": spp_total, "max_depth": depth,
                    "paths_per_step": paths_all, "segments_per_path": segments / max(1, paths_local),
                    "sharding": ("single GPU" if world == 1 else ("4-row tile bands round-robin + one NCCL int64 reduce (disjoint pixels) to rank 0" if shard_flags
@@ -419,17 +440,68 @@ def main():
                    "l2": "flushed between timed steps (256 MiB memset, untimed); path state > L2",
                    "vs_baseline_note": "README.md:23 146.440 s on 10 threads of an unspecified CPU => 1.456e6 paths/s (derived)",
                    "render_wall_s": ms_per_step * 1e-3, "commit_s": commit_s, "wall_s_timed_region": t_wall},
-        "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": W * H * 3 * 8,
-                "ms_per_step": float(e2e_local.item()), "includes": "rt_scene_commit (flatten+BVH+upload) + render + reduce + resolve + D2H of the Screen"},
+        "e2e": {"value": e2e_value, "unit": "paths/s", "h2d_bytes_per_step": scene_bytes * e2e_gpus, "d2h_bytes_per_step": W * H * 3,
+                "ms_per_step": e2e_ms_avg, "commit_ms": sum(e2e_commit_ms) / len(e2e_commit_ms), "steps": len(e2e_ms), "n_gpus": e2e_gpus,
+                "call": ("rt_scene_commit + rt_render" if e2e_gpus == 1 else "rt_scene_commit_multi + rt_render_multi (one process, peer-memory reduce + resolve)") +
+                        " with a host f64 Screen buffer (numpy, pageable); wall clock around the two calls",
+                "d2h_note": "the Screen crosses PCIe as bytes (every value is an integer 0..255) and is widened to the reference's f64 Colors on the host",
+                "gpu_launches_per_step": int(launches_e2e)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
     if not args.no_extra and world == 1 and args.workload == "book1_final" and not args.spp:
-        line["also"] = extra_workloads(api, rtb, capi, stream)
+        line["also"] = extra_workloads(api, rtb, capi, stream, args)
+    if book2 is not None:
+        line.setdefault("also", {})["book2_final_strong"] = book2
     print(json.dumps(line), flush=True)
     return 0
+
+
+def strong_render(api, rtb, capi, sharding, torch, dist, stream, name, rank, world, barrier):
+    """One full render of WORKLOADS[name] split into `world` sample ranges (strong scaling), timed on the device (max over ranks):
+    render_device + NCCL reduce + resolve.  Returns the record on rank 0, None elsewhere."""
+    sid, sseed, param, W, aspect, spp, depth, cam, desc = WORKLOADS[name]
+    s = rtb.new_scene()
+    s.world_build(sid, sseed, param)
+    s.commit()
+    H = s.image_height(capi.make_config(W, aspect, 1, depth))
+    accum = torch.zeros((H, W, 3), dtype=torch.int64, device="cuda")
+    screen = torch.zeros((H, W, 3), dtype=torch.float64, device="cuda")
+
+    def render(total, seed):
+        _, b, e = sharding.sample_range(total, rank, world, "strong")
+        cfg = capi.make_config(W, aspect, total, depth, seed=seed, sample_begin=b, sample_end=e)
+        accum.zero_()
+        st = capi.Stats()
+        if e > b:
+            api.check(api.render_device(s.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
+        sharding.reduce_accumulators(accum, dst=0)
+        if rank == 0:
+            api.check(api.resolve_device(C.c_void_p(accum.data_ptr()), C.c_void_p(screen.data_ptr()), W, H, total, H, C.c_void_p(stream.cuda_stream)))
+        return st.as_dict()
+    render(8 * world, 1)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    st = render(spp, 3)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    seg = torch.tensor([float(st["segments"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(seg, op=dist.ReduceOp.SUM)
+    s.close()
+    if rank != 0:
+        return None
+    t = float(ms.item()) * 1e-3
+    return {"description": desc, "n_gpus": world, "scaling": "strong", "spp_total": spp, "spp_per_gpu": spp / world, "paths": W * H * spp,
+            "render_wall_s": t, "host_wall_s": wall, "paths_per_s": W * H * spp / t, "segments_per_path": float(seg.item()) / (W * H * spp),
+            "timing": "CUDA events around render_device + NCCL int64 reduce + resolve, max over ranks; one full render after an 8-spp-per-GPU warm-up"}
 
 
 def run_animation(args, wl, api, rtb, capi, torch, dist, world, rank, local):
@@ -505,7 +577,7 @@ def run_animation(args, wl, api, rtb, capi, torch, dist, world, rank, local):
     return 0
 
 
-def extra_workloads(api, rtb, capi, stream):
+def extra_workloads(api, rtb, capi, stream, args=None):
     """One timed render each of the other BASELINE configs (single GPU), so every headline config has a
     measured paths/s in the round's bench record.  book2_final runs its full 10 000 spp only when a
     100-spp probe projects under 100 s; otherwise the probe is reported and flagged."""
@@ -536,7 +608,7 @@ def extra_workloads(api, rtb, capi, stream):
         del accum
     except Exception as e:
         out["bouncing_anim"] = {"error": str(e)}
-    for name in ("book1_shipped", "cornell_smoke", "book2_final", "mesh_room"):
+    for name in ("book1_shipped", "cornell_smoke", "mesh_room"):  # book2_final: see also.book2_final_strong (the full 10 000 spp)
         sid, sseed, param, W, aspect, spp, depth, cam, desc = WORKLOADS[name]
         try:
             s = rtb.new_scene()
@@ -574,6 +646,30 @@ def extra_workloads(api, rtb, capi, stream):
             del accum
         except Exception as e:  # a secondary workload must not take the headline line down
             out[name] = {"error": str(e)}
+    if args is not None and not args.no_cpu_baseline:
+        # the CPU restatement of the reference beside every config, all host cores, on a BOUNDED sample of each
+        # (full image at a reduced spp; paths/s does not depend on spp, so the full-config wall time is a linear extrapolation: flagged)
+        cpus = {}
+        per = max(3.0, min(8.0, args.cpu_seconds / 2))
+        for name in ("cornell_smoke", "book2_final", "mesh_room", "bouncing_anim"):
+            try:
+                wl = WORKLOADS[name]
+                if name == "mesh_room":
+                    # the reference builds its BVH by cloning the object list per node (bvh.rs:14-83): minutes for 871 200 triangles, so the
+                    # CPU sample uses the same room around a 131 072-triangle mesh (param 256) - per-path cost grows with log(triangles): optimistic for the CPU
+                    wl = wl[:2] + (256,) + wl[3:]
+                if name == "bouncing_anim":
+                    wl = wl[:2] + (0,) + wl[3:]  # one frame of the animation scene (param = frame count is a bench notion, not a scene size)
+                c = run_cpu_sample(wl, per, os.cpu_count() or 1, width=wl[3] // 4)  # a quarter of the width: the 1-spp calibration pass stays short
+                W, aspect, spp = wl[3], wl[4], wl[5]
+                full_paths = c["stats"]["paths"] / c["spp"] * 16.0 * spp * (WORKLOADS[name][2] if name == "bouncing_anim" else 1)
+                cpus[name] = {"value": c["paths_per_s"], "unit": "paths/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": c["sample"],
+                              "extrapolated_full_config_wall_s": full_paths / c["paths_per_s"], "extrapolated": True,
+                              "note": ("131 072-triangle stand-in mesh (see bench.py)" if name == "mesh_room" else
+                                       ("one frame (shutter [0, 10)), extrapolated to 240 frames; CPU commit / table integration not included" if name == "bouncing_anim" else ""))}
+            except Exception as e:
+                cpus[name] = {"error": str(e)}
+        out["cpu_baselines"] = cpus
     try:  # SURVEY.md 8(f) n1 / n2 on the mesh-room inputs: commit with the host SAH vs the device LBVH builder, text vs binary I/O
         import glob
         import numpy as np

@@ -104,7 +104,7 @@ def compare_hits(hg, ho, label=""):
 
 def assert_parity(hg, ho, label="", max_id_frac=0.0, max_tie_frac=0.0, max_t_frac=0.0, rays=None, require_hits=True):
     """max_t_frac: allowed fraction of rays whose t differs by more than 1e-5 relative — only for mesh
-    scenes (triangles are stored f32 on the device), and only at grazing incidence, which is checked."""
+    scenes (triangles are stored f32 on the device), and only at grazing incidence or on hits closer than 0.01 units, which is checked."""
     r = compare_hits(hg, ho, label)
     msg = {k: v for k, v in r.items() if k != "id_bad_idx"}
     if require_hits:
@@ -117,7 +117,11 @@ def assert_parity(hg, ho, label="", max_id_frac=0.0, max_tie_frac=0.0, max_t_fra
         bad = both & (np.abs(hg["t"] - ho["t"]) > T_REL * np.abs(ho["t"]))
         d = rays["d"][bad]
         cosi = np.abs((ho["normal"][bad] * d).sum(1)) / np.linalg.norm(d, axis=1)
-        assert np.all(cosi < 0.2), (msg, cosi)  # grazing incidence amplifies the f32 vertex rounding
+        length = np.abs(ho["t"][bad]) * np.linalg.norm(d, axis=1)
+        # the two documented classes of the f32 triangle storage (DESIGN.md divergence 7): grazing incidence amplifies the 6e-8 rad tilt of
+        # the f32 normal, and on a hit closer than 0.01 units (t just above t_min = 0.001) the tilt times the distance to the triangle's
+        # vertex (~1e-8 absolute) exceeds 1e-5 of such a t
+        assert np.all((cosi < 0.2) | (length < 0.01)), (msg, cosi, length)
     for k in ("normal", "uv", "front", "mat"):
         assert r[k] == 0, msg
     return r

@@ -192,10 +192,11 @@ def test_gpu_full_size_mesh_hits_equal_oracle_list_scan():
     assert os.path.exists(ply)
     o = oracle.new_scene()
     mesh = o.ply_load(ply, 100.0, o.lambertian((0.2, 0.2, 0.2)))  # TriangleModel::load_from_file(..., 100.0).to_hittable(), model.rs:13-76
+    light = o.diffuse_light((4, 4, 4))  # material ids in the order of stanford_dragon (world.rs:689-737): mesh, light, then the walls
     room = [o.xy_rect(-100, 100, -100, 100, -20, o.lambertian((0.8, 0.3, 0.3))), o.xy_rect(-100, 100, -100, 100, 20, o.lambertian((1, 1, 1))),
             o.xz_rect(-40, 40, -40, 40, 5, o.metal((0.3, 0.3, 0.3), 0.02)), o.xz_rect(-100, 100, -100, 100, 55, o.metal((1, 1, 1), 0.0)),
             o.yz_rect(-100, 100, -100, 100, -30, o.lambertian((0.3, 0.8, 0.3))), o.yz_rect(-100, 100, -100, 100, 30, o.lambertian((0.3, 0.3, 0.8))),
-            o.xz_rect(-100, 100, -100, 100, 55, o.diffuse_light((4, 4, 4)))]
+            o.xz_rect(-100, 100, -100, 100, 55, light)]
     o.set_root(o.list([mesh] + room))  # world.rs:740-747 order; the mesh as a list instead of BvhNode::from_list: same leaves, same ids
     o.set_camera((0, 20, 20), (0, 11, 0), (0, 1, 0), 60.0, 1.0, 0.0, 40.0, 0.0, 10.0)
     o.commit()
