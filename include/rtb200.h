@@ -203,6 +203,7 @@ typedef struct rt_render_config {
 #define RT_RENDER_COUNT_EVENTS 2    /* count BVH boxes tested / primitive tests on the device -> rt_stats */
 #define RT_RENDER_FORCE_WAVEFRONT 4 /* wavefront mode: k_extend + k_shade_all per iteration, per-material queues */
 #define RT_RENDER_FORCE_FUSED 8     /* fused mode: one persistent kernel, path state in registers */
+#define RT_RENDER_FORCE_POOL 16     /* pool mode: one persistent kernel, every warp runs a small wavefront of its own in shared memory */
 /* Tile sharding (the GPU analogue of the reference's row bands, world.rs:1198-1227): the image is cut
  * into bands of RT_TILE_ROWS rows; a call with RT_RENDER_TILE_SHARD(rank, count) in `flags` renders only the bands
  * b with b % count == rank (all samples of their pixels); the other pixels of out_accum / out_screen stay 0.  Path ids

@@ -709,6 +709,284 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
     if (lane_id() == 0 && segs) atomicAdd(&Q.stats[0], (unsigned long long)segs);
 }
 
+// ------------------------------------------------------------------ k_pool: warp-local wavefront in shared memory (RT_MODE_POOL)
+// k_mega keeps one path per lane in registers, so a warp's lanes wait for each other twice per segment: at the end of the BVH walk (the
+// longest ray of 32 decides) and in the shading code (32 lanes, 3-4 materials, rejection loops) - ncu: 11.3 of 32 lanes active per
+// instruction on book-1, 6.8 on the 871 200-triangle mesh.  The global wavefront (k_extend / k_shade_all) fixes the shading half with
+// per-material queues but pays 300 B of path state per segment through HBM / L2 and still walks one ray per lane to the end.
+// Here every WARP owns a pool of P paths in shared memory (~100 B of state per path) and small slot lists, all private to the warp (no
+// block-level synchronisation, no atomics besides the pixel sums), and alternates three phases:
+//   REGEN  ended slots get the next camera paths (pixel jitter + Camera::get_ray, world.rs:1212-1214) in full batches of 32
+//   TRACE  world.hit (world.rs:68): a lane that finishes its walk stores (t, primitive) in the slot, takes the next waiting ray from the
+//          list and goes on - the lanes stay busy as long as rays wait.  When the list runs dry and more than a quarter of the lanes
+//          idle, the warp goes shading; the walks still in flight stay in their lanes' registers and resume in the next TRACE phase
+//          (resumable walks as in k_mega_r), so no phase ever waits for its longest ray
+//   SHADE  finished slots are classified (miss / light / Lambertian / Metal+Dielectric / Isotropic; media are sampled here, all lanes
+//          together) into per-material lists, and each list is shaded in batches of 32: HitRecord rebuild + Material::scatter run
+//          material-coherent; survivors go back to the TRACE list, ended paths add their radiance to the pixel and go to REGEN
+// Per-path arithmetic, Philox streams and the integer pixel sums are those of the other two modes: the image is bit-identical.
+#define RT_POOL_MISS 0xffffffffu
+#define RT_POOL_IDX_BITS 26
+template <int P>
+struct alignas(16) WarpPool {
+    double ox[P], oy[P], oz[P], dx[P], dy[P], dz[P], time[P]; // the ray of the slot's current segment, world space
+    double best_t[P];                                        // closest_so_far of the finished world.hit
+    uint32_t best_ref[P];                                    // RT_POOL_MISS | type << 29 | side << 26 | index (type PRIM_MEDIUM: index = medium)
+    float tr[P], tg[P], tb[P];                               // throughput (world.rs:57 `product`)
+    uint32_t pixel[P], s_local[P];                           // path id = pixel * spp_total + sample_begin + s_local
+    uint32_t draw[P];                                        // Philox draw counter of the path
+    uint8_t segment[P], best_inst[P];
+    uint8_t q_trace[P], q_done[P], q_regen[P], q_mat[4][P];  // slot lists: waiting for world.hit / hit found / path ended / by material class
+};
+RT_DEV uint32_t lanes_below(uint32_t lane) { return (1u << lane) - 1u; }
+#ifdef RT_POOL_INLINE_RNG
+using PoolRng = PathRng;
+#else
+using PoolRng = PathRngOol; // one out-of-line Philox for the four phases: the warps of an SM sit in different phases, the instruction caches hold all of them
+#endif
+
+template <uint32_t PM, bool WIDE, bool MEDIA, bool GENERAL_MEDIA, bool XF, int P, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_pool(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q, int64_t* __restrict__ accum) {
+    static_assert(P <= 256 && P % 32 == 0, "slot ids are bytes");
+    extern __shared__ __align__(16) unsigned char pool_smem[];
+    WarpPool<P>& W = reinterpret_cast<WarpPool<P>*>(pool_smem)[threadIdx.x >> 5];
+    const unsigned full = 0xffffffffu;
+    const uint32_t lane = lane_id(), below = lanes_below(lane);
+    const uint32_t DONE = 0xffffffffu;
+    const bool planar = (PM & 0x18u) != 0 && (S.flags & 1u) != 0;
+    const uint32_t n_inst = XF ? S.n_main_instances : 1u;
+    // list lengths (warp-uniform)
+    uint32_t n_trace = 0, n_done = 0, n_regen = P, n_mat0 = 0, n_mat1 = 0, n_mat2 = 0, n_mat3 = 0;
+    for (uint32_t i = lane; i < (uint32_t)P; i += 32u) W.q_regen[i] = (uint8_t)i;
+    __syncwarp();
+    unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform: the warp's chunk of consecutive path indices
+    bool exhausted = false;
+    // the walk this lane has in flight
+    bool have = false;
+    uint32_t slot = 0, inst = 0, cur = DONE;
+    int sp = 0;
+    Ray r; // in the space of instance `inst`
+    r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.time = 0.0;
+    RayF f; f.idx = f.idy = f.idz = f.oodx = f.oody = f.oodz = 0.f;
+    RayPre pre; pre.a = 1.0; pre.inv_a = 1.0; pre.inv_d = mk3(0, 0, 0);
+    BestHit best;
+    best_init(best, RT_INF);
+    uint32_t stack[WIDE ? 1 : RT_STACK];
+    unsigned long long wstack[WIDE ? RT_WIDE_STACK : 1];
+    uint32_t my_segments = 0;
+    const uint32_t LOW = 16u;    // TRACE ends when no ray waits and at most LOW lanes still walk          (16 / 20 / 24 / 28: 101.2 / 102.1 / 103.0 / 104.0 ms, book-1 final)
+    const uint32_t REFILL = 12u; // while rays wait: lanes that must have finished before the warp refills (4 / 8 / 12 / 16: 103.4 / 103.0 / 102.5 / 102.1 ms)
+
+    for (;;) {
+        // ================================================================ REGEN
+        while (n_regen && !exhausted) {
+            const uint32_t take = n_regen < 32u ? n_regen : 32u, base = n_regen - take;
+            const unsigned long long avail = chunk_end - chunk_next;
+            unsigned long long second_base = 0;
+            if (avail < take) {
+                if (lane == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)J.chunk);
+                second_base = __shfl_sync(full, second_base, 0);
+            }
+            bool ok = false;
+            uint32_t sl = 0;
+            if (lane < take) {
+                const unsigned long long L = (lane < avail) ? chunk_next + lane : second_base + (lane - avail);
+                if (L < J.total_paths) {
+                    ok = true;
+                    sl = W.q_regen[base + lane];
+                    uint32_t s_local, pixel, draw0;
+                    split_path_index(L, J.npix_rendered, s_local, pixel);
+                    pixel = shard_pixel(J, pixel);
+                    const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
+                    const uint64_t path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
+                    const Ray cr = camera_first_ray<PoolRng>(S.cam, ii, j, J.W, J.H, J.seed, path_id, draw0); // world.rs:1212-1214
+                    W.ox[sl] = cr.o.x; W.oy[sl] = cr.o.y; W.oz[sl] = cr.o.z; W.dx[sl] = cr.d.x; W.dy[sl] = cr.d.y; W.dz[sl] = cr.d.z; W.time[sl] = cr.time;
+                    W.tr[sl] = 1.f; W.tg[sl] = 1.f; W.tb[sl] = 1.f;
+                    W.pixel[sl] = pixel; W.s_local[sl] = s_local; W.draw[sl] = draw0; W.segment[sl] = 0;
+                }
+            }
+            if (avail < take) { chunk_next = second_base + (take - avail); chunk_end = second_base + J.chunk; }
+            else chunk_next += take;
+            const unsigned okm = __ballot_sync(full, ok);
+            if (ok) W.q_trace[n_trace + __popc(okm & below)] = (uint8_t)sl;
+            n_trace += __popc(okm);
+            if ((uint32_t)__popc(okm) < take) exhausted = true; // path indices past the end: the pool drains from here on
+            n_regen = base;
+            __syncwarp();
+        }
+        if (exhausted) n_regen = 0; // slots without a path stay empty
+
+        // ================================================================ TRACE
+        for (;;) {
+            if (__ballot_sync(full, cur == DONE)) { // a lane finished its walk, or idles
+                bool setup = false, commit = false;
+                if (have && cur == DONE) {
+                    ++inst;
+                    if (XF && inst < n_inst) setup = true; // next instance of the main world (hit.rs:660-690: the list scan goes on with closest_so_far)
+                    else commit = true;
+                }
+                const unsigned cm = __ballot_sync(full, commit);
+                if (commit) { // world.hit of this slot is complete
+                    W.best_t[slot] = best.t;
+                    W.best_ref[slot] = best.type == RT_NONE ? RT_POOL_MISS : (best.type << 29) | (best.side << RT_POOL_IDX_BITS) | best.idx;
+                    W.best_inst[slot] = (uint8_t)best.inst;
+                    W.q_done[n_done + __popc(cm & below)] = (uint8_t)slot;
+                    have = false;
+                    ++my_segments;
+                }
+                n_done += __popc(cm);
+                const unsigned want = __ballot_sync(full, !have);
+                const uint32_t nw = __popc(want), got = nw < n_trace ? nw : n_trace;
+                if (!have) {
+                    const uint32_t rank = __popc(want & below);
+                    if (rank < got) {
+                        slot = W.q_trace[n_trace - 1u - rank];
+                        have = true; setup = true;
+                        inst = 0;
+                        best_init(best, RT_INF);
+                    }
+                }
+                n_trace -= got;
+                if (setup) {
+                    r.o = mk3(W.ox[slot], W.oy[slot], W.oz[slot]);
+                    r.d = mk3(W.dx[slot], W.dy[slot], W.dz[slot]);
+                    r.time = W.time[slot];
+                    uint32_t root;
+                    if (XF) {
+                        const Instance* ip = &S.instances[inst];
+                        xform_ray(S.ops, __ldg(&ip->chain_off), __ldg(&ip->chain_len), r);
+                        root = WIDE ? __ldg(&ip->root4) : __ldg(&ip->root);
+                    } else {
+                        root = WIDE ? S.root4 : __ldg(&S.instances[0].root);
+                    }
+                    f = make_rayf(r);
+                    pre = make_raypre(r, planar);
+                    cur = root;
+                    sp = 0;
+                }
+                __syncwarp();
+            }
+            const uint32_t busy = __popc(__ballot_sync(full, have));
+            if (busy == 0) break;
+            if (n_trace == 0 && busy <= LOW && n_done != 0) break; // starving: shade what is finished; the walks in flight resume afterwards
+            const uint32_t wt = n_trace ? REFILL : ((n_done != 0 && busy > LOW) ? busy - LOW : 1u);
+            if (WIDE) walk_wide<PM, true>(S, r, f, pre, 0.001, best, cur, sp, wstack, wt, XF ? inst : 0u);
+            else walk_pairs<PM>(S, r, f, pre, 0.001, best, cur, sp, stack, wt, XF ? inst : 0u);
+        }
+        if (n_done == 0 && !__any_sync(full, have)) break; // every path of this warp has ended and no index is left
+
+        // ================================================================ SHADE 1: classify (and sample the media)
+        for (uint32_t base = 0; base < n_done; base += 32u) {
+            const uint32_t i = base + lane;
+            uint32_t cls = 7u, sl = 0; // 0 Lambertian, 1 Metal / Dielectric, 2 Isotropic, 3 DiffuseLight, 5 ended
+            if (i < n_done) {
+                sl = W.q_done[i];
+                uint32_t ref = W.best_ref[sl];
+                if (MEDIA) { // ConstantMedium::hit against closest_so_far (hit.rs:955-986); order independent: keyed draws
+                    Ray wr;
+                    wr.o = mk3(W.ox[sl], W.oy[sl], W.oz[sl]); wr.d = mk3(W.dx[sl], W.dy[sl], W.dz[sl]); wr.time = W.time[sl];
+                    const uint64_t path_id = (uint64_t)W.pixel[sl] * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)W.s_local[sl]);
+                    double closest = W.best_t[sl];
+                    int32_t mwin = -1;
+                    D3 mp = mk3(0, 0, 0);
+                    for (uint32_t mi = 0; mi < S.n_media; ++mi) medium_query<false, GENERAL_MEDIA>(S, mi, wr, 0.001, closest, mwin, mp, J.seed, path_id, (uint32_t)W.segment[sl], nullptr);
+                    if (mwin >= 0) {
+                        ref = ((uint32_t)PRIM_MEDIUM << 29) | (uint32_t)mwin;
+                        W.best_t[sl] = closest;
+                        W.best_ref[sl] = ref;
+                    }
+                }
+                if (ref == RT_POOL_MISS) { // world.rs:86-89
+                    const F3 bg = miss_color(S, mk3(W.dx[sl], W.dy[sl], W.dz[sl]));
+                    accumulate(accum, W.pixel[sl], W.tr[sl] * bg.x, W.tg[sl] * bg.y, W.tb[sl] * bg.z);
+                    cls = 5u;
+                } else {
+                    const uint32_t type = ref >> 29, idx = ref & ((1u << RT_POOL_IDX_BITS) - 1u);
+                    const uint32_t mat = (MEDIA && type == PRIM_MEDIUM) ? S.media[idx].mat_id : __ldg(&S.meta[type][idx].mat_id);
+                    const uint32_t mt = __ldg(&S.materials[mat].type);
+                    cls = mt == MAT_LAMBERTIAN ? 0u : (mt == MAT_ISOTROPIC ? 2u : (mt == MAT_LIGHT ? 3u : 1u));
+                }
+            }
+            unsigned m;
+            m = __ballot_sync(full, cls == 0u); if (cls == 0u) W.q_mat[0][n_mat0 + __popc(m & below)] = (uint8_t)sl; n_mat0 += __popc(m);
+            m = __ballot_sync(full, cls == 1u); if (cls == 1u) W.q_mat[1][n_mat1 + __popc(m & below)] = (uint8_t)sl; n_mat1 += __popc(m);
+            m = __ballot_sync(full, cls == 2u); if (cls == 2u) W.q_mat[2][n_mat2 + __popc(m & below)] = (uint8_t)sl; n_mat2 += __popc(m);
+            m = __ballot_sync(full, cls == 3u); if (cls == 3u) W.q_mat[3][n_mat3 + __popc(m & below)] = (uint8_t)sl; n_mat3 += __popc(m);
+            m = __ballot_sync(full, cls == 5u); if (cls == 5u) W.q_regen[n_regen + __popc(m & below)] = (uint8_t)sl; n_regen += __popc(m);
+        }
+        n_done = 0;
+        __syncwarp();
+
+        // ================================================================ SHADE 2: per material class, batches of 32
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t n_c = c == 0 ? n_mat0 : (c == 1 ? n_mat1 : (c == 2 ? n_mat2 : n_mat3));
+            for (uint32_t base = 0; base < n_c; base += 32u) {
+                const uint32_t i = base + lane;
+                bool cont = false, ended = false;
+                uint32_t sl = 0;
+                if (i < n_c) {
+                    sl = W.q_mat[c][i];
+                    Ray wr;
+                    wr.o = mk3(W.ox[sl], W.oy[sl], W.oz[sl]); wr.d = mk3(W.dx[sl], W.dy[sl], W.dz[sl]); wr.time = W.time[sl];
+                    const uint32_t ref = W.best_ref[sl];
+                    HitRec h;
+                    if (MEDIA && (ref >> 29) == PRIM_MEDIUM) { // hit.rs:975-984
+                        const Medium md = S.media[ref & ((1u << RT_POOL_IDX_BITS) - 1u)];
+                        h.t = W.best_t[sl];
+                        h.p = medium_point(S, md, wr, h.t);
+                        h.n = mk3(0, 0, 0); h.u = 0.0; h.v = 0.0; h.front = true;
+                        h.mat = md.mat_id; h.prim_id = md.prim_id;
+                    } else {
+                        BestHit b;
+                        b.t = W.best_t[sl]; b.type = ref >> 29; b.side = (ref >> RT_POOL_IDX_BITS) & 7u; b.idx = ref & ((1u << RT_POOL_IDX_BITS) - 1u);
+                        b.inst = W.best_inst[sl];
+                        h = finalize_hit<2, PM, XF>(S, wr, b);
+                    }
+                    const DMaterial m = S.materials[h.mat];
+                    const float tr = W.tr[sl], tg = W.tg[sl], tb = W.tb[sl];
+                    if (c == 3) { // DiffuseLight: emitted, no scatter (hit.rs:1146-1151, world.rs:78-84)
+                        const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
+                        accumulate(accum, W.pixel[sl], tr * e.x, tg * e.y, tb * e.z);
+                        ended = true;
+                    } else {
+                        const uint64_t path_id = (uint64_t)W.pixel[sl] * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)W.s_local[sl]);
+                        PoolRng g;
+                        g.init(J.seed, path_id, W.draw[sl]);
+                        D3 dir = mk3(0, 0, 0);
+                        F3 att = mkf3(0.f, 0.f, 0.f);
+                        bool scattered;
+                        if (c == 0) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                        else if (c == 2) scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                        else if (m.type == MAT_METAL) scattered = scatter_metal(m, wr.d, h.n, g, dir, att);
+                        else scattered = scatter_dielectric(m, wr.d, h.n, h.front, g, dir, att);
+                        const uint32_t seg = (uint32_t)W.segment[sl] + 1u;
+                        if (scattered && (int32_t)seg < J.max_depth) { // world.rs:64-67, 75
+                            W.tr[sl] = tr * att.x; W.tg[sl] = tg * att.y; W.tb[sl] = tb * att.z;
+                            W.ox[sl] = h.p.x; W.oy[sl] = h.p.y; W.oz[sl] = h.p.z; W.dx[sl] = dir.x; W.dy[sl] = dir.y; W.dz[sl] = dir.z;
+                            W.draw[sl] = g.draw; W.segment[sl] = (uint8_t)seg;
+                            cont = true;
+                        } else {
+                            ended = true; // absorbed (Metal) or depth exhausted: nothing to add
+                        }
+                    }
+                }
+                unsigned m2 = __ballot_sync(full, cont);
+                if (cont) W.q_trace[n_trace + __popc(m2 & below)] = (uint8_t)sl;
+                n_trace += __popc(m2);
+                m2 = __ballot_sync(full, ended);
+                if (ended) W.q_regen[n_regen + __popc(m2 & below)] = (uint8_t)sl;
+                n_regen += __popc(m2);
+            }
+        }
+        n_mat0 = n_mat1 = n_mat2 = n_mat3 = 0;
+        __syncwarp();
+    }
+    uint32_t segs = my_segments;
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(full, segs, o);
+    if (lane == 0 && segs) atomicAdd(&Q.stats[0], (unsigned long long)segs);
+}
+
 __global__ void k_mega_init(Queues Q) {
     if (threadIdx.x == 0) { *Q.next_path = 0ull; *Q.dead = 0; }
     if (threadIdx.x < 9) Q.stats[threadIdx.x] = 0ull;
@@ -965,6 +1243,13 @@ static void launch_extend(int blocks, bool specialise, bool wide, cudaStream_t s
     }
 }
 
+template <uint32_t PM, bool WIDE, bool MEDIA, bool GM, bool XF, int P, int MINB>
+static void launch_pool(cudaStream_t st, const DeviceScene& scene, const JobDev& J, const Queues& Q, int64_t* d_accum) {
+    auto kern = k_pool<PM, WIDE, MEDIA, GM, XF, P, MINB>;
+    const size_t smem = 4 * sizeof(WarpPool<P>); // four warps per CTA, one pool each
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // per device: set on every launch (microseconds)
+    kern<<<148 * MINB, 128, smem, st>>>(scene, J, Q, d_accum);
+}
 cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const RenderTuning& tune, int64_t* d_accum, cudaStream_t stream,
                           rt_stats* stats, Workspace** wsp) {
     cudaError_t err = cudaSuccess;
@@ -1018,7 +1303,33 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         // RT_MODE_AUTO (measured on B200, profiles/README.md): the fused persistent kernel wins where shading is cheap
         // (book-1 scenes +20 %, mesh room +7 %); the wavefront wins with media / Perlin textures (Cornell smoke +8 %, book-2 final +56 %)
         const int mode = tune.mode != RT_MODE_AUTO ? tune.mode : ((scene.n_media == 0 && !(scene.flags & 8u)) ? RT_MODE_FUSED : RT_MODE_WAVEFRONT);
-        if (mode == RT_MODE_FUSED) {
+        if (mode == RT_MODE_POOL && job.max_depth <= 255 && scene.n_main_instances <= 255u) {
+            k_mega_init<<<1, 32, 0, stream>>>(Q);
+            {
+                const unsigned long long warps = 148ull * 4ull * 4ull;
+                unsigned long long c = J.total_paths / (warps * 64ull);
+                c = std::max(32ull, std::min((unsigned long long)RT_MEGA_CHUNK, c)) & ~31ull;
+                J.chunk = (uint32_t)c;
+            }
+            const bool wrapper_free = !(scene.flags & 32u) && scene.n_main_instances == 1;
+            const bool wide = wrapper_free && scene.nodes4 != nullptr && tune.bvh_wide != 0;
+            const uint32_t pmask = scene.prim_mask;
+            // opt-in experiment (RT_RENDER_FORCE_POOL / RTB200_MODE=2), four instantiations: measured slower than RT_MODE_AUTO's kernels on
+            // every BASELINE config (profiles/README.md, round 2), kept for the A/B and its ncu evidence
+            if (media) launch_pool<RT_PM_ALL, false, true, true, true, 128, 4>(stream, scene, J, Q, d_accum);
+            else if (wide && pmask == 0x1u) launch_pool<0x1u, true, false, false, false, 128, 4>(stream, scene, J, Q, d_accum);
+            else if (wide && (pmask & ~0x28u) == 0) launch_pool<0x28u, true, false, false, false, 128, 4>(stream, scene, J, Q, d_accum);
+            else launch_pool<RT_PM_ALL, false, false, false, true, 128, 4>(stream, scene, J, Q, d_accum);
+            CK(cudaGetLastError());
+            launches += 2;
+            iterations = 1;
+            CK(cudaEventRecord(w->ev_end, stream));
+            CK(cudaMemcpyAsync(h_stats, Q.stats, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            CK(cudaEventElapsedTime(&ms_device, w->ev_begin, w->ev_end));
+            goto done;
+        }
+        if (mode == RT_MODE_FUSED || mode == RT_MODE_POOL) {
             k_mega_init<<<1, 32, 0, stream>>>(Q);
             // Variant choice (every step A/B-measured on B200): compile-time primitive mask when the scene
             // holds only spheres / spheres + moving spheres / rects + triangles; wrapper-free (XF = false) variants at 5 CTAs/SM

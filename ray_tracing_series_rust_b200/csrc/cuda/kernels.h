@@ -21,6 +21,7 @@ struct RenderJob {
 
 #define RT_MODE_WAVEFRONT 0 // k_extend + k_shade_all per iteration, per-material queues, path state in HBM
 #define RT_MODE_FUSED 1     // k_mega: persistent threads, path state in registers
+#define RT_MODE_POOL 2      // k_pool: warp-local wavefront, path state and per-material slot lists in shared memory
 #define RT_MODE_AUTO (-1)    // measured rule: fused for scenes without media and without noise textures, else wavefront
 
 struct RenderTuning {

@@ -463,21 +463,39 @@ RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r
 // `wait_thresh` of the lanes that entered with work have finished, instead of idling them until the slowest
 // lane is done.  The unfinished lanes come back with the next call (after the finished ones have shaded and
 // started their next segment) and continue where they stopped.  Called by all 32 lanes.
+// walk_pairs = the loop of trace_resume with the per-ray constants (f32 reciprocals, a = d.d, 1/a, 1/d) supplied by the caller, who keeps
+// them in registers across calls (k_pool: a lane's walk is suspended and resumed many times), and with the lane's instance index for
+// the hit record.  MOTION: spheres + moving spheres scenes walk the motion-interpolated boxes (DeviceScene::mnodes) like trace_instance.
 template <uint32_t PM = RT_PM_ALL>
-RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, uint32_t* stack, uint32_t wait_thresh) {
+RT_DEV void walk_pairs(const DeviceScene& S, const Ray& r, const RayF& f, const RayPre& pre, double t_min, BestHit& best, uint32_t& cur, int& sp, uint32_t* stack,
+                       uint32_t wait_thresh, uint32_t inst) {
     const unsigned full = 0xffffffffu;
-    const RayF f = make_rayf(r);
-    const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
     const float tminf = f32_down(t_min);
     float tmaxf = f32_up(best.t);
     const float4* __restrict__ nodes = reinterpret_cast<const float4*>(S.nodes);
+    const float4* __restrict__ mnodes = reinterpret_cast<const float4*>(S.mnodes);
+    const bool MOTION = PM == 0x3u && mnodes != nullptr;
+    float ms = 0.f;
+    if (MOTION) { const double sd = (r.time - S.motion_t0) * S.motion_inv_dt; ms = (float)(sd < 0.0 ? 0.0 : (sd > 1.0 ? 1.0 : sd)); }
     const uint32_t DONE = 0xffffffffu;
     const uint32_t n0 = __popc(__ballot_sync(full, cur != DONE));
     for (;;) {
         uint32_t leaf_first0 = 0, leaf_cnt0 = 0, leaf_first1 = 0, leaf_cnt1 = 0;
         while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0) {
-            const float4 lo0 = __ldg(nodes + 2 * cur), hi0 = __ldg(nodes + 2 * cur + 1);
-            const float4 lo1 = __ldg(nodes + 2 * cur + 2), hi1 = __ldg(nodes + 2 * cur + 3);
+            float4 lo0, hi0, lo1, hi1;
+            if (MOTION) {
+                lo0 = __ldg(mnodes + 4 * cur); hi0 = __ldg(mnodes + 4 * cur + 1);
+                lo1 = __ldg(mnodes + 4 * cur + 4); hi1 = __ldg(mnodes + 4 * cur + 5);
+                const float4 dl0 = __ldg(mnodes + 4 * cur + 2), dh0 = __ldg(mnodes + 4 * cur + 3);
+                const float4 dl1 = __ldg(mnodes + 4 * cur + 6), dh1 = __ldg(mnodes + 4 * cur + 7);
+                lo0.x = fmaf(dl0.x, ms, lo0.x); lo0.y = fmaf(dl0.y, ms, lo0.y); lo0.z = fmaf(dl0.z, ms, lo0.z);
+                hi0.x = fmaf(dh0.x, ms, hi0.x); hi0.y = fmaf(dh0.y, ms, hi0.y); hi0.z = fmaf(dh0.z, ms, hi0.z);
+                lo1.x = fmaf(dl1.x, ms, lo1.x); lo1.y = fmaf(dl1.y, ms, lo1.y); lo1.z = fmaf(dl1.z, ms, lo1.z);
+                hi1.x = fmaf(dh1.x, ms, hi1.x); hi1.y = fmaf(dh1.y, ms, hi1.y); hi1.z = fmaf(dh1.z, ms, hi1.z);
+            } else {
+                lo0 = __ldg(nodes + 2 * cur); hi0 = __ldg(nodes + 2 * cur + 1);
+                lo1 = __ldg(nodes + 2 * cur + 2); hi1 = __ldg(nodes + 2 * cur + 3);
+            }
             float tn0, tn1;
             bool h0 = slab(lo0, hi0, f, tminf, tmaxf, tn0);
             bool h1 = slab(lo1, hi1, f, tminf, tmaxf, tn1);
@@ -499,12 +517,19 @@ RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestH
         }
         for (int k = 0; k < 2; ++k) {
             const uint32_t lc = k ? leaf_cnt1 : leaf_cnt0, lf = k ? leaf_first1 : leaf_first0;
-            if (lc & 0xffffffu) leaf_test<PM>(S, r, pre, t_min, best, lc >> 24, lf, lc & 0xffffffu, 0u);
+            if (lc & 0xffffffu) leaf_test<PM>(S, r, pre, t_min, best, lc >> 24, lf, lc & 0xffffffu, inst);
         }
         tmaxf = f32_up(best.t);
         const uint32_t still = __popc(__ballot_sync(full, cur != DONE));
         if (still == 0 || n0 - still >= wait_thresh) break;
     }
+}
+
+template <uint32_t PM = RT_PM_ALL>
+RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, uint32_t* stack, uint32_t wait_thresh) {
+    const RayF f = make_rayf(r);
+    const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
+    walk_pairs<PM>(S, r, f, pre, t_min, best, cur, sp, stack, wait_thresh, 0u);
 }
 
 // ------------------------------------------------------------------ 4-wide walk (rt_types.h RT_WIDE_EMPTY, host/bvh_wide.hpp)
@@ -539,12 +564,11 @@ RT_DEV uint32_t wide_pop(const unsigned long long* stack, int& sp, float tmaxf) 
 // RESUME = true: the resumable form used by k_mega_r (see trace_resume below): state (cur, sp, stack, best) lives in the
 // caller, called by all 32 lanes, returns once `wait_thresh` of the lanes that entered with work have finished.
 // RESUME = false: walks until this lane is done.
+// walk_wide: the per-ray constants come from the caller (see walk_pairs); trace_wide below derives them per call.
 template <uint32_t PM, bool RESUME, bool COUNT = false>
-RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack, uint32_t wait_thresh,
-                       uint32_t inst = 0u, TraceCounters* cnt = nullptr) {
+RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const RayPre& pre, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack,
+                      uint32_t wait_thresh, uint32_t inst = 0u, TraceCounters* cnt = nullptr) {
     const unsigned full = 0xffffffffu;
-    const RayF f = make_rayf(r);
-    const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
     const float tminf = fmaxf(f32_down(t_min), 0.f);
     float tmaxf = f32_up(best.t);
     const float4* __restrict__ nodes4 = S.nodes4;
@@ -600,6 +624,14 @@ RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit
             break;
         }
     }
+}
+
+template <uint32_t PM, bool RESUME, bool COUNT = false>
+RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack, uint32_t wait_thresh,
+                       uint32_t inst = 0u, TraceCounters* cnt = nullptr) {
+    const RayF f = make_rayf(r);
+    const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
+    walk_wide<PM, RESUME, COUNT>(S, r, f, pre, t_min, best, cur, sp, stack, wait_thresh, inst, cnt);
 }
 
 RT_DEV bool inst_box_hit(const Instance* ip, const Ray& r, double t_min, double t_max) {
@@ -799,6 +831,20 @@ RT_DEV void medium_query(const DeviceScene& S, uint32_t mi, const Ray& world_ray
     p_out = p;
 }
 
+// rec.p of a medium hit at parameter t (hit.rs:976): r.at(t) in the medium's own space, brought out through the medium's chain -
+// the same operations, in the same order, as the tail of medium_query (k_pool rebuilds the record when it shades the slot)
+RT_DEV D3 medium_point(const DeviceScene& S, const Medium& md, const Ray& world_ray, double t) {
+    Ray r = world_ray;
+    xform_ray(S.ops, md.chain_off, md.chain_len, r);
+    D3 p = ray_at(r, t);
+    for (int i = (int)md.chain_len - 1; i >= 0; --i) {
+        const XformOp op = S.ops[md.chain_off + i];
+        if (op.type == XF_TRANSLATE) p = mk3(p.x + op.a, p.y + op.b, p.z + op.c);
+        else p = mk3(op.b * p.x + op.a * p.z, p.y, -op.a * p.x + op.b * p.z);
+    }
+    return p;
+}
+
 // world.hit(ray, t_min, t_max) (world.rs:68): surfaces first, then every medium against the closest
 // surface (order independent because medium draws are keyed).
 template <bool COUNT, int UVMODE, bool MEDIA, bool GENERAL_MEDIA = true, uint32_t PM = RT_PM_ALL, bool XF = true, bool WIDE = false>
@@ -870,8 +916,8 @@ RT_DEV F3 tex_value(const DeviceScene& S, uint32_t tex, double u, double v, D3 p
         const uint32_t type = __ldg(&t->type);
         if (type == TEX_SOLID) return mkf3(__ldg(&t->rgb[0]), __ldg(&t->rgb[1]), __ldg(&t->rgb[2])); // texture.rs:27-31
         if (type == TEX_CHECKER) { // texture.rs:54-64: sign of sin(10x) sin(10y) sin(10z)
-            const float sines = sinf((float)(10.0 * p.x)) * sinf((float)(10.0 * p.y)) * sinf((float)(10.0 * p.z));
-            tex = sines < 0.0f ? __ldg(&t->b) : __ldg(&t->a);
+            const double sines = sin(10.0 * p.x) * sin(10.0 * p.y) * sin(10.0 * p.z); // f64 like the reference: an f32 argument moves the checker boundaries by ~5e-4 rad at |10 p| ~ 1e4
+            tex = sines < 0.0 ? __ldg(&t->b) : __ldg(&t->a);
             continue;
         }
         if (!FULL) break;

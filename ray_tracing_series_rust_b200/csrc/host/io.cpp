@@ -77,10 +77,18 @@ inline bool parse_double(const char*& p, const char* end, double& v) {
     const char* q = (p < end && *p == '+') ? p + 1 : p;
     const std::from_chars_result r = std::from_chars(q, end, v);
     if (r.ec == std::errc() && r.ptr != q) { p = r.ptr; return true; }
+    // strtod knows no end pointer and skips '\n': run it on a bounded copy of the token, so that a line with too few numbers
+    // is an error (the reference panics on such a file, model.rs:44-48) instead of borrowing a value from the next line
+    const char* t = p;
+    while (t < end && *t != ' ' && *t != '\t' && *t != '\r' && *t != '\n') ++t;
+    if (t == p || t - p > 63) return false;
+    char tok[64];
+    std::memcpy(tok, p, (size_t)(t - p));
+    tok[t - p] = 0;
     char* e;
-    v = std::strtod(p, &e);
-    if (e == p) return false;
-    p = e;
+    v = std::strtod(tok, &e);
+    if (e == tok || *e != 0) return false;
+    p = t;
     return true;
 }
 inline bool parse_ulong(const char*& p, const char* end, unsigned long& v) {
@@ -137,6 +145,7 @@ bool parse_ply_ascii(const std::string& s, double scale, std::vector<double>& ve
     while (p < end) {
         const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
         const char* le = nl ? nl : end;
+        if (le > p && le[-1] == '\r') --le; // CRLF files: read_ply_any's format probe tolerates the '\r', so does the header scan
         const size_t len = (size_t)(le - p);
         if (len == 10 && std::memcmp(p, "end_header", 10) == 0) { header_done = true; p = nl ? nl + 1 : end; break; }
         if (len > 15 && std::memcmp(p, "element vertex ", 15) == 0) nv = std::strtol(p + 15, nullptr, 10);

@@ -334,6 +334,13 @@ struct Flattener {
         const double q0 = s->span0 / 0.001, q1 = s->span1 / 0.001;
         i0 = q0 > 0.0 ? (int64_t)q0 : 0;
         i1 = q1 > 0.0 ? (int64_t)q1 : 0;
+        // hit.rs:373: the table answers while (time / incr) as usize + 1 <= stored.len(); past it GravitySphere::get_center re-integrates
+        // with other constants (2 * radius, -0.8 bounce: hit.rs:381-393), which is not reproduced here (DESIGN.md divergence 5): refuse the
+        // shutter instead of silently holding the last table entry
+        if (i1 + 1 > (int64_t)tab.size() && status == RT_OK) {
+            status = RT_ERR_UNSUPPORTED;
+            error = "camera shutter reaches past the GravitySphere height table (time >= ~100): the reference's fallback integration (hit.rs:381-393) is not supported";
+        }
         i1 += 1; // time2 itself is exclusive, one guard entry
         const int64_t last = (int64_t)tab.size() - 1;
         i0 = std::min(std::max<int64_t>(i0, 0), last);
@@ -1212,6 +1219,7 @@ int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg, int64_t* d_ac
     tune.count_events = (cfg->flags & RT_RENDER_COUNT_EVENTS) ? 1 : 0;
     if (cfg->flags & RT_RENDER_FORCE_WAVEFRONT) tune.mode = RT_MODE_WAVEFRONT;
     if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
+    if (cfg->flags & RT_RENDER_FORCE_POOL) tune.mode = RT_MODE_POOL;
     if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
     const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats, &s->workspace);
     if (e != cudaSuccess) return fail_cuda(e, "render");
@@ -1272,6 +1280,7 @@ RenderTuning tuning_for(const rt_scene* s, const rt_render_config* cfg) {
     tune.count_events = (cfg->flags & RT_RENDER_COUNT_EVENTS) ? 1 : 0;
     if (cfg->flags & RT_RENDER_FORCE_WAVEFRONT) tune.mode = RT_MODE_WAVEFRONT;
     if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
+    if (cfg->flags & RT_RENDER_FORCE_POOL) tune.mode = RT_MODE_POOL;
     if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
     return tune;
 }

@@ -347,6 +347,22 @@ def test_fused_mode_is_bit_identical_to_wavefront(scene_id):
     assert res[1][2] == 2 and res[0][2] > 2
 
 
+@pytest.mark.parametrize("scene_id", [13, 99, 8, 5, 6, 14, 4, 1, 9])
+def test_pool_mode_is_bit_identical(scene_id):
+    # RT_RENDER_FORCE_POOL (k_pool: every warp runs a wavefront of its own in shared memory - slot lists, resumable walks, per-material
+    # batches, media sampled in the classify pass, instances walked one after the other): same image, bit for bit, and the same number of
+    # world.hit queries as RT_MODE_AUTO's kernel, also at a depth limit that ends paths early and with tile-sharded renders
+    g = rtb.new_scene()
+    g.world_build(scene_id, 3, 48 if scene_id == 14 else 0)
+    g.commit()
+    aspect = {13: 1.5, 99: 16 / 9, 8: 1.5, 1: 1.5, 9: 1.5}.get(scene_id, 1.0)
+    for depth, extra in ((50, 0), (3, 0), (50, (1 << 16) | (3 << 24))):  # RT_RENDER_TILE_SHARD(1, 3)
+        _, a0, s0 = g.render(capi.make_config(88, aspect, 5, depth, seed=4, flags=extra), want_accum=True)
+        _, a1, s1 = g.render(capi.make_config(88, aspect, 5, depth, seed=4, flags=16 | extra), want_accum=True)
+        assert np.array_equal(a0, a1) and a0.any() and s0["segments"] == s1["segments"] and s1["kernel_launches"] == 2
+    g.close()
+
+
 @pytest.mark.parametrize("scene_id,param", [(14, 48), (6, 0), (13, 0), (99, 0)])
 def test_device_lbvh_builder_parity(orc, scene_id, param, monkeypatch):
     # SURVEY.md 8(f) n1 (csrc/cuda/lbvh.cu replaces BvhNode::new, bvh.rs:14-83): the tree built on the device gives

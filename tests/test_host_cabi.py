@@ -159,6 +159,25 @@ def test_medium_inside_medium_boundary_is_unsupported(api):
     assert api.lib.rt_scene_host_check(C.c_void_p(s.h), out) == -3
 
 
+def test_gravity_shutter_past_the_table_is_refused(api):
+    # GravitySphere::get_center (hit.rs:370-395) leaves its 100 001-entry table for time >= ~100 and re-integrates with other constants;
+    # that fallback is not reproduced (DESIGN.md divergence 5), so such a shutter is an error at commit, not a silent clamp
+    s = rtb.new_scene()
+    s.world_build(8, 0xB005)
+    s.set_camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.1, 10.0, 99.5, 100.5)
+    with pytest.raises(capi.RtError) as e:
+        s.commit()
+    assert e.value.code == -3 and "hit.rs:381-393" in str(e.value)
+    s.set_camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.1, 10.0, 95.6, 96.0)  # the last frame of the 240-frame schedule
+    if has_cuda():
+        s.commit()
+    else:
+        with pytest.raises(capi.RtError) as e:
+            s.commit()
+        assert e.value.code == -5  # the scene itself is fine: only the device is missing
+    s.close()
+
+
 def test_ply_and_ppm_io_roundtrip(api, orc, tmp_path):
     # ASCII PLY subset of model.rs:13-62: product loader vs oracle loader on the same file
     ply = tmp_path / "m.ply"
@@ -215,9 +234,15 @@ def test_ascii_ply_number_formats_and_errors(api, tmp_path):
     s = rtb.new_scene()
     m = s.lambertian((0.2, 0.2, 0.2))
     s.ply_load(ply, 2.0, m)
+    crlf = tmp_path / "crlf.ply"  # CRLF header lines too (exported from a Windows tool): same mesh
+    crlf.write_bytes((hdr % (4, 2) + body).replace("\r\n", "\n").replace("\n", "\r\n").encode())
+    s.ply_load(crlf, 2.0, m)
     cases = {
         "short vertex line": (hdr % (2, 0) + "0 0 0\n1 1\n", "bad vertex line"),
         "not a number": (hdr % (1, 0) + "0 zero 0\n", "bad vertex line"),
+        # a value that only strtod spells ("inf") on a short line must not be completed from the next line (the reference panics, model.rs:44-48)
+        "short line ending in a strtod token": (hdr % (2, 0) + "0 inf\n1 1 1\n", "bad vertex line"),
+        "short line, number borrowed across the newline": (hdr % (2, 0) + "0 0\n0x1p0 1 1\n", "bad vertex line"),
         "short face line": (hdr % (3, 1) + "0 0 0\n1 0 0\n0 1 0\n3 0 1\n", "bad face line"),
         "index out of range": (hdr % (3, 1) + "0 0 0\n1 0 0\n0 1 0\n3 0 1 3\n", "out of range"),
         "truncated vertices": (hdr % (3, 1) + "0 0 0\n1 0 0\n", "truncated vertex list"),
