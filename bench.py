@@ -165,7 +165,7 @@ def reference_arm(args, wl, name):
     value = tot_paths / tot_s
     out = {
         "impl": "reference", "metric": "paths/s", "value": value, "unit": "paths/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": value / README_BOOK1_10T_PATHS_PER_S if name == "book1_final" else None,
+        "ms_per_step": 1e3 * tot_s / max(1, len(vals)), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": value / README_BOOK1_10T_PATHS_PER_S if name == "book1_final" else None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "description": wl[8], "note": "CPU restatement of the reference (oracle/, C++ f64, not rustc-built); each step is a bounded sample"},
         "cpu_baseline": {"value": value, "unit": "paths/s", "cores": threads, "kind": "port", "sample": last["sample"]},
@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--sharding", default="samples", choices=["samples", "tiles"],
                     help="N>1: sample ranges of every pixel (default) or 4-row tile bands dealt round-robin (SURVEY 8e alternative)")
+    ap.add_argument("--reduce", default="reduce", choices=["reduce", "allreduce"], help="N>1: the collective that sums the accumulators")
     ap.add_argument("--slots", type=int, default=0, help="resident path slots of the wavefront (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads reported under 'also'")
@@ -245,14 +246,17 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     host_screen = torch.empty((H, W, 3), dtype=torch.float64).pin_memory()
 
-    def one_step(step, timed_extend=False, count=False, local_only=False):
-        cfg = capi.make_config(W, aspect, spp_total, depth, seed=1 + step, sample_begin=s_begin, sample_end=s_end, flags=(1 if timed_extend else 0) | (2 if count else 0) | shard_flags)
+    def one_step(step, timed_extend=False, count=False, local_only=False, no_wait=False):
+        # no_wait (RT_RENDER_NO_WAIT): the call returns once the render is enqueued, so the reduce and the resolve queue up behind the kernel
+        # on the same stream without a host round trip in between (single-launch modes; the wavefront ignores it)
+        cfg = capi.make_config(W, aspect, spp_total, depth, seed=1 + step, sample_begin=s_begin, sample_end=s_end,
+                               flags=(1 if timed_extend else 0) | (2 if count else 0) | (32 if no_wait else 0) | shard_flags)
         accum.zero_()
         st = capi.Stats()
         api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
         if local_only:  # rank-0-only diagnostics after the other ranks have left: no collective
             return st.as_dict()
-        sharding.reduce_accumulators(accum, dst=0)
+        sharding.reduce_accumulators(accum, dst=0, how=args.reduce)
         if rank == 0:
             api.check(api.resolve_device(C.c_void_p(accum.data_ptr()), C.c_void_p(screen.data_ptr()), W, H, spp_total, H, C.c_void_p(stream.cuda_stream)))
         return st.as_dict()
@@ -262,8 +266,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    st_warm = None
     for i in range(args.warmup):
-        one_step(i)
+        st_warm = one_step(i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -277,9 +282,11 @@ def main():
         flush.zero_()  # L2 flush between timed iterations (outside the timed events)
         barrier()
         ev[k][0].record(stream)
-        st = one_step(args.warmup + k)
+        st = one_step(args.warmup + k, no_wait=True)
         ev[k][1].record(stream)
         launches += st["kernel_launches"] + (1 if rank == 0 else 0)
+        if st["segments"] == 0 and st_warm is not None:  # enqueued without waiting: the device counters were not read back; the warm-up render of the same workload has them
+            st = st_warm
         segments += st["segments"]
         paths_local += st["paths"]
     barrier()

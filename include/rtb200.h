@@ -204,6 +204,11 @@ typedef struct rt_render_config {
 #define RT_RENDER_FORCE_WAVEFRONT 4 /* wavefront mode: k_extend + k_shade_all per iteration, per-material queues */
 #define RT_RENDER_FORCE_FUSED 8     /* fused mode: one persistent kernel, path state in registers */
 #define RT_RENDER_FORCE_POOL 16     /* pool mode: one persistent kernel, every warp runs a small wavefront of its own in shared memory */
+/* rt_render_device only: return as soon as the render is enqueued on the caller's stream instead of waiting for it, so that the
+ * caller's next stream operations (the NCCL reduce, rt_resolve_device) queue up behind the kernel without a host round trip.
+ * Honoured by the single-launch modes (fused, pool); the wavefront's host loop ignores it.  stats then carry only what the host
+ * knows (paths, kernel_launches); segments and ms_device stay 0. */
+#define RT_RENDER_NO_WAIT 32
 /* Tile sharding (the GPU analogue of the reference's row bands, world.rs:1198-1227): the image is cut
  * into bands of RT_TILE_ROWS rows; a call with RT_RENDER_TILE_SHARD(rank, count) in `flags` renders only the bands
  * b with b % count == rank (all samples of their pixels); the other pixels of out_accum / out_screen stay 0.  Path ids

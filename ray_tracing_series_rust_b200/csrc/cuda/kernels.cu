@@ -1323,6 +1323,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             CK(cudaGetLastError());
             launches += 2;
             iterations = 1;
+            if (tune.no_wait) goto done; // RT_RENDER_NO_WAIT: the caller's stream carries on behind the kernel
             CK(cudaEventRecord(w->ev_end, stream));
             CK(cudaMemcpyAsync(h_stats, Q.stats, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
@@ -1385,6 +1386,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             CK(cudaGetLastError());
             launches += 2;
             iterations = 1;
+            if (tune.no_wait) goto done; // RT_RENDER_NO_WAIT: the caller's stream carries on behind the kernel
             CK(cudaEventRecord(w->ev_end, stream));
             CK(cudaMemcpyAsync(h_stats, Q.stats, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));

@@ -1221,6 +1221,7 @@ int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg, int64_t* d_ac
     if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
     if (cfg->flags & RT_RENDER_FORCE_POOL) tune.mode = RT_MODE_POOL;
     if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
+    tune.no_wait = (cfg->flags & RT_RENDER_NO_WAIT) ? 1 : 0;
     const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats, &s->workspace);
     if (e != cudaSuccess) return fail_cuda(e, "render");
     if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -21,11 +21,16 @@ def sample_range(spp: int, rank: int, world: int, scaling: str = "strong"):
     return spp, (spp * rank) // world, (spp * (rank + 1)) // world
 
 
-def reduce_accumulators(accum, dst: int = 0):
-    """Sum the per-rank int64 accumulators onto `dst` (NCCL on GPU tensors, gloo on CPU tensors)."""
+def reduce_accumulators(accum, dst: int = 0, how: str = "reduce"):
+    """Sum the per-rank int64 accumulators onto `dst` (NCCL on GPU tensors, gloo on CPU tensors).
+    how = "reduce" (one ncclReduce to dst) or "allreduce" (every rank ends with the sum; on NVSwitch boxes NCCL can then reduce
+    inside the switch, NVLS)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
+        if how == "allreduce":
+            dist.all_reduce(accum, op=dist.ReduceOp.SUM)
+        else:
+            dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
     return accum
 
 
