@@ -75,10 +75,23 @@ extern "C" {
     fn rt_scene_set_root(s: *mut RtScene, id: i32) -> i32;
     fn rt_scene_set_camera_fields(s: *mut RtScene, fields: *const f64) -> i32;
     fn rt_scene_set_background(s: *mut RtScene, rgb: *const f64) -> i32;
+    fn rt_scene_set_background_gradient(s: *mut RtScene, horizon_rgb: *const f64, zenith_rgb: *const f64) -> i32;
     fn rt_scene_commit(s: *mut RtScene) -> i32;
+    fn rt_scene_commit_multi(s: *mut RtScene, n_gpus: i32) -> i32;
     fn rt_image_height(cfg: *const RtRenderConfig) -> i32;
     fn rt_render(s: *mut RtScene, cfg: *const RtRenderConfig, out_screen: *mut f64, out_accum: *mut i64, stats: *mut u8) -> i32;
+    /// one host thread, n_gpus devices of the box: shards rendered per GPU, summed + resolved over NVLink peer memory (include/rtb200.h)
+    fn rt_render_multi(s: *mut RtScene, cfg: *const RtRenderConfig, n_gpus: i32, shard_mode: i32, out_screen: *mut f64, out_accum: *mut i64, stats: *mut u8) -> i32;
+    fn rt_render_scene_with_time(s: *mut RtScene, t0: f64, t1: f64, path: *const c_char, cfg: *const RtRenderConfig, out_screen: *mut f64, stats: *mut u8) -> i32;
     fn rt_write_ppm(path: *const c_char, screen: *const f64, w: i32, h: i32) -> i32;
+}
+
+pub const RT_SHARD_SAMPLES: i32 = 0; // contiguous sample ranges of every pixel per GPU (perfect balance)
+pub const RT_SHARD_TILES: i32 = 1; // 4-row bands dealt round-robin (the reference's row bands, world.rs:1198-1227)
+
+/// GPUs to use: RTB200_GPUS in the environment, else 1 (the library refuses more than the box has).
+fn n_gpus() -> i32 {
+    std::env::var("RTB200_GPUS").ok().and_then(|v| v.parse().ok()).unwrap_or(1)
 }
 
 /// The reference panics where the C-ABI returns a negative rt_status (world.rs:36-40, screen.rs:14, bvh.rs:27-28, model.rs:15).
@@ -316,14 +329,16 @@ impl Camera {
     }
 }
 
-/// Drop-in for `render_scene` (src/world.rs:1181-1247): same arguments, same P3 PPM on stdout.
+/// Drop-in for `render_scene` (src/world.rs:1181-1247): same arguments, same P3 PPM on stdout.  With RTB200_GPUS=8 the same call
+/// drives the whole 8 x B200 node (rt_render_multi): the image is bit-identical for every GPU count.
 pub fn render_scene_gpu(world: Arc<Box<dyn Hittable + Sync>>, cam: Arc<Camera>, background: Vec3, config: Config) {
     let mut b = FlatSceneBuilder::new();
     let root = b.hittable(&world);
     check(unsafe { rt_scene_set_root(b.s, root) });
     cam.flatten(&mut b);
     check(unsafe { rt_scene_set_background(b.s, xyz(&background).as_ptr()) });
-    check(unsafe { rt_scene_commit(b.s) }); // flatten + BVH build + one upload
+    let gpus = n_gpus();
+    check(unsafe { rt_scene_commit_multi(b.s, gpus) }); // flatten + BVH build + one upload per GPU
     let cfg = RtRenderConfig {
         image_width: config.image_width,
         aspect_ratio: config.aspect_ratio,
@@ -339,20 +354,24 @@ pub fn render_scene_gpu(world: Arc<Box<dyn Hittable + Sync>>, cam: Arc<Camera>, 
     let h = check(unsafe { rt_image_height(&cfg) }) as usize;
     let w = config.image_width as usize;
     let mut pixels = vec![0.0f64; w * h * 3]; // Screen layout: row 0 = bottom, integer-valued 0..255 (vec3.rs:89-107)
-    check(unsafe { rt_render(b.s, &cfg, pixels.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) });
+    check(unsafe { rt_render_multi(b.s, &cfg, gpus, RT_SHARD_SAMPLES, pixels.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) });
     check(unsafe { rt_write_ppm(std::ptr::null(), pixels.as_ptr(), w as i32, h as i32) }); // byte-identical to Screen::write_to_ppm
 }
 
-/// Drop-in for `render_scene_with_time` (src/world.rs:1249-1330): the caller's scene, the frame's shutter, a file.
-pub fn render_frame_gpu(b: &mut FlatSceneBuilder, cam: &Camera, cfg: &RtRenderConfig, path: &str) -> Screen {
-    cam.flatten(b); // Camera::new(.., t0, t1) of the frame
-    check(unsafe { rt_scene_commit(b.s) }); // re-derives GravitySphere windows and bounds for this shutter
-    let h = check(unsafe { rt_image_height(cfg) }) as usize;
-    let w = cfg.image_width as usize;
+/// Drop-in for `render_scene_with_time(t0, t1, path, world)` (src/world.rs:1249-1330): binds the library's own frame entry, which
+/// sets the reference's hard-coded frame camera ((13,2,3) -> 0, vfov 20, aperture 0.1, focus 10, shutter [t0, t1)) and background,
+/// re-commits (GravitySphere windows and moving bounds follow the shutter), renders and writes the P3 file.  `cfg` = None gives
+/// the reference's 500 x 500, 500 spp, depth 50, 11 row bands.
+pub fn render_frame_gpu(b: &mut FlatSceneBuilder, t0: f64, t1: f64, path: &str, cfg: Option<&RtRenderConfig>) -> Screen {
+    let probe = RtRenderConfig { image_width: 500, aspect_ratio: 1.0, samples_per_pixel: 500, max_depth: 50, compat_threads: 11, seed: 1,
+                                 sample_begin: 0, sample_end: 0, threads: 0, flags: 0 };
+    let c: &RtRenderConfig = cfg.unwrap_or(&probe);
+    let h = check(unsafe { rt_image_height(c) }) as usize;
+    let w = c.image_width as usize;
     let mut pixels = vec![0.0f64; w * h * 3];
-    check(unsafe { rt_render(b.s, cfg, pixels.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) });
     let cpath = CString::new(path).unwrap();
-    check(unsafe { rt_write_ppm(cpath.as_ptr(), pixels.as_ptr(), w as i32, h as i32) });
+    let cfg_ptr = match cfg { Some(p) => p as *const RtRenderConfig, None => std::ptr::null() };
+    check(unsafe { rt_render_scene_with_time(b.s, t0, t1, cpath.as_ptr(), cfg_ptr, pixels.as_mut_ptr(), std::ptr::null_mut()) });
     let mut screen = Screen::new(w, h);
     for j in 0..h {
         for i in 0..w {
@@ -361,4 +380,11 @@ pub fn render_frame_gpu(b: &mut FlatSceneBuilder, cam: &Camera, cfg: &RtRenderCo
         }
     }
     screen
+}
+
+/// The sky of the revision that rendered images/book1.png (README.md:18): not in HEAD's ray_color (world.rs:86-89 has the constant
+/// background only); exposed so that renders can be checked against that shipped image.
+pub fn set_book1_sky(b: &mut FlatSceneBuilder) {
+    let (horizon, zenith) = ([1.0f64, 1.0, 1.0], [0.5f64, 0.7, 1.0]);
+    check(unsafe { rt_scene_set_background_gradient(b.s, horizon.as_ptr(), zenith.as_ptr()) });
 }

@@ -294,6 +294,7 @@ struct TraceCounters {
 // for "spheres only" etc. drop the other tests from the hot loop.
 #define RT_PM_ALL 0x3fu
 #define RT_PM_HAS(PM, T) (((PM) >> (T)) & 1u)
+#define RT_PAIR_BOUND(PM) (((PM) == 0x3u || (PM) == 0x5u) ? 2 : 0) // node steps of the sibling-pair walk before pending leaves are tested; 0 = unbounded
 // Tests every primitive of one leaf against the object-space ray.
 template <uint32_t PM = RT_PM_ALL>
 RT_DEV void leaf_test(const DeviceScene& S, const Ray& r, const RayPre& pre, double t_min, BestHit& best, uint32_t type, uint32_t first, uint32_t n,
@@ -411,7 +412,11 @@ RT_DEV void trace_instance(const DeviceScene& S, uint32_t inst_idx, const Ray& r
     uint32_t cur = __ldg(&S.instances[inst_idx].root);
     while (cur != DONE) {
         uint32_t leaf_first0 = 0, leaf_cnt0 = 0, leaf_first1 = 0, leaf_cnt1 = 0; // cnt = (type << 24) | n, 0 = none
-        while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0) {
+        // bounded node loop for the spheres + moving / gravity spheres kernels (see walk_wide): 2 steps, then the pending leaves are looked at
+        // (book-1 as shipped 169.0 -> 156.6 ms per 500 spp); unbounded elsewhere (Cornell smoke and book-2 final lose 2-9 % with any bound)
+        int inner = 0;
+#pragma unroll 1
+        while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0 && (RT_PAIR_BOUND(PM) == 0 || inner++ < RT_PAIR_BOUND(PM))) {
             // cur = index of the left node of a sibling pair: one 64-byte fetch, two slab tests
             float4 lo0, hi0, lo1, hi1;
             if (MOTION) { // box(t) = box at the shutter's start + s * delta: 128 bytes per sibling pair
@@ -481,7 +486,11 @@ RT_DEV void walk_pairs(const DeviceScene& S, const Ray& r, const RayF& f, const 
     const uint32_t n0 = __popc(__ballot_sync(full, cur != DONE));
     for (;;) {
         uint32_t leaf_first0 = 0, leaf_cnt0 = 0, leaf_first1 = 0, leaf_cnt1 = 0;
-        while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0) {
+        // bounded node loop for the spheres + moving / gravity spheres kernels (see walk_wide): 2 steps, then the pending leaves are looked at
+        // (book-1 as shipped 169.0 -> 156.6 ms per 500 spp); unbounded elsewhere (Cornell smoke and book-2 final lose 2-9 % with any bound)
+        int inner = 0;
+#pragma unroll 1
+        while (cur != DONE && (leaf_cnt0 | leaf_cnt1) == 0 && (RT_PAIR_BOUND(PM) == 0 || inner++ < RT_PAIR_BOUND(PM))) {
             float4 lo0, hi0, lo1, hi1;
             if (MOTION) {
                 lo0 = __ldg(mnodes + 4 * cur); hi0 = __ldg(mnodes + 4 * cur + 1);
@@ -581,7 +590,13 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
     uint32_t n0 = 0;
     if (RESUME) n0 = __popc(__ballot_sync(full, cur != DONE));
     for (;;) {
-        while (cur != DONE && !(cur & RT_LEAF_FLAG)) {
+        // Bounded node loop: a lane takes at most INNER node steps before the warp looks at the leaves that are pending.  Unbounded
+        // (the classic while-while) every lane that already holds a leaf idles until the slowest lane of the warp has found one; one
+        // step at a time (if-if) the leaf code is issued every iteration for few lanes.  Measured, same box (profiles/r2_41_ab_inner.txt):
+        // sphere scenes are best at 1 (book-1 final 86.9 -> 83.5 ms), the 871 200-triangle mesh at 6 (58.3 -> 52.0 ms per 10 spp).
+        constexpr int INNER = RT_PM_HAS(PM, PRIM_TRI) ? 6 : 1;
+#pragma unroll 1
+        for (int inner = 0; inner < INNER && cur != DONE && !(cur & RT_LEAF_FLAG); ++inner) {
             float4 lx, hx, ly, hy, lz, hz, rf;
             if (MOTION) { // box(t) = box at the shutter's start + s * delta: 256 bytes per node
                 const float4* __restrict__ q = mnodes4 + 16 * (size_t)cur;
@@ -611,7 +626,7 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
             if (k1 != ~0ull) stack[sp++] = k1;
             cur = (k0 != ~0ull) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
         }
-        if (cur != DONE) { // a leaf reference
+        if (cur != DONE && (cur & RT_LEAF_FLAG)) { // a leaf reference
             if (COUNT) cnt->prims += ((cur >> 25) & 7u) + 1u;
             leaf_test<PM>(S, r, pre, t_min, best, (cur >> 28) & 7u, cur & 0x1ffffffu, ((cur >> 25) & 7u) + 1u, inst);
             tmaxf = f32_up(best.t);
