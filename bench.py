@@ -426,7 +426,7 @@ def main():
             roofline["traffic_source"] = f"profiles/extend_traffic.json (ncu --set full capture {pj.get('capture', '?')}, kernel {pj.get('kernel', '?')}); not re-measured by this run"
             if "ncu" in pj:
                 roofline["ncu"] = pj["ncu"]  # issue-slot utilisation, active threads per instruction, stalls: what actually bounds the kernel
-                ia, th = pj["ncu"].get("issue_active_pct"), pj["ncu"].get("threads_per_inst")
+                ia, th = pj["ncu"].get("issue_active_pct"), pj["ncu"].get("threads_per_instruction")
                 if ia and th:
                     roofline["frac_binding"] = (ia / 100.0) * (th / 32.0)
                     roofline["binding"] = {"roof": "SIMT lane-issue slots (4 schedulers x 32 lanes per SM per cycle)", "issue_active": ia / 100.0, "active_threads_per_instruction": th,

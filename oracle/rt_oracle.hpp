@@ -5,10 +5,15 @@
 // cpu_baseline / --impl reference legs use it, as the checker and the CPU baseline.
 //
 // Parity pin: the reference (patrickzbhe/ray-tracing-series-rust) is pure Rust and cannot be
-// built here (no cargo/rustc).  Its own tests pin only src/vec3.rs:343-428 (replicated in
-// tests/test_oracle_kat.py).  Everything else is pinned by the hand-derived known-answer vectors
-// of SURVEY.md Appendix B and by structural invariants => "parity unpinned by reference tests,
-// pinned by derived KATs" (see DESIGN.md).
+// built here (no cargo/rustc).  What the reference itself holds for this path, and what pins
+// this restatement to it: (1) its only unit tests, src/vec3.rs:343-428 (replicated exactly in
+// tests/test_oracle_kat.py); (2) the three renders it ships, images/book1.png, book2.png,
+// stanford_dragon.png: unrendered black rows, saturated light, the analytic book-1 sky and the
+// mean radiance of every region the scene code fixes (tests/test_reference_images.py against
+// tests/golden/reference_images.json, made by tools/make_reference_image_fixture.py).  The
+// renders pin the path statistically (the reference's RNG is unseeded); the exact arithmetic
+// of single functions beyond vec3 has no reference-owned vector and is pinned by the
+// hand-derived known-answer vectors of SURVEY.md Appendix B and by structural invariants.
 //
 // Every function cites the reference file:line it follows.  Data structures deliberately keep
 // the reference's shape (pointer-based object graph, virtual dispatch, per-node reciprocal
