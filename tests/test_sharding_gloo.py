@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, scaling, out_path, tiles=False):
+def _worker(rank, world, port, scaling, out_path, tiles=False, how="reduce"):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -44,8 +44,10 @@ def _worker(rank, world, port, scaling, out_path, tiles=False):
     _, acc, st = s.render(cfg, want_accum=True)
     t = torch.from_numpy(acc)
     paths = torch.tensor([st["paths"]], dtype=torch.int64)
-    sharding.reduce_accumulators(t, dst=0)
+    sharding.reduce_accumulators(t, dst=0, how=how)
     dist.reduce(paths, dst=0, op=dist.ReduceOp.SUM)
+    if how == "allreduce" and rank == 1:  # every rank ends with the sum
+        np.save(out_path + ".rank1.npy", t.numpy())
     if rank == 0:
         np.save(out_path, t.numpy())
         np.save(out_path + ".paths.npy", paths.numpy())
@@ -93,6 +95,14 @@ def test_two_rank_tile_sharding_matches_single_process(orc, tmp_path):
         s.render(capi.make_config(40, 1.0, 6, 50, flags=(5 << 16) | (3 << 24)))
     with pytest.raises(ValueError):
         sharding.tile_flags(3, 3)
+
+
+def test_two_rank_allreduce_leaves_the_sum_on_every_rank(orc, tmp_path):
+    """bench.py --reduce allreduce (NVLS-capable collective on NVSwitch boxes): same sum, on both ranks"""
+    world = 2
+    out = str(tmp_path / "acc_all.npy")
+    mp.spawn(_worker, args=(world, _free_port(), "strong", out, False, "allreduce"), nprocs=world, join=True)
+    assert np.array_equal(np.load(out), np.load(out + ".rank1.npy")) and np.load(out).any()
 
 
 def test_sample_range_partition():
