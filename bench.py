@@ -187,7 +187,9 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--sharding", default="samples", choices=["samples", "tiles"],
                     help="N>1: sample ranges of every pixel (default) or 4-row tile bands dealt round-robin (SURVEY 8e alternative)")
-    ap.add_argument("--reduce", default="reduce", choices=["reduce", "allreduce"], help="N>1: the collective that sums the accumulators")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "reduce", "allreduce"],
+                    help="N>1: how the accumulators are summed: peer = the library's own kernel over NVLink peer memory (CUDA IPC, rt_peer_*; default), "
+                         "reduce / allreduce = one NCCL collective")
     ap.add_argument("--slots", type=int, default=0, help="resident path slots of the wavefront (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads reported under 'also'")
@@ -241,6 +243,19 @@ def main():
     paths_all = W * H * spp_total
 
     stream = torch.cuda.current_stream()
+    pg = None
+    if world > 1 and args.reduce == "peer":
+        try:
+            pg = sharding.PeerGroup(api, rank, world, W * H * 3)
+        except Exception as e:  # no IPC / peer route on this box: the NCCL reduce does the same sum
+            print(f"[bench] rank {rank}: peer group unavailable ({e})", file=sys.stderr)
+            pg = None
+        ok = torch.tensor([1 if pg is not None else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same path
+        if int(ok.item()) == 0:
+            if pg is not None:
+                pg.close()
+            pg, args.reduce = None, "reduce"
     accum = torch.zeros((H, W, 3), dtype=torch.int64, device="cuda")
     screen = torch.zeros((H, W, 3), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -251,14 +266,24 @@ def main():
         # on the same stream without a host round trip in between (single-launch modes; the wavefront ignores it)
         cfg = capi.make_config(W, aspect, spp_total, depth, seed=1 + step, sample_begin=s_begin, sample_end=s_end,
                                flags=(1 if timed_extend else 0) | (2 if count else 0) | (32 if no_wait else 0) | shard_flags)
-        accum.zero_()
         st = capi.Stats()
-        api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
+        sp = C.c_void_p(stream.cuda_stream)
+        if pg is not None and not local_only:
+            # the library's own exchange: render into the IPC-shared accumulator, publish a flag behind the kernel; rank 0's gather kernel
+            # waits for the flags on the device, reads the peers' sums over NVLink and resolves - nothing returns to the host in between
+            pg.begin(sp)
+            api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(pg.accum), sp, C.byref(st)))
+            pg.publish(sp)
+            if rank == 0:
+                pg.gather_resolve(C.c_void_p(screen.data_ptr()), W, H, spp_total, H, sp)
+            return st.as_dict()
+        accum.zero_()
+        api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), sp, C.byref(st)))
         if local_only:  # rank-0-only diagnostics after the other ranks have left: no collective
             return st.as_dict()
         sharding.reduce_accumulators(accum, dst=0, how=args.reduce)
         if rank == 0:
-            api.check(api.resolve_device(C.c_void_p(accum.data_ptr()), C.c_void_p(screen.data_ptr()), W, H, spp_total, H, C.c_void_p(stream.cuda_stream)))
+            api.check(api.resolve_device(C.c_void_p(accum.data_ptr()), C.c_void_p(screen.data_ptr()), W, H, spp_total, H, sp))
         return st.as_dict()
 
     def barrier():
@@ -284,7 +309,7 @@ def main():
         ev[k][0].record(stream)
         st = one_step(args.warmup + k, no_wait=True)
         ev[k][1].record(stream)
-        launches += st["kernel_launches"] + (1 if rank == 0 else 0)
+        launches += st["kernel_launches"] + ((2 + (2 if rank == 0 else 0)) if pg is not None else (1 if rank == 0 else 0))  # flag wait / publish kernels, gather + consumed flag
         if st["segments"] == 0 and st_warm is not None:  # enqueued without waiting: the device counters were not read back; the warm-up render of the same workload has them
             st = st_warm
         segments += st["segments"]
@@ -300,6 +325,10 @@ def main():
     ms_per_step = ms_total / args.steps
     value = paths_all * args.steps / (ms_total * 1e-3)
 
+    if pg is not None:
+        torch.cuda.synchronize()
+        if pg.timed_out():
+            raise SystemExit("bench.py: a peer never published its accumulator (rt_peer_timed_out)")
     # ---- book-2 final, the other north-star render, split the same way (all ranks; one timed render after a short warm-up)
     book2 = None
     if not args.no_extra and args.workload == "book1_final" and not args.spp and args.scaling == "strong":
@@ -441,8 +470,9 @@ def main():
         "dtype": "f64 geometry / f32 slabs+colour", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "image": [W, H], "spp_per_gpu": s_end - s_begin, "spp_total": spp_total, "max_depth": depth,
                    "paths_per_step": paths_all, "segments_per_path": segments / max(1, paths_local),
-                   "sharding": ("single GPU" if world == 1 else ("4-row tile bands round-robin + one NCCL int64 reduce (disjoint pixels) to rank 0" if shard_flags
-                                                                      else "sample ranges + one NCCL int64 reduce to rank 0")),
+                   "sharding": ("single GPU" if world == 1 else (("4-row tile bands round-robin" if shard_flags else "sample ranges") +
+                                                                      (" + the library's peer-memory gather (CUDA IPC, k_reduce_resolve on rank 0 reads the shards over NVLink)" if pg is not None
+                                                                       else f" + one NCCL int64 {args.reduce} to rank 0"))),
                    "render_mode": "fused persistent kernel (RT_MODE_AUTO)" if fused else "wavefront (RT_MODE_AUTO)",
                    "l2": "flushed between timed steps (256 MiB memset, untimed); path state > L2",
                    "vs_baseline_note": "README.md:23 146.440 s on 10 threads of an unspecified CPU => 1.456e6 paths/s (derived)",

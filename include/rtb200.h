@@ -283,6 +283,32 @@ RTB_EXPORT int32_t rt_resolve_device(const int64_t* d_accum, double* d_screen, i
                                      int32_t rendered_rows, void* cuda_stream);
 #endif
 
+/* ---------------------------------------------------------------- peer group (product only)
+ * The exchange of the one-process-per-GPU layout (torchrun) done by the library itself over NVLink peer memory instead of a
+ * collective: every rank renders into an accumulator the library allocates and exports through CUDA IPC; rank 0 maps all of them
+ * and ONE kernel there (the k_reduce_resolve of rt_render_multi) waits for each peer's "published" flag - written by the peer's
+ * stream behind its render - reads the shards in place, sums and resolves.  No host round trip between the render and the gather.
+ *   all ranks : g = rt_peer_create(rank, world, W*H*3, handle);  exchange the `world` handles (any transport);  rt_peer_connect(g, handles)
+ *   per step  : rt_peer_begin(g, stream)          waits until rank 0 has consumed the previous step, clears the accumulator
+ *               rt_render_device(scene, cfg | RT_RENDER_NO_WAIT, rt_peer_accum(g), stream, stats)
+ *               rt_peer_publish(g, stream)
+ *   rank 0    : rt_peer_gather_resolve(g, d_screen, W, H, spp, rows, stream)     Screen-layout doubles in device memory
+ * Waits are bounded (~2 s): rt_peer_timed_out(g) != 0 afterwards means a peer never published.  [ref: the mpsc gather of
+ * src/world.rs:1228-1240] */
+#ifndef RTB_PREFIX_ORC
+#define RT_PEER_HANDLE_BYTES 64
+typedef struct rt_peer_group rt_peer_group;
+RTB_EXPORT rt_peer_group* rt_peer_create(int32_t rank, int32_t world, int64_t n_elems, uint8_t out_handle[RT_PEER_HANDLE_BYTES]);
+RTB_EXPORT int32_t rt_peer_connect(rt_peer_group* g, const uint8_t* all_handles /* world x RT_PEER_HANDLE_BYTES */);
+RTB_EXPORT int64_t* rt_peer_accum(rt_peer_group* g);
+RTB_EXPORT int32_t rt_peer_begin(rt_peer_group* g, void* cuda_stream);
+RTB_EXPORT int32_t rt_peer_publish(rt_peer_group* g, void* cuda_stream);
+RTB_EXPORT int32_t rt_peer_gather_resolve(rt_peer_group* g, double* d_screen, int32_t width, int32_t height,
+                                          int32_t samples_per_pixel, int32_t rendered_rows, void* cuda_stream);
+RTB_EXPORT int32_t rt_peer_timed_out(rt_peer_group* g);
+RTB_EXPORT void rt_peer_destroy(rt_peer_group* g);
+#endif
+
 /* render_scene_with_time(t0, t1, path, world): the per-frame animation entry.  cfg == NULL uses the
  * reference's hard-coded frame settings: 500x500 (aspect 1.0), 500 spp, depth 50, camera
  * (13,2,3)->(0,0,0), vfov 20, aperture 0.1, focus 10, background (0.7,0.8,1), THREADS = 11 row bands

@@ -118,7 +118,17 @@ DEVICE_SIGNATURES = {
     # one process, N GPUs: shards rendered per device, accumulators summed + resolved over NVLink peer memory
     "render_multi": (C.c_int32, [_P, C.POINTER(RenderConfig), C.c_int32, C.c_int32, c_d3, C.POINTER(C.c_int64), C.POINTER(Stats)]),
     "scene_commit_multi": (C.c_int32, [_P, C.c_int32]),
+    # peer group: the one-process-per-GPU exchange over CUDA IPC + NVLink peer memory (no collective on the data path)
+    "peer_create": (_P, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_uint8)]),
+    "peer_connect": (C.c_int32, [_P, C.POINTER(C.c_uint8)]),
+    "peer_accum": (_P, [_P]),
+    "peer_begin": (C.c_int32, [_P, _P]),
+    "peer_publish": (C.c_int32, [_P, _P]),
+    "peer_gather_resolve": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "peer_timed_out": (C.c_int32, [_P]),
+    "peer_destroy": (None, [_P]),
 }
+RT_PEER_HANDLE_BYTES = 64
 RT_SHARD_SAMPLES = 0
 RT_SHARD_TILES = 1
 

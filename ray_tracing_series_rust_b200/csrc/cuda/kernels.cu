@@ -1024,16 +1024,28 @@ __global__ void __launch_bounds__(256) k_reduce_resolve(const AccumShards A, int
     const int64_t n = (int64_t)W * H * 3, n2 = n >> 1; // pairs of channels: 16-byte loads
     const int64_t rendered = (int64_t)W * rows * 3;
     const double scale = 1.0 / (double)spp;
+    if (A.need) { // shards rendered by other processes: wait until every peer's stream has published this step (flag in the peer's memory)
+        if (threadIdx.x < (unsigned)A.n && A.ready[threadIdx.x]) {
+            const volatile uint32_t* fl = A.ready[threadIdx.x];
+            const long long t0 = clock64();
+            while ((int32_t)(*fl - A.need) < 0) {
+                if (clock64() - t0 > 4000000000ll) break; // ~2 s at 1.9 GHz: a dead peer must not hang this GPU; the host checks the flags again
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        __threadfence_system();
+    }
     for (int64_t i2 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i2 < n2 + (n & 1); i2 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = 2 * i2;
         const bool pair = i + 1 < n;
         long long s0 = 0, s1 = 0;
         for (int g = 0; g < A.n; ++g) {
-            if (pair) {
-                const longlong2 v = *reinterpret_cast<const longlong2*>(A.p[g] + i);
+            if (pair) { // ld.cv: peers rewrite these lines every step; never served from a stale L1 line
+                const longlong2 v = __ldcv(reinterpret_cast<const longlong2*>(A.p[g] + i));
                 s0 += v.x; s1 += v.y;
             } else {
-                s0 += A.p[g][i];
+                s0 += __ldcv(reinterpret_cast<const long long*>(A.p[g] + i));
             }
         }
         if (sum_out) {
@@ -1119,6 +1131,29 @@ cudaError_t launch_resolve(const int64_t* d_accum, double* d_screen, int32_t W, 
     const int64_t n = (int64_t)W * H * 3;
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
     k_resolve<<<blocks, 256, 0, stream>>>(d_accum, d_screen, W, H, spp, rows);
+    return cudaGetLastError();
+}
+
+__global__ void k_flag_publish(uint32_t* flag, uint32_t value) {
+    __threadfence_system(); // everything this stream wrote before (the render's pixel sums) is visible to peers before the flag is
+    *reinterpret_cast<volatile uint32_t*>(flag) = value;
+    __threadfence_system();
+}
+__global__ void k_flag_wait(const uint32_t* flag, uint32_t need, uint32_t* timeout_flag) {
+    const volatile uint32_t* fl = flag;
+    const long long t0 = clock64();
+    while ((int32_t)(*fl - need) < 0) {
+        if (clock64() - t0 > 4000000000ll) { *timeout_flag = 1u; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+cudaError_t launch_flag_publish(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    k_flag_publish<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_flag_wait(const uint32_t* flag, uint32_t need, uint32_t* timeout_flag, cudaStream_t stream) {
+    k_flag_wait<<<1, 1, 0, stream>>>(flag, need, timeout_flag);
     return cudaGetLastError();
 }
 

@@ -55,7 +55,15 @@ cudaError_t launch_resolve(const int64_t* d_accum, double* d_screen, int32_t wid
 struct AccumShards {
     const int64_t* p[RT_MAX_GPUS];
     int32_t n;
+    // Cross-process shards (rt_peer_*, one process per GPU): shard g is complete once *ready[g] >= need (a flag in the peer's own
+    // allocation, written by its stream after its render); the kernel waits for that itself.  need == 0: no waiting (one process).
+    const uint32_t* ready[RT_MAX_GPUS];
+    uint32_t need;
 };
+// one-thread flag kernels of the peer group: publish writes `value` to a flag after a system-wide fence; wait spins until a (peer's)
+// flag reaches `need` (bounded: ~2 s, then *timeout_flag = 1 and it gives up instead of hanging the GPU)
+cudaError_t launch_flag_publish(uint32_t* flag, uint32_t value, cudaStream_t stream);
+cudaError_t launch_flag_wait(const uint32_t* flag, uint32_t need, uint32_t* timeout_flag, cudaStream_t stream);
 cudaError_t launch_reduce_resolve(const AccumShards& shards, int64_t* d_sum_out, uint8_t* d_screen_u8, double* d_screen_f64, int32_t W, int32_t H, int32_t spp,
                                   int32_t rows, cudaStream_t stream);
 

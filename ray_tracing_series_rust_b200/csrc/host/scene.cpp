@@ -1302,6 +1302,7 @@ int32_t rt_render(rt_scene* s, const rt_render_config* cfg, double* out_screen, 
     if (stats) std::memset(stats, 0, sizeof *stats);
     if ((e = launch_render(s->dev.scene, job, tuning_for(s, cfg), o.d_accum, o.stream, stats, &s->workspace)) != cudaSuccess) return fail_cuda(e, "render");
     AccumShards sh;
+    std::memset(&sh, 0, sizeof sh);
     sh.n = 1;
     sh.p[0] = o.d_accum;
     if ((rc = gather_and_copy_out(s, sh, job, out_screen, out_accum)) != RT_OK) return rc;
@@ -1446,6 +1447,7 @@ int32_t rt_render_multi(rt_scene* s, const rt_render_config* cfg, int32_t n_gpus
     for (int g = 0; g < n_gpus; ++g)
         if (errs[(size_t)g] != cudaSuccess) return fail_cuda(errs[(size_t)g], "render (multi-GPU shard)");
     AccumShards sh;
+    std::memset(&sh, 0, sizeof sh);
     sh.n = n_gpus;
     sh.p[0] = s->out.d_accum;
     for (int g = 1; g < n_gpus; ++g) {
@@ -1475,6 +1477,109 @@ int32_t rt_render_multi(rt_scene* s, const rt_render_config* cfg, int32_t n_gpus
         stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     return RT_OK;
+}
+
+// ---- peer group: the exchange of the one-process-per-GPU layout without a collective library on the data path
+struct rt_peer_group {
+    int32_t rank = 0, world = 1;
+    int64_t n_elems = 0;
+    char* base = nullptr;                 // own allocation: n_elems int64 + one 256-byte flag block
+    std::vector<char*> peer;              // every rank's allocation as mapped here (own slot = base)
+    uint32_t step = 0;                    // steps published by this rank so far
+    uint32_t* d_timeout = nullptr;
+    bool connected = false;
+    int64_t* accum(int r) const { return reinterpret_cast<int64_t*>(peer[(size_t)r]); }
+    uint32_t* published(int r) const { return reinterpret_cast<uint32_t*>(peer[(size_t)r] + (size_t)n_elems * sizeof(int64_t)); }
+    uint32_t* consumed(int r) const { return published(r) + 16; } // its own 64-byte line
+};
+
+rt_peer_group* rt_peer_create(int32_t rank, int32_t world, int64_t n_elems, uint8_t out_handle[RT_PEER_HANDLE_BYTES]) {
+    if (rank < 0 || world < 1 || rank >= world || world > RT_MAX_GPUS || n_elems <= 0 || !out_handle) { fail(RT_ERR_INVALID, "bad peer group request"); return nullptr; }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= RT_PEER_HANDLE_BYTES, "handle size");
+    rt_peer_group* g = new rt_peer_group();
+    g->rank = rank; g->world = world; g->n_elems = n_elems;
+    const size_t bytes = (size_t)n_elems * sizeof(int64_t) + 256;
+    cudaError_t e = cudaMalloc(&g->base, bytes);
+    if (e == cudaSuccess) e = cudaMemset(g->base, 0, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_timeout, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(g->d_timeout, 0, sizeof(uint32_t));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, g->base);
+    if (e != cudaSuccess) { fail_cuda(e, "peer group allocation"); rt_peer_destroy(g); return nullptr; }
+    std::memset(out_handle, 0, RT_PEER_HANDLE_BYTES);
+    std::memcpy(out_handle, &h, sizeof h);
+    g->peer.assign((size_t)world, nullptr);
+    g->peer[(size_t)rank] = g->base;
+    return g;
+}
+
+int32_t rt_peer_connect(rt_peer_group* g, const uint8_t* all_handles) {
+    if (!g || !all_handles) return fail(RT_ERR_INVALID, "null peer group");
+    for (int r = 0; r < g->world; ++r) {
+        if (r == g->rank || g->peer[(size_t)r]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, all_handles + (size_t)r * RT_PEER_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaIpcOpenMemHandle (peer accumulator)");
+        g->peer[(size_t)r] = static_cast<char*>(p);
+    }
+    g->connected = true;
+    return RT_OK;
+}
+
+int64_t* rt_peer_accum(rt_peer_group* g) { return g ? reinterpret_cast<int64_t*>(g->base) : nullptr; }
+
+int32_t rt_peer_begin(rt_peer_group* g, void* cuda_stream) {
+    if (!g || !g->connected) return fail(RT_ERR_STATE, "peer group not connected");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaError_t e = cudaSuccess;
+    // the gatherer (rank 0) must have read the previous step's sums before they are cleared
+    if (g->rank != 0 && g->step > 0) e = launch_flag_wait(g->consumed(0), g->step, g->d_timeout, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->base, 0, (size_t)g->n_elems * sizeof(int64_t), st);
+    if (e != cudaSuccess) return fail_cuda(e, "peer begin");
+    return RT_OK;
+}
+
+int32_t rt_peer_publish(rt_peer_group* g, void* cuda_stream) {
+    if (!g || !g->connected) return fail(RT_ERR_STATE, "peer group not connected");
+    ++g->step;
+    const cudaError_t e = launch_flag_publish(g->published(g->rank), g->step, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return fail_cuda(e, "peer publish");
+    return RT_OK;
+}
+
+int32_t rt_peer_gather_resolve(rt_peer_group* g, double* d_screen, int32_t width, int32_t height, int32_t spp, int32_t rendered_rows, void* cuda_stream) {
+    if (!g || !g->connected) return fail(RT_ERR_STATE, "peer group not connected");
+    if (g->rank != 0) return fail(RT_ERR_STATE, "rank 0 gathers");
+    if (!d_screen || width <= 0 || height <= 0 || spp <= 0 || (int64_t)width * height * 3 != g->n_elems) return fail(RT_ERR_INVALID, "bad gather arguments");
+    if (g->step == 0) return fail(RT_ERR_STATE, "rt_peer_publish first");
+    AccumShards sh;
+    std::memset(&sh, 0, sizeof sh);
+    sh.n = g->world;
+    sh.need = g->step;
+    for (int r = 0; r < g->world; ++r) { sh.p[r] = g->accum(r); sh.ready[r] = g->published(r); }
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaError_t e = launch_reduce_resolve(sh, nullptr, nullptr, d_screen, width, height, spp, rendered_rows, st);
+    if (e == cudaSuccess) e = launch_flag_publish(g->consumed(0), g->step, st); // the peers may clear their accumulators now
+    if (e != cudaSuccess) return fail_cuda(e, "peer gather");
+    return RT_OK;
+}
+
+int32_t rt_peer_timed_out(rt_peer_group* g) {
+    if (!g) return RT_ERR_INVALID;
+    uint32_t v = 0;
+    if (cudaMemcpy(&v, g->d_timeout, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return RT_ERR_CUDA;
+    return (int32_t)v;
+}
+
+void rt_peer_destroy(rt_peer_group* g) {
+    if (!g) return;
+    for (int r = 0; r < (int)g->peer.size(); ++r)
+        if (r != g->rank && g->peer[(size_t)r]) cudaIpcCloseMemHandle(g->peer[(size_t)r]);
+    if (g->base) cudaFree(g->base);
+    if (g->d_timeout) cudaFree(g->d_timeout);
+    delete g;
 }
 
 int32_t rt_write_ppm(const char* path, const double* screen, int32_t width, int32_t height) {

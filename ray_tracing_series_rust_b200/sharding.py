@@ -34,6 +34,56 @@ def reduce_accumulators(accum, dst: int = 0, how: str = "reduce"):
     return accum
 
 
+class PeerGroup:
+    """The accumulator exchange of the one-process-per-GPU layout done by librtb200 itself over NVLink peer memory (rt_peer_*,
+    include/rtb200.h): every rank renders into a library-owned accumulator exported through CUDA IPC, rank 0 maps them all and one
+    kernel there waits for each peer's published flag, sums the shards in place and resolves the Screen.  torch.distributed is used
+    once, to hand the 64-byte IPC handles round (plumbing); the data path has no collective.
+
+        pg = PeerGroup(api, rank, world, W * H * 3)           # collective: all ranks
+        per step:  pg.begin(stream); rt_render_device(..., pg.accum, stream, NO_WAIT); pg.publish(stream)
+                   rank 0: pg.gather_resolve(screen_ptr, W, H, spp, rows, stream)
+    """
+
+    def __init__(self, api, rank: int, world: int, n_elems: int):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        self.api, self.rank, self.world = api, rank, world
+        handle = (C.c_uint8 * 64)()
+        self.h = api.peer_create(rank, world, int(n_elems), handle)
+        if not self.h:
+            raise RuntimeError("rt_peer_create failed: " + api.err())
+        mine = torch.tensor(list(handle), dtype=torch.uint8)
+        if world > 1:
+            dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+            parts = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(parts, mine.to(dev))
+            allh = torch.cat([p.cpu() for p in parts])
+        else:
+            allh = mine
+        buf = (C.c_uint8 * (64 * world))(*allh.tolist())
+        api.check(api.peer_connect(self.h, buf))
+        self.accum = api.peer_accum(self.h)
+
+    def begin(self, stream_ptr):
+        self.api.check(self.api.peer_begin(self.h, stream_ptr))
+
+    def publish(self, stream_ptr):
+        self.api.check(self.api.peer_publish(self.h, stream_ptr))
+
+    def gather_resolve(self, screen_ptr, W, H, spp, rows, stream_ptr):
+        self.api.check(self.api.peer_gather_resolve(self.h, screen_ptr, W, H, spp, rows, stream_ptr))
+
+    def timed_out(self) -> bool:
+        return self.api.peer_timed_out(self.h) != 0
+
+    def close(self):
+        if self.h:
+            self.api.peer_destroy(self.h)
+            self.h = None
+
+
 def frames_for_rank(n_frames: int, rank: int, world: int):
     """Animation sharding: frame f goes to rank f mod world; no collective, each frame is
     committed (shutter window) and rendered on one GPU.  [ref: render_scene_with_time, src/world.rs:1249]"""

@@ -131,3 +131,68 @@ def test_multi_symbols_are_exported_and_refuse_without_gpu():
         with pytest.raises(capi.RtError) as e:
             s.render_multi(capi.make_config(32, 1.5, 1, 5), 2)
         assert e.value.code == -2  # not committed
+
+
+# ---------------------------------------------------------------- peer group: one process per GPU, exchange over CUDA IPC
+def _peer_worker(rank, world, port, out_path, n_dev):
+    import sys
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # plumbing only: hands the IPC handles round
+    torch.cuda.set_device(rank % n_dev)  # two processes share cuda:0 on a 1-GPU box: CUDA IPC works between processes on one device too
+    import ray_tracing_series_rust_b200 as rtb
+    from ray_tracing_series_rust_b200 import capi, sharding
+    api = rtb.load()
+    g = rtb.new_scene()
+    g.world_build(13, 0xB001, 0)
+    g.commit()
+    W, aspect, spp = 120, 1.5, 9
+    H = g.image_height(capi.make_config(W, aspect, 1, 50))
+    pg = sharding.PeerGroup(api, rank, world, W * H * 3)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    screen = torch.zeros((H, W, 3), dtype=torch.float64, device="cuda")
+    outs = []
+    for step in range(3):  # several steps: begin() must wait for rank 0's consumption of the previous one
+        _, b, e = sharding.sample_range(spp, rank, world, "strong")
+        cfg = capi.make_config(W, aspect, spp, 50, seed=40 + step, sample_begin=b, sample_end=e, flags=32)  # RT_RENDER_NO_WAIT
+        pg.begin(sp)
+        st = capi.Stats()
+        api.check(api.render_device(g.h, C.byref(cfg), C.c_void_p(pg.accum), sp, C.byref(st)))
+        pg.publish(sp)
+        if rank == 0:
+            pg.gather_resolve(C.c_void_p(screen.data_ptr()), W, H, spp, H, sp)
+            torch.cuda.synchronize()
+            outs.append(screen.cpu().numpy().copy())
+    torch.cuda.synchronize()
+    assert not pg.timed_out()
+    dist.barrier()
+    if rank == 0:
+        np.save(out_path, np.stack(outs))
+    pg.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_group_gather_equals_single_render(tmp_path):
+    """two processes (one GPU each when the box has two, else both on cuda:0) render sample ranges into IPC-shared accumulators;
+    rank 0's k_reduce_resolve waits for the published flags, sums the shards where they lie and resolves: the Screen of every
+    step equals the single-process rt_render Screen of the same seed, bit for bit"""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "peer_screens.npy")
+    world = 2
+    mp.spawn(_peer_worker, args=(world, port, out, max(1, _device_count())), nprocs=world, join=True)
+    got = np.load(out)
+    g = _scene(13)
+    for step in range(3):
+        ref, _, _ = g.render(capi.make_config(120, 1.5, 9, 50, seed=40 + step))
+        assert np.array_equal(got[step], ref), step
+    g.close()
