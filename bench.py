@@ -325,6 +325,15 @@ def main():
     ms_per_step = ms_total / args.steps
     value = paths_all * args.steps / (ms_total * 1e-3)
 
+    if os.environ.get("RTB200_BENCH_DEBUG"):  # per-rank device time of this rank's shard alone (waits for the kernel: not part of any reported number)
+        barrier()
+        ms_dbg = []
+        for k in range(3):
+            flush.zero_()
+            barrier()
+            ms_dbg.append(one_step(2000 + k, local_only=True)["ms_device"])
+        print(f"[bench debug] rank {rank}: shard spp {s_end - s_begin}, k_mega ms {[round(x, 3) for x in ms_dbg]}, ideal {ms_per_step:.3f} step", file=sys.stderr, flush=True)
+        barrier()
     if pg is not None:
         torch.cuda.synchronize()
         if pg.timed_out():

@@ -1025,12 +1025,15 @@ __global__ void __launch_bounds__(256) k_reduce_resolve(const AccumShards A, int
     const int64_t rendered = (int64_t)W * rows * 3;
     const double scale = 1.0 / (double)spp;
     if (A.need) { // shards rendered by other processes: wait until every peer's stream has published this step (flag in the peer's memory)
-        if (threadIdx.x < (unsigned)A.n && A.ready[threadIdx.x]) {
-            const volatile uint32_t* fl = A.ready[threadIdx.x];
+        if (threadIdx.x == 0) { // one poller per CTA, the peers one after the other: the flags live in the peers' memory (NVLink reads)
             const long long t0 = clock64();
-            while ((int32_t)(*fl - A.need) < 0) {
-                if (clock64() - t0 > 4000000000ll) break; // ~2 s at 1.9 GHz: a dead peer must not hang this GPU; the host checks the flags again
-                __nanosleep(200);
+            for (int g = 0; g < A.n; ++g) {
+                const volatile uint32_t* fl = A.ready[g];
+                if (!fl) continue;
+                while ((int32_t)(*fl - A.need) < 0) {
+                    if (clock64() - t0 > 4000000000ll) break; // ~2 s at 1.9 GHz: a dead peer must not hang this GPU
+                    __nanosleep(500);
+                }
             }
         }
         __syncthreads();
@@ -1375,9 +1378,11 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
             // Path indices are claimed per warp in chunks of consecutive indices (neighbouring pixels of one sample).  512 is best for
             // long renders (fewer atomics, coherent refills: book-1 final -1.7 % at 128); short renders need smaller chunks or the
             // last chunks leave most warps idle (871k mesh at 10 spp: 127 -> 141 Mpaths/s at 128, 64 at 4096): aim at >= 64 chunks per warp
+            // Round 2 (tools/chunk_probe.py, book-1 final): the sphere scenes want the full 512 down to 31-spp renders (62 spp, one of
+            // eight strong-scaling shards: 10.98 ms at 96, 10.87 at 512, 11.35 at 1024), so only deep-mesh renders shrink their chunks
             {
                 const unsigned long long warps = 148ull * 7ull * 4ull;
-                unsigned long long c = J.total_paths / (warps * 64ull);
+                unsigned long long c = J.total_paths / (warps * ((scene.flags & 4u) ? 64ull : 4ull));
                 c = std::max(32ull, std::min((unsigned long long)RT_MEGA_CHUNK, c)) & ~31ull;
                 J.chunk = (uint32_t)c;
             }
