@@ -241,6 +241,11 @@ def main():
         s_begin, s_end = 0, spp_total
         shard_flags = sharding.tile_flags(rank, world)
     paths_all = W * H * spp_total
+    # strong scaling with sample sharding: split the PATHS evenly (rt_render_device_paths), not the samples: 500 spp on 8 GPUs is 62.5 each
+    path_shard = None
+    if world > 1 and args.scaling == "strong" and not shard_flags:
+        path_shard = sharding.path_range(W * H, spp_total, rank, world)
+        s_begin, s_end = 0, spp_total
 
     stream = torch.cuda.current_stream()
     pg = None
@@ -272,13 +277,19 @@ def main():
             # the library's own exchange: render into the IPC-shared accumulator, publish a flag behind the kernel; rank 0's gather kernel
             # waits for the flags on the device, reads the peers' sums over NVLink and resolves - nothing returns to the host in between
             pg.begin(sp)
-            api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(pg.accum), sp, C.byref(st)))
+            if path_shard is not None:  # an even split of any sample count: whole samples plus a partial first / last one
+                api.check(api.render_device_paths(scene.h, C.byref(cfg), path_shard[0], path_shard[1], C.c_void_p(pg.accum), sp, C.byref(st)))
+            else:
+                api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(pg.accum), sp, C.byref(st)))
             pg.publish(sp)
             if rank == 0:
                 pg.gather_resolve(C.c_void_p(screen.data_ptr()), W, H, spp_total, H, sp)
             return st.as_dict()
         accum.zero_()
-        api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), sp, C.byref(st)))
+        if path_shard is not None and not local_only:
+            api.check(api.render_device_paths(scene.h, C.byref(cfg), path_shard[0], path_shard[1], C.c_void_p(accum.data_ptr()), sp, C.byref(st)))
+        else:
+            api.check(api.render_device(scene.h, C.byref(cfg), C.c_void_p(accum.data_ptr()), sp, C.byref(st)))
         if local_only:  # rank-0-only diagnostics after the other ranks have left: no collective
             return st.as_dict()
         sharding.reduce_accumulators(accum, dst=0, how=args.reduce)
@@ -477,7 +488,7 @@ def main():
         "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": (value / README_BOOK1_10T_PATHS_PER_S) if (args.workload == "book1_final" and not args.spp) else None,
         "dtype": "f64 geometry / f32 slabs+colour", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "image": [W, H], "spp_per_gpu": s_end - s_begin, "spp_total": spp_total, "max_depth": depth,
+        "config": {"workload": args.workload, "description": desc, "image": [W, H], "spp_per_gpu": (spp_total / world) if path_shard is not None else (s_end - s_begin), "spp_total": spp_total, "max_depth": depth,
                    "paths_per_step": paths_all, "segments_per_path": segments / max(1, paths_local),
                    "sharding": ("single GPU" if world == 1 else (("4-row tile bands round-robin" if shard_flags else "sample ranges") +
                                                                       (" + the library's peer-memory gather (CUDA IPC, k_reduce_resolve on rank 0 reads the shards over NVLink)" if pg is not None

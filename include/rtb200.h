@@ -278,6 +278,11 @@ RTB_EXPORT int32_t RTB_FN(image_height)(const rt_render_config* cfg);
  * rt_resolve_device turns a reduced accumulator into the Screen-layout image (device doubles). */
 RTB_EXPORT int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg,
                                     int64_t* d_accum, void* cuda_stream, rt_stats* stats);
+/* A path-range shard: of the call's paths (its pixels x its samples [sample_begin, sample_end), enumerated sample-major: index =
+ * sample * pixels + pixel) only [path_begin, path_end) are rendered - whole samples plus a partial first / last one.  Lets N ranks
+ * split ANY sample count evenly (500 spp on 8 GPUs = 62.5 each); the sum of the shards is bit-identical to the whole render. */
+RTB_EXPORT int32_t rt_render_device_paths(rt_scene* s, const rt_render_config* cfg, uint64_t path_begin, uint64_t path_end,
+                                          int64_t* d_accum, void* cuda_stream, rt_stats* stats);
 RTB_EXPORT int32_t rt_resolve_device(const int64_t* d_accum, double* d_screen, int32_t width,
                                      int32_t height, int32_t samples_per_pixel,
                                      int32_t rendered_rows, void* cuda_stream);

@@ -115,6 +115,7 @@ SIGNATURES = {
 DEVICE_SIGNATURES = {
     "render_device": (C.c_int32, [_P, C.POINTER(RenderConfig), _P, _P, C.POINTER(Stats)]),
     "resolve_device": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "render_device_paths": (C.c_int32, [_P, C.POINTER(RenderConfig), C.c_uint64, C.c_uint64, _P, _P, C.POINTER(Stats)]),
     # one process, N GPUs: shards rendered per device, accumulators summed + resolved over NVLink peer memory
     "render_multi": (C.c_int32, [_P, C.POINTER(RenderConfig), C.c_int32, C.c_int32, c_d3, C.POINTER(C.c_int64), C.POINTER(Stats)]),
     "scene_commit_multi": (C.c_int32, [_P, C.c_int32]),

@@ -66,6 +66,7 @@ struct JobDev {
     uint32_t wait_thresh; // k_mega_r: finished lanes that end a traversal round
     uint32_t tile_rank, tile_count; // RT_RENDER_TILE_SHARD: npix_rendered counts this shard's pixels only
     uint32_t chunk;                 // fused kernels: consecutive path indices a warp claims per atomic
+    unsigned long long path_base;   // this call renders the path indices [path_base, path_base + total_paths) of the sample-major enumeration
 };
 
 // Path-state chunks are streamed (read once / written once per kernel): evict-first hints keep them from
@@ -161,7 +162,7 @@ RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queu
     }
     // sample-major order: consecutive path indices are neighbouring pixels of one sample => coherent primary rays
     uint32_t s_local, pix;
-    split_path_index(L, J.npix_rendered, s_local, pix);
+    split_path_index(L + J.path_base, J.npix_rendered, s_local, pix);
     pix = shard_pixel(J, pix);
     const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix - (uint32_t)j * (uint32_t)J.W);
     const uint64_t path_id = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                     exhausted = true;
                 } else {
                     uint32_t s_local;
-                    split_path_index(L, J.npix_rendered, s_local, pixel);
+                    split_path_index(L + J.path_base, J.npix_rendered, s_local, pixel);
                     pixel = shard_pixel(J, pixel);
                     const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
                     path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
                     exhausted = true;
                 } else {
                     uint32_t s_local;
-                    split_path_index(L, J.npix_rendered, s_local, pixel);
+                    split_path_index(L + J.path_base, J.npix_rendered, s_local, pixel);
                     pixel = shard_pixel(J, pixel);
                     const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
                     path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
@@ -795,7 +796,7 @@ __global__ void __launch_bounds__(128, MINB) k_pool(const __grid_constant__ Devi
                     ok = true;
                     sl = W.q_regen[base + lane];
                     uint32_t s_local, pixel, draw0;
-                    split_path_index(L, J.npix_rendered, s_local, pixel);
+                    split_path_index(L + J.path_base, J.npix_rendered, s_local, pixel);
                     pixel = shard_pixel(J, pixel);
                     const int32_t j = (int32_t)(pixel / (uint32_t)J.W), ii = (int32_t)(pixel - (uint32_t)j * (uint32_t)J.W);
                     const uint64_t path_id = (uint64_t)pixel * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
@@ -1303,6 +1304,11 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
     }
     J.npix_rendered = (uint32_t)job.width * local_rows;
     J.total_paths = (unsigned long long)J.npix_rendered * (unsigned long long)(job.sample_end - job.sample_begin);
+    J.path_base = 0;
+    if (job.path_end > job.path_begin) { // a path-range shard of [sample_begin, sample_end): whole samples plus a partial first / last one
+        J.path_base = std::min<unsigned long long>(job.path_begin, J.total_paths);
+        J.total_paths = std::min<unsigned long long>(job.path_end, J.total_paths) - J.path_base;
+    }
     J.seed = job.seed;
     J.count_events = tune.count_events;
     uint32_t N = tune.wave_slots;

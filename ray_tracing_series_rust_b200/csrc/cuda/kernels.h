@@ -17,6 +17,9 @@ struct RenderJob {
     int32_t max_depth;
     uint64_t seed;
     int32_t tile_rank = 0, tile_count = 1; // RT_RENDER_TILE_SHARD: this call renders the row bands b with b % tile_count == tile_rank
+    // rt_render_device_paths: only the path indices [path_begin, path_end) of the call's (pixels x samples) in sample-major order
+    // (index = sample * pixels + pixel); 0, 0 = all of them
+    uint64_t path_begin = 0, path_end = 0;
 };
 
 #define RT_MODE_WAVEFRONT 0 // k_extend + k_shade_all per iteration, per-material queues, path state in HBM

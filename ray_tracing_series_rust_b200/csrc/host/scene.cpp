@@ -1206,6 +1206,17 @@ static int32_t make_job(rt_scene* s, const rt_render_config* cfg, RenderJob& job
     return RT_OK;
 }
 
+static RenderTuning tuning_for_flags(const rt_scene* s, const rt_render_config* cfg) {
+    RenderTuning tune = s->tuning;
+    tune.timed_extend = (cfg->flags & RT_RENDER_TIMED_EXTEND) ? 1 : 0;
+    tune.count_events = (cfg->flags & RT_RENDER_COUNT_EVENTS) ? 1 : 0;
+    if (cfg->flags & RT_RENDER_FORCE_WAVEFRONT) tune.mode = RT_MODE_WAVEFRONT;
+    if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
+    if (cfg->flags & RT_RENDER_FORCE_POOL) tune.mode = RT_MODE_POOL;
+    if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
+    return tune;
+}
+
 int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg, int64_t* d_accum, void* cuda_stream, rt_stats* stats) {
     CHECK_SCENE(s);
     if (!d_accum) return fail(RT_ERR_INVALID, "null accumulator");
@@ -1214,13 +1225,29 @@ int32_t rt_render_device(rt_scene* s, const rt_render_config* cfg, int64_t* d_ac
     if (r != RT_OK) return r;
     if (stats) std::memset(stats, 0, sizeof *stats);
     const auto t0 = std::chrono::steady_clock::now();
-    RenderTuning tune = s->tuning;
-    tune.timed_extend = (cfg->flags & RT_RENDER_TIMED_EXTEND) ? 1 : 0;
-    tune.count_events = (cfg->flags & RT_RENDER_COUNT_EVENTS) ? 1 : 0;
-    if (cfg->flags & RT_RENDER_FORCE_WAVEFRONT) tune.mode = RT_MODE_WAVEFRONT;
-    if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
-    if (cfg->flags & RT_RENDER_FORCE_POOL) tune.mode = RT_MODE_POOL;
-    if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
+    RenderTuning tune = tuning_for_flags(s, cfg);
+    tune.no_wait = (cfg->flags & RT_RENDER_NO_WAIT) ? 1 : 0;
+    const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats, &s->workspace);
+    if (e != cudaSuccess) return fail_cuda(e, "render");
+    if (stats) stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return RT_OK;
+}
+
+int32_t rt_render_device_paths(rt_scene* s, const rt_render_config* cfg, uint64_t path_begin, uint64_t path_end, int64_t* d_accum, void* cuda_stream, rt_stats* stats) {
+    CHECK_SCENE(s);
+    if (!d_accum) return fail(RT_ERR_INVALID, "null accumulator");
+    RenderJob job;
+    const int32_t r = make_job(s, cfg, job);
+    if (r != RT_OK) return r;
+    if (path_begin > path_end) return fail(RT_ERR_INVALID, "bad path range");
+    if (path_begin == path_end) { // an empty shard renders nothing
+        if (stats) std::memset(stats, 0, sizeof *stats);
+        return RT_OK;
+    }
+    job.path_begin = path_begin; job.path_end = path_end;
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    const auto t0 = std::chrono::steady_clock::now();
+    RenderTuning tune = tuning_for_flags(s, cfg);
     tune.no_wait = (cfg->flags & RT_RENDER_NO_WAIT) ? 1 : 0;
     const cudaError_t e = launch_render(s->dev.scene, job, tune, d_accum, (cudaStream_t)cuda_stream, stats, &s->workspace);
     if (e != cudaSuccess) return fail_cuda(e, "render");
@@ -1275,16 +1302,7 @@ int32_t gather_and_copy_out(rt_scene* s, const AccumShards& shards, const Render
     return RT_OK;
 }
 
-RenderTuning tuning_for(const rt_scene* s, const rt_render_config* cfg) {
-    RenderTuning tune = s->tuning;
-    tune.timed_extend = (cfg->flags & RT_RENDER_TIMED_EXTEND) ? 1 : 0;
-    tune.count_events = (cfg->flags & RT_RENDER_COUNT_EVENTS) ? 1 : 0;
-    if (cfg->flags & RT_RENDER_FORCE_WAVEFRONT) tune.mode = RT_MODE_WAVEFRONT;
-    if (cfg->flags & RT_RENDER_FORCE_FUSED) tune.mode = RT_MODE_FUSED;
-    if (cfg->flags & RT_RENDER_FORCE_POOL) tune.mode = RT_MODE_POOL;
-    if (tune.timed_extend || tune.count_events) tune.mode = RT_MODE_WAVEFRONT; // both are diagnostics of the wavefront's k_extend
-    return tune;
-}
+RenderTuning tuning_for(const rt_scene* s, const rt_render_config* cfg) { return tuning_for_flags(s, cfg); }
 
 } // namespace
 

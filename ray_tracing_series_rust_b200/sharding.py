@@ -21,6 +21,16 @@ def sample_range(spp: int, rank: int, world: int, scaling: str = "strong"):
     return spp, (spp * rank) // world, (spp * (rank + 1)) // world
 
 
+def path_range(n_pixels: int, spp: int, rank: int, world: int):
+    """Even split of ANY sample count: rank r renders the path indices [T r / N, T (r + 1) / N) of the sample-major enumeration
+    (index = sample * pixels + pixel, T = pixels * spp) through rt_render_device_paths: whole samples plus a partial first / last one
+    (500 spp on 8 GPUs = 62.5 each instead of 62 or 63)."""
+    if world < 1 or not (0 <= rank < world) or spp < 1 or n_pixels < 1:
+        raise ValueError("bad shard request")
+    total = n_pixels * spp
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
 def reduce_accumulators(accum, dst: int = 0, how: str = "reduce"):
     """Sum the per-rank int64 accumulators onto `dst` (NCCL on GPU tensors, gloo on CPU tensors).
     how = "reduce" (one ncclReduce to dst) or "allreduce" (every rank ends with the sum; on NVSwitch boxes NCCL can then reduce

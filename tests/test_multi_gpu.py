@@ -196,3 +196,31 @@ def test_peer_group_gather_equals_single_render(tmp_path):
         ref, _, _ = g.render(capi.make_config(120, 1.5, 9, 50, seed=40 + step))
         assert np.array_equal(got[step], ref), step
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene_id,flags", [(13, 0), (13, 4), (5, 0), (14, 0)])
+def test_path_range_shards_add_up(scene_id, flags):
+    """rt_render_device_paths: N contiguous ranges of the sample-major path enumeration (whole samples plus partial ones) sum to the
+    whole render, bit for bit, for shard counts that do not divide the sample count; fused, wavefront and resumable kernels"""
+    import ctypes as C
+    import torch
+    from ray_tracing_series_rust_b200 import sharding
+    api = rtb.load()
+    g = _scene(scene_id, param=40 if scene_id == 14 else 0)
+    W, aspect, spp = 72, 1.0 if scene_id != 13 else 1.5, 5
+    cfg = capi.make_config(W, aspect, spp, 50, seed=8, flags=flags)
+    _, ref, st_ref = g.render(cfg, want_accum=True)
+    H = ref.shape[0]
+    stream = torch.cuda.current_stream()
+    for n in (3, 8):
+        acc = torch.zeros((H, W, 3), dtype=torch.int64, device="cuda")
+        paths = 0
+        for r in range(n):
+            b, e = sharding.path_range(W * H, spp, r, n)
+            st = capi.Stats()
+            api.check(api.render_device_paths(g.h, C.byref(cfg), b, e, C.c_void_p(acc.data_ptr()), C.c_void_p(stream.cuda_stream), C.byref(st)))
+            paths += st.paths
+        torch.cuda.synchronize()
+        assert paths == st_ref["paths"] and np.array_equal(acc.cpu().numpy(), ref), (scene_id, n)
+    g.close()
