@@ -253,8 +253,8 @@ RTB_EXPORT int32_t RTB_FN(render)(rt_scene* s, const rt_render_config* cfg, doub
 /* The same render spread over n_gpus GPUs of this box by ONE host thread of ONE process (what a Rust render_scene_gpu calls to
  * use the whole 8 x B200 node; SURVEY.md 8(b) n_gpus / shard_mode, 8(e)).  GPU 0 is the device the scene was committed on, GPUs
  * 1..n-1 are the next visible devices; each gets the committed scene's flattened bytes (uploaded once per commit, or ahead of time
- * by rt_scene_commit_multi) and renders one shard: RT_SHARD_SAMPLES = a contiguous range of the samples of every pixel (perfect
- * balance), RT_SHARD_TILES = every sample of the RT_TILE_ROWS-row bands b with b % n_gpus == g (the reference's row bands,
+ * by rt_scene_commit_multi) and renders one shard: RT_SHARD_SAMPLES = a contiguous range of the samples of every pixel, cut evenly for any
+ * sample count (whole samples plus a partial first / last one: perfect balance), RT_SHARD_TILES = every sample of the RT_TILE_ROWS-row bands b with b % n_gpus == g (the reference's row bands,
  * world.rs:1198-1227).  The shards' int64 accumulators are summed and resolved by one kernel on GPU 0 that reads the peers'
  * accumulators in place over NVLink (P2P-mapped pointers; a staged peer copy only where no P2P route exists).  Integer sums and
  * Philox streams keyed by the global pixel / sample index make the image bit-identical to rt_render for every n_gpus and either

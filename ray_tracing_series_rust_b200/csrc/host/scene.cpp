@@ -1426,13 +1426,15 @@ int32_t rt_render_multi(rt_scene* s, const rt_render_config* cfg, int32_t n_gpus
     if ((rc = ensure_out_buffers(s, n)) != RT_OK) return rc;
     if ((rc = ensure_replicas(s, n_gpus, n)) != RT_OK) return rc;
     const RenderTuning tune = tuning_for(s, cfg);
-    // shard g: samples [b + g * S / N, b + (g + 1) * S / N) of every pixel, or every sample of the 4-row bands b with b % N == g
+    // shard g: the g-th of N equal ranges of the paths (sample-major: sample ranges of every pixel, cut evenly), or every sample of the 4-row bands b with b % N == g
     std::vector<RenderJob> jobs((size_t)n_gpus, job);
     const int32_t S = job.sample_end - job.sample_begin;
     for (int g = 0; g < n_gpus; ++g) {
-        if (shard_mode == RT_SHARD_SAMPLES) {
-            jobs[(size_t)g].sample_begin = job.sample_begin + (int32_t)(((int64_t)S * g) / n_gpus);
-            jobs[(size_t)g].sample_end = job.sample_begin + (int32_t)(((int64_t)S * (g + 1)) / n_gpus);
+        if (shard_mode == RT_SHARD_SAMPLES) { // an even share of the paths in sample-major order: whole samples plus a partial first / last one
+            const uint64_t T = (uint64_t)job.width * (uint64_t)job.rows * (uint64_t)S;
+            jobs[(size_t)g].path_begin = T * (uint64_t)g / (uint64_t)n_gpus;
+            jobs[(size_t)g].path_end = T * (uint64_t)(g + 1) / (uint64_t)n_gpus;
+            if (jobs[(size_t)g].path_end == jobs[(size_t)g].path_begin) jobs[(size_t)g].sample_end = jobs[(size_t)g].sample_begin; // nothing for this GPU
         } else {
             jobs[(size_t)g].tile_rank = g;
             jobs[(size_t)g].tile_count = n_gpus;
