@@ -147,6 +147,18 @@ RT_DEV void split_path_index(unsigned long long L, uint32_t npix, uint32_t& s_lo
     pix = (uint32_t)r;
 }
 
+// Chunk claim of the persistent kernels (lane 0 of the warp): J.chunk consecutive path indices while much work is left, fewer towards
+// the end (remaining / (2 x resident warps), at least 32), so that the warps run out of work within tens of microseconds of each other
+// instead of one chunk time (512 paths = 0.6 ms on book-1: a fixed cost that an 11 ms strong-scaling shard feels).
+RT_DEV unsigned long long claim_chunk(const JobDev& J, const Queues& Q, uint32_t& got) {
+    const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(Q.next_path);
+    const unsigned long long rem = seen < J.total_paths ? J.total_paths - seen : 0ull;
+    unsigned long long c = rem / (148ull * 7ull * 4ull * 2ull);
+    c = c > (unsigned long long)J.chunk ? (unsigned long long)J.chunk : (c < 32ull ? 32ull : (c & ~31ull));
+    got = (uint32_t)c;
+    return atomicAdd(Q.next_path, c);
+}
+
 // New camera path into `slot` (pixel jitter world.rs:1212-1213 + Camera::get_ray), or retire the slot.
 RT_DEV void regenerate(const DeviceScene& S, const JobDev& J, PathState& P, Queues& Q, uint32_t slot) {
     const unsigned act = __activemask();
@@ -522,9 +534,11 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
             // make sure the warp's chunk covers the request; leftover indices of the old chunk are used first
             unsigned long long avail = chunk_end - chunk_next;
             unsigned long long second_base = 0;
+            uint32_t got = 0;
             if (avail < n_need) {
-                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)J.chunk);
+                if (lane_id() == 0) second_base = claim_chunk(J, Q, got);
                 second_base = __shfl_sync(full, second_base, 0);
+                got = __shfl_sync(full, got, 0);
             }
             if (!alive && !exhausted) {
                 const uint32_t rank = __popc(need & ((1u << lane_id()) - 1u));
@@ -543,7 +557,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                     alive = true;
                 }
             }
-            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + J.chunk; }
+            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + got; }
             else chunk_next += n_need;
         }
         if (!__any_sync(full, alive)) break;
@@ -635,9 +649,11 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
             const uint32_t n_need = __popc(need);
             unsigned long long avail = chunk_end - chunk_next;
             unsigned long long second_base = 0;
+            uint32_t got = 0;
             if (avail < n_need) {
-                if (lane_id() == 0) second_base = atomicAdd(Q.next_path, (unsigned long long)J.chunk);
+                if (lane_id() == 0) second_base = claim_chunk(J, Q, got);
                 second_base = __shfl_sync(full, second_base, 0);
+                got = __shfl_sync(full, got, 0);
             }
             if (!alive && !exhausted) {
                 const uint32_t rank = __popc(need & ((1u << lane_id()) - 1u));
@@ -658,7 +674,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
                     cur = root; sp = 0;
                 }
             }
-            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + J.chunk; }
+            if (avail < n_need) { chunk_next = second_base + (n_need - avail); chunk_end = second_base + got; }
             else chunk_next += n_need;
         }
         if (!__any_sync(full, alive)) break;
@@ -1032,7 +1048,10 @@ __global__ void __launch_bounds__(256) k_reduce_resolve(const AccumShards A, int
                 const volatile uint32_t* fl = A.ready[g];
                 if (!fl) continue;
                 while ((int32_t)(*fl - A.need) < 0) {
-                    if (clock64() - t0 > 4000000000ll) break; // ~2 s at 1.9 GHz: a dead peer must not hang this GPU
+                    if (clock64() - t0 > 4000000000ll) { // ~2 s at 1.9 GHz: a dead peer must not hang this GPU; the host sees the flag (rt_peer_timed_out)
+                        if (A.timeout_flag) *A.timeout_flag = 1u;
+                        break;
+                    }
                     __nanosleep(500);
                 }
             }

@@ -62,6 +62,7 @@ struct AccumShards {
     // allocation, written by its stream after its render); the kernel waits for that itself.  need == 0: no waiting (one process).
     const uint32_t* ready[RT_MAX_GPUS];
     uint32_t need;
+    uint32_t* timeout_flag; // set to 1 when a wait gave up (nullable)
 };
 // one-thread flag kernels of the peer group: publish writes `value` to a flag after a system-wide fence; wait spins until a (peer's)
 // flag reaches `need` (bounded: ~2 s, then *timeout_flag = 1 and it gives up instead of hanging the GPU)

@@ -1265,6 +1265,20 @@ int32_t rt_resolve_device(const int64_t* d_accum, double* d_screen, int32_t widt
 // ---- rt_render / rt_render_multi: host-buffer entry points (what a Rust render_scene_gpu calls, world.rs:1181-1247)
 namespace {
 
+// The host-buffer entry points run on the device the scene was committed on, whatever device is current in the calling thread, and
+// leave the caller's current device as they found it.
+struct DeviceGuard {
+    int home = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&home) != cudaSuccess) home = -1;
+        if (home != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (home >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != home) cudaSetDevice(home);
+    }
+};
+
 int32_t ensure_out_buffers(rt_scene* s, size_t n) {
     RenderBuffers& o = s->out;
     cudaError_t e;
@@ -1312,6 +1326,7 @@ int32_t rt_render(rt_scene* s, const rt_render_config* cfg, double* out_screen, 
     int32_t rc = make_job(s, cfg, job);
     if (rc != RT_OK) return rc;
     const auto t0 = std::chrono::steady_clock::now();
+    DeviceGuard guard(s->dev.device);
     const size_t n = (size_t)job.width * job.height * 3;
     if ((rc = ensure_out_buffers(s, n)) != RT_OK) return rc;
     RenderBuffers& o = s->out;
@@ -1422,6 +1437,7 @@ int32_t rt_render_multi(rt_scene* s, const rt_render_config* cfg, int32_t n_gpus
     if (rc != RT_OK) return rc;
     if (job.tile_count > 1) return fail(RT_ERR_INVALID, "rt_render_multi shards the image itself: RT_RENDER_TILE_SHARD must not be set");
     const auto t0 = std::chrono::steady_clock::now();
+    DeviceGuard guard(s->dev.device);
     const size_t n = (size_t)job.width * job.height * 3;
     if ((rc = ensure_out_buffers(s, n)) != RT_OK) return rc;
     if ((rc = ensure_replicas(s, n_gpus, n)) != RT_OK) return rc;
@@ -1578,6 +1594,7 @@ int32_t rt_peer_gather_resolve(rt_peer_group* g, double* d_screen, int32_t width
     std::memset(&sh, 0, sizeof sh);
     sh.n = g->world;
     sh.need = g->step;
+    sh.timeout_flag = g->d_timeout;
     for (int r = 0; r < g->world; ++r) { sh.p[r] = g->accum(r); sh.ready[r] = g->published(r); }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     cudaError_t e = launch_reduce_resolve(sh, nullptr, nullptr, d_screen, width, height, spp, rendered_rows, st);
