@@ -121,6 +121,21 @@ def test_sample_range_partition():
         sharding.sample_range(10, 2, 2)
 
 
+def test_path_range_partition():
+    """sharding.path_range: N contiguous, disjoint, near-equal ranges of the sample-major path enumeration, for any spp / N"""
+    from ray_tracing_series_rust_b200 import sharding
+    for npix, spp in ((426400, 500), (1000000, 10000), (7, 3), (1, 1)):
+        for world in (1, 2, 3, 8):
+            edges = [sharding.path_range(npix, spp, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == npix * spp
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 1
+    assert sharding.path_range(426400, 500, 3, 8) == (426400 * 500 * 3 // 8, 426400 * 500 * 4 // 8)  # 62.5 spp each
+    with pytest.raises(ValueError):
+        sharding.path_range(10, 5, 2, 2)
+
+
 def test_frames_for_rank_partition():
     from ray_tracing_series_rust_b200 import sharding
     for n in (0, 1, 7, 240):
