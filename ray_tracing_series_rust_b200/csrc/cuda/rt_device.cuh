@@ -107,8 +107,39 @@ struct PathRngT {
         ++draw;
         return w == 0 ? blk.x : (w == 1 ? blk.y : (w == 2 ? blk.z : blk.w));
     }
-    RT_DEV double gen() { return (double)next_u32() * (1.0 / 4294967296.0); }
+    // xi = u * 2^-32 and 2 xi - 1 without an integer -> double conversion: the bits (0x43300000, u) ARE the double 2^52 + u, and
+    // (2^52 + u) * 2^-32 - 2^20 = u * 2^-32, (2^52 + u) * 2^-31 - (2^21 + 1) = u * 2^-31 - 1 are exact, so one fma returns the very
+    // double that (double)u * 2^-32 resp. fma(xi, 2.0, -1.0) round to (they are exact as well)
+    static RT_DEV double unit_of(uint32_t u) { return fma(__hiloint2double(0x43300000, (int)u), 1.0 / 4294967296.0, -1048576.0); }
+    static RT_DEV double pm1_of(uint32_t u) { return fma(__hiloint2double(0x43300000, (int)u), 1.0 / 2147483648.0, -2097153.0); }
+    RT_DEV double gen() { return unit_of(next_u32()); }
     RT_DEV double gen_range(double a, double b) { return fma(gen(), b - a, a); }
+    // The next two / three draws as gen_range(-1, 1) values, for the rejection samplers (random_in_unit_sphere, random_in_unit_disk):
+    // the same words of the same blocks as two / three next_u32() calls, picked with selects instead of a branch ladder per draw
+    // (the loops run at 5-6 of 32 lanes and were a quarter of the fused kernels' instructions, profiles/README.md)
+    RT_DEV void next3_pm1(double& a, double& b, double& c) {
+        const uint32_t bi = draw >> 2, w = draw & 3u;
+        if (bi != cached) { blk = block(bi); cached = bi; }
+        uint4 nb = blk;
+        if (w >= 2u) nb = block(bi + 1u);
+        const bool w1 = (w & 1u) != 0, w2 = (w & 2u) != 0;
+        a = pm1_of(w2 ? (w1 ? blk.w : blk.z) : (w1 ? blk.y : blk.x));
+        b = pm1_of(w2 ? (w1 ? nb.x : blk.w) : (w1 ? blk.z : blk.y));
+        c = pm1_of(w2 ? (w1 ? nb.y : nb.x) : (w1 ? blk.w : blk.z));
+        if (w >= 2u) { blk = nb; cached = bi + 1u; }
+        draw += 3u;
+    }
+    RT_DEV void next2_pm1(double& a, double& b) {
+        const uint32_t bi = draw >> 2, w = draw & 3u;
+        if (bi != cached) { blk = block(bi); cached = bi; }
+        uint4 nb = blk;
+        if (w == 3u) nb = block(bi + 1u);
+        const bool w1 = (w & 1u) != 0, w2 = (w & 2u) != 0;
+        a = pm1_of(w2 ? (w1 ? blk.w : blk.z) : (w1 ? blk.y : blk.x));
+        b = pm1_of(w2 ? (w1 ? nb.x : blk.w) : (w1 ? blk.z : blk.y));
+        if (w == 3u) { blk = nb; cached = bi + 1u; }
+        draw += 2u;
+    }
 };
 using PathRng = PathRngT<false>;    // wavefront kernels, parity hooks
 using PathRngOol = PathRngT<true>;  // fused kernels
@@ -120,7 +151,8 @@ RT_DEV double medium_xi(uint64_t seed, uint64_t path_id, uint32_t medium_prim_id
 
 template <class G> RT_DEV D3 random_in_unit_sphere(G& g) { // vec3.rs:287-295
     for (;;) {
-        const double a = g.gen_range(-1.0, 1.0), b = g.gen_range(-1.0, 1.0), c = g.gen_range(-1.0, 1.0);
+        double a, b, c;
+        g.next3_pm1(a, b, c);
         const D3 p = mk3(a, b, c);
         if (length_squared(p) < 1.0) return p;
     }
@@ -548,6 +580,9 @@ RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestH
 // has fallen behind closest_so_far is dropped when popped, so no primitive of a box that a nearer hit already culled is
 // tested.  Same closest hit as the binary walk (topology independent; ties by depth-first id in consider()).
 // Requires t_min >= 0 (distance bits are compared as unsigned integers).
+#ifndef RT_WIDE_SIGNED
+#define RT_WIDE_SIGNED 1
+#endif
 RT_DEV unsigned long long wide_key(float lx, float hx, float ly, float hy, float lz, float hz, float ref, const RayF& f, float t_min, float t_max) {
     const float x0 = fmaf(lx, f.idx, -f.oodx), x1 = fmaf(hx, f.idx, -f.oodx);
     const float y0 = fmaf(ly, f.idy, -f.oody), y1 = fmaf(hy, f.idy, -f.oody);
@@ -558,14 +593,54 @@ RT_DEV unsigned long long wide_key(float lx, float hx, float ly, float hy, float
     if (!(tn <= tf) || r == RT_WIDE_EMPTY) return ~0ull;
     return ((unsigned long long)(__float_as_uint(tn) & 0x7fffffffu) << 32) | (unsigned long long)r;
 }
+// The same key from the planes the ray enters / leaves through, picked per RAY (by the sign of 1/d) when the node rows are loaded
+// instead of per box with six min / max: 1/d is finite and non-zero (make_rayf) and lo <= hi, so fma(lo, idx, -ood) <= fma(hi, idx, -ood)
+// for idx > 0 and >= for idx < 0 (a correctly rounded fma is monotonic): min(x0, x1) and max(x0, x1) ARE the near and the far value,
+// bit for bit.  An unused slot holds the inverted box (3e38, -3e38) (host/bvh_wide.hpp): near > far on every axis, so it fails
+// tn <= tf without a look at its reference.
+// node + byte offset (0 / 16), added to the node's address once it is formed (left to nvcc, the sum is re-associated into three wide
+// multiplies and six 64-bit adds per visit; this form costs two instructions per address and three registers per ray)
+RT_DEV const float4* wide_row(const float4* node, uint32_t byte_off) {
+#ifdef __CUDA_ARCH__
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(a) : "r"(byte_off), "l"(reinterpret_cast<unsigned long long>(node)));
+    return reinterpret_cast<const float4*>(a);
+#else
+    return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(node) + byte_off);
+#endif
+}
+RT_DEV unsigned long long wide_key_nf(float nx, float fx, float ny, float fy, float nz, float fz, float ref, const RayF& f, float t_min, float t_max) {
+    const float xn = fmaf(nx, f.idx, -f.oodx), xf = fmaf(fx, f.idx, -f.oodx);
+    const float yn = fmaf(ny, f.idy, -f.oody), yf = fmaf(fy, f.idy, -f.oody);
+    const float zn = fmaf(nz, f.idz, -f.oodz), zf = fmaf(fz, f.idz, -f.oodz);
+    const float tn = fmaxf(fmaxf(xn, yn), fmaxf(zn, t_min));
+    const float tf = fminf(fminf(xf, yf), fminf(zf, t_max));
+    if (!(tn <= tf)) return ~0ull;
+    return ((unsigned long long)(__float_as_uint(tn) & 0x7fffffffu) << 32) | (unsigned long long)__float_as_uint(ref);
+}
 RT_DEV void wide_ce(unsigned long long& a, unsigned long long& b) {
     const bool s = a > b;
     const unsigned long long lo = s ? b : a, hi = s ? a : b;
     a = lo; b = hi;
 }
-RT_DEV uint32_t wide_pop(const unsigned long long* stack, int& sp, float tmaxf) {
+// The walk's stack: a plain (local-memory) array, or WStackSm: entries [0, S) in shared memory, laid out [entry][thread] (a warp's
+// row is 256 contiguous bytes: conflict free whatever the lanes' depths are), the rest in a local array.  Local-memory stacks of
+// lanes at different depths touch a different 128-byte line per lane and compete with the nodes for L1 (871 200-triangle mesh:
+// 14 % of the stall samples sat on the pop, 327 MB of stack lines written back to DRAM per 2-spp launch, profiles/README.md).
+RT_DEV void wstk_put(unsigned long long* s, int i, unsigned long long v) { s[i] = v; }
+RT_DEV unsigned long long wstk_get(const unsigned long long* s, int i) { return s[i]; }
+template <int S, int NT>
+struct WStackSm {
+    unsigned long long* col; // this thread's column of the CTA's [S][NT] array
+    unsigned long long over[RT_WIDE_STACK - S];
+};
+template <int S, int NT> RT_DEV void wstk_put(WStackSm<S, NT>& s, int i, unsigned long long v) {
+    if (i < S) s.col[i * NT] = v; else s.over[i - S] = v;
+}
+template <int S, int NT> RT_DEV unsigned long long wstk_get(const WStackSm<S, NT>& s, int i) { return i < S ? s.col[i * NT] : s.over[i - S]; }
+template <class STK> RT_DEV uint32_t wide_pop(const STK& stack, int& sp, float tmaxf) {
     while (sp) {
-        const unsigned long long e = stack[--sp];
+        const unsigned long long e = wstk_get(stack, --sp);
         if ((uint32_t)(e >> 32) <= __float_as_uint(tmaxf)) return (uint32_t)e; // both non-negative floats: integer compare
     }
     return 0xffffffffu;
@@ -574,8 +649,8 @@ RT_DEV uint32_t wide_pop(const unsigned long long* stack, int& sp, float tmaxf) 
 // caller, called by all 32 lanes, returns once `wait_thresh` of the lanes that entered with work have finished.
 // RESUME = false: walks until this lane is done.
 // walk_wide: the per-ray constants come from the caller (see walk_pairs); trace_wide below derives them per call.
-template <uint32_t PM, bool RESUME, bool COUNT = false>
-RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const RayPre& pre, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack,
+template <uint32_t PM, bool RESUME, bool COUNT = false, class STK>
+RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const RayPre& pre, double t_min, BestHit& best, uint32_t& cur, int& sp, STK& stack,
                       uint32_t wait_thresh, uint32_t inst = 0u, TraceCounters* cnt = nullptr) {
     const unsigned full = 0xffffffffu;
     const float tminf = fmaxf(f32_down(t_min), 0.f);
@@ -586,6 +661,8 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
     const bool MOTION = PM == 0x3u && mnodes4 != nullptr;
     float ms = 0.f;
     if (MOTION) { const double sd = (r.time - S.motion_t0) * S.motion_inv_dt; ms = (float)(sd < 0.0 ? 0.0 : (sd > 1.0 ? 1.0 : sd)); }
+    // byte offset of the row the ray enters through, per axis (0 = lo, 16 = hi)
+    uint32_t sgx = f.idx < 0.f ? 16u : 0u, sgy = f.idy < 0.f ? 16u : 0u, sgz = f.idz < 0.f ? 16u : 0u;
     const uint32_t DONE = 0xffffffffu;
     uint32_t n0 = 0;
     if (RESUME) n0 = __popc(__ballot_sync(full, cur != DONE));
@@ -608,22 +685,34 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
                 hy.x = fmaf(dhy.x, ms, hy.x); hy.y = fmaf(dhy.y, ms, hy.y); hy.z = fmaf(dhy.z, ms, hy.z); hy.w = fmaf(dhy.w, ms, hy.w);
                 lz.x = fmaf(dlz.x, ms, lz.x); lz.y = fmaf(dlz.y, ms, lz.y); lz.z = fmaf(dlz.z, ms, lz.z); lz.w = fmaf(dlz.w, ms, lz.w);
                 hz.x = fmaf(dhz.x, ms, hz.x); hz.y = fmaf(dhz.y, ms, hz.y); hz.z = fmaf(dhz.z, ms, hz.z); hz.w = fmaf(dhz.w, ms, hz.w);
+            } else if (RT_WIDE_SIGNED) { // rows picked by the ray's direction signs: l* = the planes it enters through, h* = leaves through
+                const float4* __restrict__ q = nodes4 + 8 * (size_t)cur;
+                lx = __ldg(wide_row(q, sgx)); hx = __ldg(wide_row(q, sgx ^ 16u)); ly = __ldg(wide_row(q, sgy) + 2); hy = __ldg(wide_row(q, sgy ^ 16u) + 2);
+                lz = __ldg(wide_row(q, sgz) + 4); hz = __ldg(wide_row(q, sgz ^ 16u) + 4); rf = __ldg(q + 6);
             } else {
                 const float4* __restrict__ q = nodes4 + 8 * (size_t)cur;
                 lx = __ldg(q); hx = __ldg(q + 1); ly = __ldg(q + 2); hy = __ldg(q + 3); lz = __ldg(q + 4); hz = __ldg(q + 5); rf = __ldg(q + 6);
             }
             if (COUNT) cnt->nodes += 4;
-            unsigned long long k0 = wide_key(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, rf.x, f, tminf, tmaxf);
-            unsigned long long k1 = wide_key(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
-            unsigned long long k2 = wide_key(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);
-            unsigned long long k3 = wide_key(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, rf.w, f, tminf, tmaxf);
+            unsigned long long k0, k1, k2, k3;
+            if (RT_WIDE_SIGNED && !MOTION) {
+                k0 = wide_key_nf(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, rf.x, f, tminf, tmaxf);
+                k1 = wide_key_nf(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
+                k2 = wide_key_nf(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);
+                k3 = wide_key_nf(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, rf.w, f, tminf, tmaxf);
+            } else {
+                k0 = wide_key(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, rf.x, f, tminf, tmaxf);
+                k1 = wide_key(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
+                k2 = wide_key(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);
+                k3 = wide_key(lx.w, hx.w, ly.w, hy.w, lz.w, hz.w, rf.w, f, tminf, tmaxf);
+            }
             // Only the nearest child is found exactly (three compare-exchanges); k1..k3 are pushed as they are.  The full five-exchange
             // sort (far-to-near pushes) measured 2.7 % slower on book-1 final and 3 % on the 871 200-triangle mesh (profiles/r2_00_ab.log):
             // an entry that a nearer hit has culled is dropped when popped, so the order of the queued ones matters little.
             wide_ce(k0, k1); wide_ce(k2, k3); wide_ce(k0, k2);
-            if (k3 != ~0ull) stack[sp++] = k3;
-            if (k2 != ~0ull) stack[sp++] = k2;
-            if (k1 != ~0ull) stack[sp++] = k1;
+            if (k3 != ~0ull) wstk_put(stack, sp++, k3);
+            if (k2 != ~0ull) wstk_put(stack, sp++, k2);
+            if (k1 != ~0ull) wstk_put(stack, sp++, k1);
             cur = (k0 != ~0ull) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
         }
         if (cur != DONE && (cur & RT_LEAF_FLAG)) { // a leaf reference
@@ -641,8 +730,8 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
     }
 }
 
-template <uint32_t PM, bool RESUME, bool COUNT = false>
-RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, unsigned long long* stack, uint32_t wait_thresh,
+template <uint32_t PM, bool RESUME, bool COUNT = false, class STK>
+RT_DEV void trace_wide(const DeviceScene& S, const Ray& r, double t_min, BestHit& best, uint32_t& cur, int& sp, STK& stack, uint32_t wait_thresh,
                        uint32_t inst = 0u, TraceCounters* cnt = nullptr) {
     const RayF f = make_rayf(r);
     const RayPre pre = make_raypre(r, (PM & 0x18u) != 0 && (S.flags & 1u) != 0);
@@ -1014,8 +1103,7 @@ RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, do
 template <class G> RT_DEV Ray camera_get_ray(const DCamera& c, double s, double t, G& g) {
     double rx, ry;
     for (;;) { // random_in_unit_disk, vec3.rs:310-322 (runs even when lens_radius == 0)
-        rx = g.gen_range(-1.0, 1.0);
-        ry = g.gen_range(-1.0, 1.0);
+        g.next2_pm1(rx, ry);
         if (rx * rx + ry * ry + 0.0 < 1.0) break;
     }
     rx *= c.lens_radius; ry *= c.lens_radius;

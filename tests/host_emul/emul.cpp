@@ -51,7 +51,74 @@ static void wide_batch(const DeviceScene& S, const rt_ray* rays, int64_t n, doub
         store_hit(out[i], hit, h);
     }
 }
+// A stack that counts its accesses per index: how deep the 4-wide walk's stack really gets (sizes WStackSm's shared-memory part)
+namespace rtb {
+struct WStackStat {
+    unsigned long long e[RT_WIDE_STACK];
+    uint64_t* hist; // [RT_WIDE_STACK] puts + gets per index
+};
+inline void wstk_put(WStackStat& s, int i, unsigned long long v) { s.e[i] = v; ++s.hist[i]; }
+inline unsigned long long wstk_get(const WStackStat& s, int i) { ++s.hist[i]; return s.e[i]; }
+} // namespace rtb
+
 extern "C" {
+
+// Paths of the fused WIDE kernels (single main instance, no wrappers, no media) with the counting stack; hist[RT_WIDE_STACK].
+int32_t emul_wide_stack_hist(const void* scene, int32_t W, int32_t H, int32_t spp, int32_t max_depth, uint64_t seed, uint64_t* hist, uint64_t* segments_out) {
+    const DeviceScene& S = *static_cast<const DeviceScene*>(scene);
+    if (!S.nodes4) return -1;
+    uint64_t segments = 0;
+    for (int32_t j = 0; j < H; ++j)
+        for (int32_t ii = 0; ii < W; ++ii)
+            for (int32_t sl = 0; sl < spp; ++sl) {
+                const uint32_t pixel = (uint32_t)j * (uint32_t)W + (uint32_t)ii;
+                const uint64_t path_id = (uint64_t)pixel * (uint64_t)spp + (uint64_t)sl;
+                uint32_t draw = 0;
+                Ray r = camera_first_ray<PathRng>(S.cam, ii, j, W, H, seed, path_id, draw);
+                for (uint32_t segment = 0;; ++segment) {
+                    BestHit best;
+                    best_init(best, RT_INF);
+                    WStackStat st;
+                    st.hist = hist;
+                    uint32_t cur = S.root4;
+                    int sp = 0;
+                    trace_wide<RT_PM_ALL, false>(S, r, 0.001, best, cur, sp, st, 0u);
+                    ++segments;
+                    if (best.type == RT_NONE) break;
+                    const HitRec h = finalize_hit<2, RT_PM_ALL, false>(S, r, best);
+                    const DMaterial m = S.materials[h.mat];
+                    if (m.type == MAT_LIGHT) break;
+                    PathRng g;
+                    g.init(seed, path_id, draw);
+                    D3 dir = mk3(0, 0, 0);
+                    F3 att = mkf3(0.f, 0.f, 0.f);
+                    bool scattered;
+                    if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                    else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
+                    else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
+                    else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                    if (!(scattered && (int32_t)(segment + 1) < max_depth)) break;
+                    r.o = h.p; r.d = dir;
+                    draw = g.draw;
+                }
+            }
+    if (segments_out) *segments_out = segments;
+    return 0;
+}
+
+// PathRng's conversions against the formulas they replace ((double)u * 2^-32 and fma(xi, 2, -1)); -> number of mismatching u
+uint64_t emul_rng_convert_mismatches(uint64_t n_random, uint64_t seed) {
+    uint64_t bad = 0, x = seed | 1u;
+    auto check = [&](uint32_t u) {
+        const double xi = (double)u * (1.0 / 4294967296.0);
+        const double a = PathRng::unit_of(u), b = PathRng::pm1_of(u), b0 = fma(xi, 1.0 - -1.0, -1.0);
+        if (std::memcmp(&a, &xi, 8) != 0 || std::memcmp(&b, &b0, 8) != 0) ++bad;
+    };
+    const uint32_t edge[] = {0u, 1u, 2u, 0x7fffffffu, 0x80000000u, 0x80000001u, 0xfffffffeu, 0xffffffffu, 0x00100000u, 0x001fffffu};
+    for (uint32_t u : edge) check(u);
+    for (uint64_t i = 0; i < n_random; ++i) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; check((uint32_t)(x >> 16)); }
+    return bad;
+}
 
 uint64_t emul_sizeof_device_scene(void) { return sizeof(DeviceScene); }
 
