@@ -513,23 +513,11 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // close.  Same device functions, same Philox streams, same integer accumulation as the wavefront: the
 // two modes produce bit-identical images.
 #define RT_MEGA_CHUNK 512u // path indices a warp claims at once; the host lowers it (JobDev.chunk) for short renders, see launch_render
-// Entries of the 4-wide walk's stack that live in shared memory (WStackSm, rt_device.cuh), per thread; 0 = the whole stack in local memory
-#ifndef RT_SMEM_STACK_MEGA
-#define RT_SMEM_STACK_MEGA 0
-#endif
-#ifndef RT_SMEM_STACK_MEGA_R
-#define RT_SMEM_STACK_MEGA_R 0
-#endif
-#ifndef RT_MEGA_R_OCC
-#define RT_MEGA_R_OCC 7 // resident CTAs per SM of the wide mesh kernel k_mega_r<., 0x28, true>
-#endif
 // WIDE = true (media-free, wrapper-free, single instance): world.hit walks the 4-wide collapse (DeviceScene::nodes4).
 template <bool MEDIA, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL, bool XF = true, bool WIDE = false>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
     const unsigned full = 0xffffffffu;
-    constexpr int SST = WIDE ? RT_SMEM_STACK_MEGA : 0;
-    __shared__ unsigned long long s_wstack[SST ? SST * 128 : 1];
     unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform
     Ray r;
     r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.time = 0.0;
@@ -580,16 +568,10 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
         if (WIDE) {
             BestHit best;
             best_init(best, RT_INF);
+            unsigned long long wstack[RT_WIDE_STACK];
             uint32_t cur = S.root4;
             int sp = 0;
-            if (SST) {
-                WStackSm<SST ? SST : 1, 128> wstack;
-                wstack.col = s_wstack + threadIdx.x;
-                trace_wide<PM, false>(S, r, 0.001, best, cur, sp, wstack, 0u);
-            } else {
-                unsigned long long wstack[RT_WIDE_STACK];
-                trace_wide<PM, false>(S, r, 0.001, best, cur, sp, wstack, 0u);
-            }
+            trace_wide<PM, false>(S, r, 0.001, best, cur, sp, wstack, 0u);
             hit = best.type != RT_NONE;
             if (hit) h = finalize_hit<2, PM, false>(S, r, best);
         } else {
@@ -607,15 +589,17 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
                 const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
                 contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
             } else {
-                PathRngOol g;
+                PathRngOolBegun g;
                 g.init(J.seed, path_id, draw);
-                D3 dir = mk3(0, 0, 0);
+                g.open_event(); // Material::scatter starts on a block boundary: the first block for every scattering lane at once
+                D3 dir = mk3(0, 0, 0), rs = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
                 bool scattered;
-                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
-                else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
+                if (m.type != MAT_DIELECTRIC) rs = random_in_unit_sphere(g); // one rejection loop for Lambertian, Metal and Isotropic lanes
+                if (m.type == MAT_LAMBERTIAN) scattered = lambertian_finish(S, m, h.p, h.n, h.u, h.v, rs, dir, att);
+                else if (m.type == MAT_METAL) scattered = metal_finish(m, r.d, h.n, rs, dir, att);
                 else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
-                else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                else scattered = isotropic_finish(S, m, h.p, h.u, h.v, rs, dir, att);
                 if (scattered && (int32_t)(segment + 1) < J.max_depth) {
                     tr *= att.x; tg *= att.y; tb *= att.z;
                     r.o = h.p; r.d = dir;
@@ -654,11 +638,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
     bool alive = false, exhausted = false;
     uint32_t my_segments = 0;
     uint32_t stack[WIDE ? 1 : RT_STACK];
-    constexpr int SST = WIDE ? RT_SMEM_STACK_MEGA_R : 0;
-    __shared__ unsigned long long s_wstack[SST ? SST * 128 : 1];
-    unsigned long long wstack[WIDE && !SST ? RT_WIDE_STACK : 1];
-    WStackSm<SST ? SST : RT_WIDE_STACK - 1, 128> wstack_sm; // (a one-entry overflow array when unused)
-    wstack_sm.col = s_wstack + threadIdx.x;
+    unsigned long long wstack[WIDE ? RT_WIDE_STACK : 1];
     uint32_t cur = DONE;
     int sp = 0;
     BestHit best;
@@ -701,8 +681,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
         }
         if (!__any_sync(full, alive)) break;
         // ---- world.hit for every lane that has a ray; returns when enough lanes are ready to shade
-        if (WIDE && SST) trace_wide<PM, true>(S, r, 0.001, best, cur, sp, wstack_sm, J.wait_thresh);
-        else if (WIDE) trace_wide<PM, true>(S, r, 0.001, best, cur, sp, wstack, J.wait_thresh);
+        if (WIDE) trace_wide<PM, true>(S, r, 0.001, best, cur, sp, wstack, J.wait_thresh);
         else trace_resume<PM>(S, r, 0.001, best, cur, sp, stack, J.wait_thresh);
         if (!alive || cur != DONE) continue;
         // ---- the rest of this ray_color iteration (world.rs:63-91)
@@ -719,15 +698,17 @@ __global__ void __launch_bounds__(128, MINB) k_mega_r(const __grid_constant__ De
                 const F3 e = tex_value(S, m.tex, h.u, h.v, h.p);
                 contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
             } else {
-                PathRngOol g;
+                PathRngOolBegun g;
                 g.init(J.seed, path_id, draw);
-                D3 dir = mk3(0, 0, 0);
+                g.open_event(); // Material::scatter starts on a block boundary: the first block for every scattering lane at once
+                D3 dir = mk3(0, 0, 0), rs = mk3(0, 0, 0);
                 F3 att = mkf3(0.f, 0.f, 0.f);
                 bool scattered;
-                if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
-                else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
+                if (m.type != MAT_DIELECTRIC) rs = random_in_unit_sphere(g); // one rejection loop for Lambertian, Metal and Isotropic lanes
+                if (m.type == MAT_LAMBERTIAN) scattered = lambertian_finish(S, m, h.p, h.n, h.u, h.v, rs, dir, att);
+                else if (m.type == MAT_METAL) scattered = metal_finish(m, r.d, h.n, rs, dir, att);
                 else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
-                else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                else scattered = isotropic_finish(S, m, h.p, h.u, h.v, rs, dir, att);
                 if (scattered && (int32_t)(segment + 1) < J.max_depth) {
                     tr *= att.x; tg *= att.y; tb *= att.z;
                     r.o = h.p; r.d = dir;
@@ -1450,7 +1431,7 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 // 5 CTAs/SM (96 regs, 132 B spilled) 126, 6 (80 regs) 134.5, 7 (72 regs, 652 B spilled) 139.7, 8 (64 regs) 135 Mpaths/s
                 else if (scene.nodes4 && tune.bvh_wide != 0) {
                     // 4-wide walk: 871k mesh 149.8 -> 179.5 Mpaths/s at 7 CTAs/SM (6: 175.5, 5: 165.9; profiles/r2_00_ab.log)
-                    k_mega_r<RT_MEGA_R_OCC, 0x28u, true><<<148 * RT_MEGA_R_OCC, 128, 0, stream>>>(scene, J, Q, d_accum);
+                    k_mega_r<7, 0x28u, true><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
                 } else k_mega_r<7, 0x28u><<<148 * 7, 128, 0, stream>>>(scene, J, Q, d_accum);
             } else if (wrapper_free && scene.nodes4 && tune.bvh_wide != 0 && scene.n_main_instances == 1 && (pm == 0x1u || pm == 0x3u || pm == 0x5u || pm == 0x28u)) {
                 if (pm == 0x1u) k_mega<false, 5, false, 0x1u, false, true><<<148 * 5, 128, 0, stream>>>(scene, J, Q, d_accum);

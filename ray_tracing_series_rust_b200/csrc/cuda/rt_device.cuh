@@ -143,6 +143,12 @@ struct PathRngT {
 };
 using PathRng = PathRngT<false>;    // wavefront kernels, parity hooks
 using PathRngOol = PathRngT<true>;  // fused kernels
+// The fused kernels open the event ONCE for all lanes that scatter, before the branch on the material type, and hand the samplers
+// this type, whose own begin_event() does nothing: one Philox call at ~20 lanes instead of one per material present in the warp
+struct PathRngOolBegun : PathRngOol {
+    RT_DEV void open_event() { PathRngOol::begin_event(); }
+    RT_DEV void begin_event() {}
+};
 RT_DEV double medium_xi(uint64_t seed, uint64_t path_id, uint32_t medium_prim_id, uint32_t segment) {
     const uint4 o = philox4x32_10(make_uint4((uint32_t)path_id, (uint32_t)(path_id >> 32), medium_prim_id, 0x80000000u | segment),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -581,7 +587,7 @@ RT_DEV void trace_resume(const DeviceScene& S, const Ray& r, double t_min, BestH
 // tested.  Same closest hit as the binary walk (topology independent; ties by depth-first id in consider()).
 // Requires t_min >= 0 (distance bits are compared as unsigned integers).
 #ifndef RT_WIDE_SIGNED
-#define RT_WIDE_SIGNED 1
+#define RT_WIDE_SIGNED 1 // 0 = the per-box min / max form (A/B: book-1 final 83.5 -> 80.8 ms, mesh +1.8 % with 1)
 #endif
 RT_DEV unsigned long long wide_key(float lx, float hx, float ly, float hy, float lz, float hz, float ref, const RayF& f, float t_min, float t_max) {
     const float x0 = fmaf(lx, f.idx, -f.oodx), x1 = fmaf(hx, f.idx, -f.oodx);
@@ -623,21 +629,13 @@ RT_DEV void wide_ce(unsigned long long& a, unsigned long long& b) {
     const unsigned long long lo = s ? b : a, hi = s ? a : b;
     a = lo; b = hi;
 }
-// The walk's stack: a plain (local-memory) array, or WStackSm: entries [0, S) in shared memory, laid out [entry][thread] (a warp's
-// row is 256 contiguous bytes: conflict free whatever the lanes' depths are), the rest in a local array.  Local-memory stacks of
-// lanes at different depths touch a different 128-byte line per lane and compete with the nodes for L1 (871 200-triangle mesh:
-// 14 % of the stall samples sat on the pop, 327 MB of stack lines written back to DRAM per 2-spp launch, profiles/README.md).
+// The walk's stack is reached through wstk_put / wstk_get so that it can be something else than a plain local-memory array: the host
+// emulation counts the accesses per depth with it (tests/host_emul: book-1 never goes past 8 entries, the 871 200-triangle mesh past 19),
+// and round 2 measured a variant with the first 8 / 12 / 16 entries per thread in shared memory ([entry][thread], conflict free):
+// book-1 final -3.6 %, mesh -1 ... +1.3 % (profiles/r2_50_ab_signed_rows_smem_stack.txt) - the local-memory stack is not what the
+// pop stalls on, so it stays.
 RT_DEV void wstk_put(unsigned long long* s, int i, unsigned long long v) { s[i] = v; }
 RT_DEV unsigned long long wstk_get(const unsigned long long* s, int i) { return s[i]; }
-template <int S, int NT>
-struct WStackSm {
-    unsigned long long* col; // this thread's column of the CTA's [S][NT] array
-    unsigned long long over[RT_WIDE_STACK - S];
-};
-template <int S, int NT> RT_DEV void wstk_put(WStackSm<S, NT>& s, int i, unsigned long long v) {
-    if (i < S) s.col[i * NT] = v; else s.over[i - S] = v;
-}
-template <int S, int NT> RT_DEV unsigned long long wstk_get(const WStackSm<S, NT>& s, int i) { return i < S ? s.col[i * NT] : s.over[i - S]; }
 template <class STK> RT_DEV uint32_t wide_pop(const STK& stack, int& sp, float tmaxf) {
     while (sp) {
         const unsigned long long e = wstk_get(stack, --sp);
@@ -1055,22 +1053,39 @@ RT_DEV F3 miss_color(const DeviceScene& S, D3 d) {
 
 // ------------------------------------------------------------------ Material::scatter (hit.rs:1004-1152)
 // Returns true when the path continues; `dir` = scattered direction, `att` = attenuation.
-template <bool FULLTEX = true, class G>
-RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, G& g, D3& dir, F3& att,
-                               const PerlinTable* perlin0 = nullptr) {
-    g.begin_event();
-    D3 sd = n + random_unit_vector(g);
+// Lambertian, Metal and Isotropic all start with random_in_unit_sphere (hit.rs:1033, 1068, 1007); the *_finish halves take its
+// result `rs`, so that the fused kernels can run ONE rejection loop for every lane of a warp that needs one, whatever its material
+// (book-1: a second, metal-only loop of 4-5 diverged iterations per warp and segment otherwise)
+template <bool FULLTEX = true>
+RT_DEV bool lambertian_finish(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, D3 rs, D3& dir, F3& att,
+                              const PerlinTable* perlin0 = nullptr) {
+    D3 sd = n + unit(rs); // random_unit_vector, vec3.rs:297-299
     if (near_zero(sd)) sd = n;
     dir = sd;
     att = tex_value<FULLTEX>(S, m.tex, u, v, p, perlin0);
     return true;
 }
-template <class G> RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, G& g, D3& dir, F3& att) {
-    g.begin_event();
+RT_DEV bool metal_finish(const DMaterial& m, D3 d_in, D3 n, D3 rs, D3& dir, F3& att) {
     const D3 reflected = reflect(unit(d_in), n);
-    dir = reflected + m.fuzz_or_ir * random_in_unit_sphere(g); // the draw happens even when fuzz == 0
+    dir = reflected + m.fuzz_or_ir * rs; // the draw happens even when fuzz == 0
     att = mkf3(m.albedo[0], m.albedo[1], m.albedo[2]);
     return dot(dir, n) > 0.0;
+}
+template <bool FULLTEX = true>
+RT_DEV bool isotropic_finish(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, D3 rs, D3& dir, F3& att, const PerlinTable* perlin0 = nullptr) {
+    dir = rs; // not normalised (hit.rs:1007)
+    att = tex_value<FULLTEX>(S, m.tex, u, v, p, perlin0);
+    return true;
+}
+template <bool FULLTEX = true, class G>
+RT_DEV bool scatter_lambertian(const DeviceScene& S, const DMaterial& m, D3 p, D3 n, double u, double v, G& g, D3& dir, F3& att,
+                               const PerlinTable* perlin0 = nullptr) {
+    g.begin_event();
+    return lambertian_finish<FULLTEX>(S, m, p, n, u, v, random_in_unit_sphere(g), dir, att, perlin0);
+}
+template <class G> RT_DEV bool scatter_metal(const DMaterial& m, D3 d_in, D3 n, G& g, D3& dir, F3& att) {
+    g.begin_event();
+    return metal_finish(m, d_in, n, random_in_unit_sphere(g), dir, att);
 }
 RT_DEV double reflectance(double cosine, double ref_idx) { // hit.rs:1095-1099
     double r0 = (1.0 - ref_idx) / (1.0 + ref_idx);
@@ -1094,9 +1109,7 @@ template <bool FULLTEX = true, class G>
 RT_DEV bool scatter_isotropic(const DeviceScene& S, const DMaterial& m, D3 p, double u, double v, G& g, D3& dir, F3& att,
                               const PerlinTable* perlin0 = nullptr) {
     g.begin_event();
-    dir = random_in_unit_sphere(g); // not normalised (hit.rs:1007)
-    att = tex_value<FULLTEX>(S, m.tex, u, v, p, perlin0);
-    return true;
+    return isotropic_finish<FULLTEX>(S, m, p, u, v, random_in_unit_sphere(g), dir, att, perlin0);
 }
 
 // ------------------------------------------------------------------ Camera::get_ray (camera.rs:59-71)
