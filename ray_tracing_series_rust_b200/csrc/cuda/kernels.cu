@@ -514,6 +514,20 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 // two modes produce bit-identical images.
 #define RT_MEGA_CHUNK 512u // path indices a warp claims at once; the host lowers it (JobDev.chunk) for short renders, see launch_render
 // WIDE = true (media-free, wrapper-free, single instance): world.hit walks the 4-wide collapse (DeviceScene::nodes4).
+#ifndef RT_CAM_BATCH
+#define RT_CAM_BATCH 1
+#endif
+// Camera rays are generated 32 at a time by the whole warp into a per-warp buffer in shared memory, and ended lanes take theirs from
+// it: pixel jitter, lens-disk rejection loop and the two Philox blocks of a new path run at 32 lanes every third iteration or so
+// instead of at the ~10 lanes that happen to have ended in this one.  Measured (profiles/r2_57_ab_cam_batch.txt): book-1 final 70.3 ->
+// 68.2 ms; book-1 as shipped +-0, a bouncing-spheres frame -2.2 % (their pair walks over motion boxes / gravity tables miss the 9 KB
+// per CTA that the buffer takes from L1), so only the plain-sphere kernel on the 4-wide tree uses it (RT_CAM_BATCH = 0: none does).
+template <bool ON> struct CamBufferT {
+    double v[4][7][32]; // [warp][o.x o.y o.z d.x d.y d.z time][entry]
+    unsigned long long path_id[4][32];
+    uint32_t pixel[4][32], draw[4][32];
+};
+template <> struct CamBufferT<false> {};
 template <bool MEDIA, int MINB, bool GENERAL_MEDIA, uint32_t PM = RT_PM_ALL, bool XF = true, bool WIDE = false>
 __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ DeviceScene S, const __grid_constant__ JobDev J, Queues Q,
                                                       int64_t* __restrict__ accum) {
@@ -526,10 +540,69 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
     uint64_t path_id = 0;
     bool alive = false, exhausted = false;
     uint32_t my_segments = 0;
+    constexpr bool CAMB = RT_CAM_BATCH && WIDE && PM == 0x1u;
+    __shared__ CamBufferT<CAMB> cam;
+    const uint32_t wid = threadIdx.x >> 5, ln = lane_id();
+    uint32_t buf_head = 0, buf_count = 0; // warp-uniform
+    bool gen_done = false;                // warp-uniform: the path indices have run out
     for (;;) {
         // ---- refill idle lanes
         const unsigned need = __ballot_sync(full, !alive && !exhausted);
-        if (need) {
+        if constexpr (CAMB) {
+          if (need) {
+            uint32_t rank = __popc(need & ((1u << ln) - 1u));
+            bool want = !alive && !exhausted;
+            for (int round = 0; round < 2; ++round) { // what the buffer holds first; then, if lanes are left over, 32 new rays and the rest
+                const uint32_t want_n = __popc(__ballot_sync(full, want));
+                const uint32_t served = want_n < buf_count ? want_n : buf_count;
+                if (want && rank < served) {
+                    const uint32_t e = buf_head + rank;
+                    r.o = mk3(cam.v[wid][0][e], cam.v[wid][1][e], cam.v[wid][2][e]);
+                    r.d = mk3(cam.v[wid][3][e], cam.v[wid][4][e], cam.v[wid][5][e]);
+                    r.time = cam.v[wid][6][e];
+                    path_id = cam.path_id[wid][e]; pixel = cam.pixel[wid][e]; draw = cam.draw[wid][e];
+                    tr = tg = tb = 1.f;
+                    segment = 0;
+                    alive = true;
+                    want = false;
+                } else if (want) {
+                    rank -= served;
+                }
+                buf_head += served; buf_count -= served;
+                if (served == want_n) break;
+                if (round == 1 || gen_done) { if (want) exhausted = true; break; }
+                // the buffer is empty: the whole warp generates the next 32 camera rays
+                __syncwarp();
+                if (chunk_next == chunk_end) {
+                    unsigned long long base = 0;
+                    uint32_t got = 0;
+                    if (ln == 0) base = claim_chunk(J, Q, got);
+                    base = __shfl_sync(full, base, 0);
+                    got = __shfl_sync(full, got, 0);
+                    chunk_next = base; chunk_end = base + got;
+                }
+                const unsigned long long L = chunk_next + ln;
+                chunk_next += 32;
+                const bool valid = L < J.total_paths;
+                if (valid) {
+                    uint32_t s_local, pix, d0;
+                    split_path_index(L + J.path_base, J.npix_rendered, s_local, pix);
+                    pix = shard_pixel(J, pix);
+                    const int32_t j = (int32_t)(pix / (uint32_t)J.W), ii = (int32_t)(pix - (uint32_t)j * (uint32_t)J.W);
+                    const uint64_t pid = (uint64_t)pix * (uint64_t)J.spp_total + (uint64_t)(J.sample_begin + (int32_t)s_local);
+                    const Ray cr = camera_first_ray<PathRngOol>(S.cam, ii, j, J.W, J.H, J.seed, pid, d0); // world.rs:1212-1214
+                    cam.v[wid][0][ln] = cr.o.x; cam.v[wid][1][ln] = cr.o.y; cam.v[wid][2][ln] = cr.o.z;
+                    cam.v[wid][3][ln] = cr.d.x; cam.v[wid][4][ln] = cr.d.y; cam.v[wid][5][ln] = cr.d.z;
+                    cam.v[wid][6][ln] = cr.time;
+                    cam.path_id[wid][ln] = pid; cam.pixel[wid][ln] = pix; cam.draw[wid][ln] = d0;
+                }
+                buf_head = 0;
+                buf_count = __popc(__ballot_sync(full, valid)); // valid lanes are a prefix: L grows with the lane
+                if (buf_count < 32u) gen_done = true;
+                __syncwarp();
+            }
+          }
+        } else if (need) {
             const uint32_t n_need = __popc(need);
             // make sure the warp's chunk covers the request; leftover indices of the old chunk are used first
             unsigned long long avail = chunk_end - chunk_next;
