@@ -624,8 +624,13 @@ RT_DEV unsigned long long wide_key_nf(float nx, float fx, float ny, float fy, fl
     if (!(tn <= tf)) return ~0ull;
     return ((unsigned long long)(__float_as_uint(tn) & 0x7fffffffu) << 32) | (unsigned long long)__float_as_uint(ref);
 }
+#ifndef RT_WIDE_CE32
+#define RT_WIDE_CE32 1
+#endif
+#define RT_WIDE_MISS(k) (RT_WIDE_CE32 ? (uint32_t)((k) >> 32) == 0xffffffffu : (k) == ~0ull) // a hit's distance bits are never all ones
 RT_DEV void wide_ce(unsigned long long& a, unsigned long long& b) {
-    const bool s = a > b;
+    // ordered by the distance word alone: equal distances may come out either way, which only the visiting order sees
+    const bool s = RT_WIDE_CE32 ? (uint32_t)(a >> 32) > (uint32_t)(b >> 32) : a > b;
     const unsigned long long lo = s ? b : a, hi = s ? a : b;
     a = lo; b = hi;
 }
@@ -669,7 +674,13 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
         // (the classic while-while) every lane that already holds a leaf idles until the slowest lane of the warp has found one; one
         // step at a time (if-if) the leaf code is issued every iteration for few lanes.  Measured, same box (profiles/r2_41_ab_inner.txt):
         // sphere scenes are best at 1 (book-1 final 86.9 -> 83.5 ms), the 871 200-triangle mesh at 6 (58.3 -> 52.0 ms per 10 spp).
-        constexpr int INNER = RT_PM_HAS(PM, PRIM_TRI) ? 6 : 1;
+#ifndef RT_INNER_SPH
+#define RT_INNER_SPH 1
+#endif
+#ifndef RT_INNER_TRI
+#define RT_INNER_TRI 6
+#endif
+        constexpr int INNER = RT_PM_HAS(PM, PRIM_TRI) ? RT_INNER_TRI : RT_INNER_SPH;
 #pragma unroll 1
         for (int inner = 0; inner < INNER && cur != DONE && !(cur & RT_LEAF_FLAG); ++inner) {
             float4 lx, hx, ly, hy, lz, hz, rf;
@@ -708,10 +719,10 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
             // sort (far-to-near pushes) measured 2.7 % slower on book-1 final and 3 % on the 871 200-triangle mesh (profiles/r2_00_ab.log):
             // an entry that a nearer hit has culled is dropped when popped, so the order of the queued ones matters little.
             wide_ce(k0, k1); wide_ce(k2, k3); wide_ce(k0, k2);
-            if (k3 != ~0ull) wstk_put(stack, sp++, k3);
-            if (k2 != ~0ull) wstk_put(stack, sp++, k2);
-            if (k1 != ~0ull) wstk_put(stack, sp++, k1);
-            cur = (k0 != ~0ull) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
+            if (!RT_WIDE_MISS(k3)) wstk_put(stack, sp++, k3);
+            if (!RT_WIDE_MISS(k2)) wstk_put(stack, sp++, k2);
+            if (!RT_WIDE_MISS(k1)) wstk_put(stack, sp++, k1);
+            cur = !RT_WIDE_MISS(k0) ? (uint32_t)k0 : wide_pop(stack, sp, tmaxf);
         }
         if (cur != DONE && (cur & RT_LEAF_FLAG)) { // a leaf reference
             if (COUNT) cnt->prims += ((cur >> 25) & 7u) + 1u;
