@@ -1358,11 +1358,16 @@ static void launch_extend(int blocks, bool specialise, bool wide, cudaStream_t s
     // bytes but gain 5 % (tools/explore.py ab, Cornell smoke 634 -> 668, book-2 final 325 -> 340 Mpaths/s); 6 CTAs/SM (80
     // registers, 130-340 B spilled) is +1 % on Cornell smoke and -1.4 % on book-2 final.  Media whose boundary is one sphere / one box (scene.flags bit 1) use the kernel without
     // the general two-traversal path; the two media scenes of the reference also get their primitive mask compiled in.
-    // wide: only the counting pass of a scene whose fused kernel walks the 4-wide collapse.  The wavefront kernels themselves stay on
-    // sibling pairs: forced onto the wide tree they measured 718.7 vs 719.2 (Cornell smoke) and 341.3 vs 341.9 Mpaths/s (book-2 final)
+    // wide: the counting pass of a scene whose fused kernel walks the 4-wide collapse, and the two specialised media kernels (with
+    // the min / max node test they measured 718.7 vs 719.2 (Cornell smoke) and 341.3 vs 341.9 Mpaths/s (book-2 final) against the
+    // sibling pairs; with the signed-row test 722 vs 705 and 350 vs 340: profiles/r2_59_ab_ext_wide.txt)
     if constexpr (MEDIA) {
         if (!(scene.flags & 2u)) {
             k_extend<true, COUNT, 4, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
+        } else if (!COUNT && specialise && wide && (scene.prim_mask & ~0x18u) == 0) {
+            k_extend<true, false, 5, false, 0x18u, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // ... on the 4-wide tree
+        } else if (!COUNT && specialise && wide && (scene.prim_mask & ~0x1bu) == 0) {
+            k_extend<true, false, 5, false, 0x1bu, true><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity);
         } else if (!COUNT && specialise && (scene.prim_mask & ~0x18u) == 0) {
             k_extend<true, false, 5, false, 0x18u><<<blocks, 128, 0, st>>>(scene, J, P, Q, parity); // rects + boxes (Cornell scenes)
         } else if (!COUNT && specialise && (scene.prim_mask & ~0x1bu) == 0) {
@@ -1436,8 +1441,8 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
         // wavefront kernels walk the 4-wide collapse only when it was forced (unmeasured for them) - and in the counting pass of a
         // scene whose fused kernel walks it, so that the device counters describe the tree the timed kernel walks (4 boxes per visit)
         const bool count_wide = tune.count_events && !media && scene.nodes4 != nullptr && tune.bvh_wide != 0;
-        const bool ext_wide = count_wide;
-        const int ext_kind = count_wide ? 0 : ext_kind_auto; // k_extend_p has no wide form
+        const bool ext_wide = count_wide || (media && scene.nodes4 != nullptr && tune.bvh_wide != 0); // see launch_extend
+        const int ext_kind = ext_wide ? 0 : ext_kind_auto; // k_extend_p has no wide form
         const int eblocks = (int)std::min<uint32_t>((N + 127) / 128, 148u * (uint32_t)std::max(4, ext_occ) * (uint32_t)std::max(1, tune.extend_waves));
         CK(cudaEventRecord(w->ev_begin, stream));
         // RT_MODE_AUTO (measured on B200, profiles/README.md): the fused persistent kernel wins where shading is cheap

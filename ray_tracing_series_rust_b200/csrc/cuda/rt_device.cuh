@@ -680,7 +680,10 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
 #ifndef RT_INNER_TRI
 #define RT_INNER_TRI 6
 #endif
-        constexpr int INNER = RT_PM_HAS(PM, PRIM_TRI) ? RT_INNER_TRI : RT_INNER_SPH;
+#ifndef RT_INNER_MEDIA
+#define RT_INNER_MEDIA 1 // the media wavefront kernels' masks (rects + boxes, + spheres + moving spheres): 1 / 2 / unbounded measured, 1 is best
+#endif
+        constexpr int INNER = RT_PM_HAS(PM, PRIM_TRI) ? RT_INNER_TRI : ((PM == 0x18u || PM == 0x1bu) ? RT_INNER_MEDIA : RT_INNER_SPH);
 #pragma unroll 1
         for (int inner = 0; inner < INNER && cur != DONE && !(cur & RT_LEAF_FLAG); ++inner) {
             float4 lx, hx, ly, hy, lz, hz, rf;

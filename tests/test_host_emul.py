@@ -159,7 +159,7 @@ def test_wide_world_hit_equals_pair_world_hit(orc, emul, scene_id):
 
 def test_wide_collapse_is_built_only_where_asked_or_measured(emul):
     nbytes = emul.emul_sizeof_device_scene()
-    for scene_id, width, built in ((5, 0, False), (6, 0, False), (8, 0, False), (13, 0, True), (13, 2, False), (6, 4, True), (5, 4, True)):
+    for scene_id, width, built in ((5, 0, True), (6, 0, True), (5, 2, False), (3, 0, False), (8, 0, False), (13, 0, True), (13, 2, False), (6, 4, True), (5, 4, True)):
         s, ds = host_scene(emul, scene_id, width=width)
         assert (emul.emul_trace_batch(ds, None, 0, 0.001, 1.0, 0, 0, 1, None, None) == 0) == built, (scene_id, width)
         s.close()
@@ -274,3 +274,27 @@ def test_motion_form_of_the_wide_walk(orc, emul, scene_id):
     assert emul.emul_trace_wide(d13, None, 0, 0.001, 1.0, 0, 1, None) == -2
     for x in (s2, s4, o, s13):
         x.close()
+
+
+def test_rng_conversions_equal_the_formulas_they_replace(emul):
+    """PathRng::unit_of / pm1_of (bits of 2^52 + u, one fma) against (double)u * 2^-32 and fma(xi, 2, -1): bit-equal for the edge
+    words and 2 M random ones (both forms are exact, so this is an identity, not a tolerance)."""
+    emul.emul_rng_convert_mismatches.restype = C.c_uint64
+    emul.emul_rng_convert_mismatches.argtypes = [C.c_uint64, C.c_uint64]
+    assert emul.emul_rng_convert_mismatches(2_000_000, 0x9E3779B97F4A7C15) == 0
+
+
+@pytest.mark.parametrize("scene_id,param,W,H,spp,max_index", [(13, 0, 120, 80, 2, 12), (14, 64, 60, 60, 2, 32)])
+def test_wide_stack_depth_stays_far_below_its_capacity(emul, scene_id, param, W, H, spp, max_index):
+    """The 4-wide walk's stack (RT_WIDE_STACK = 96 entries per lane) as the fused kernels use it: accesses per index over whole
+    paths.  book-1 never goes past 8 entries (the full 871 200-triangle mesh: 19, tools/ measured once); what the shared-memory
+    stack experiment of round 2 was sized with (profiles/r2_50_ab_signed_rows_smem_stack.txt)."""
+    emul.emul_wide_stack_hist.restype = C.c_int32
+    emul.emul_wide_stack_hist.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]
+    s, ds = host_scene(emul, scene_id, param=param, width=4)
+    hist = np.zeros(96, dtype=np.uint64)
+    seg = C.c_uint64(0)
+    assert emul.emul_wide_stack_hist(ds, W, H, spp, 50, 3, hist.ctypes.data, C.byref(seg)) == 0
+    assert seg.value > W * H * spp and hist.sum() > 0
+    assert int(np.nonzero(hist)[0].max()) < max_index
+    s.close()
