@@ -192,13 +192,14 @@ RT_DEV void best_init(BestHit& b, double t_max) { b.t = t_max; b.type = RT_NONE;
 // Accepts t <= closest_so_far like the reference's list scan (hit.rs:675-683: the later element wins
 // an exact tie).  Ties are decided by the depth-first leaf id, fetched only when a tie happens.
 RT_DEV void consider(const DeviceScene& S, BestHit& best, double t, uint32_t type, uint32_t idx, uint32_t side, uint32_t inst) {
-    if (!(t <= best.t) || !(t < RT_INF)) return; // NaN and +inf are rejected (documented divergence: the reference lets t = +inf through)
-    if (t == best.t && best.type != RT_NONE) {
+    bool ok = (t <= best.t) & (t < RT_INF); // NaN and +inf are rejected (documented divergence: the reference lets t = +inf through)
+    if (ok & (t == best.t) & (best.type != RT_NONE)) { // the one (rare) branch; the update below is selects (see box_side_ok)
         const uint32_t pid_new = __ldg(&S.meta[type][idx].prim_id) + side;
         const uint32_t pid_old = __ldg(&S.meta[best.type][best.idx].prim_id) + best.side;
-        if (pid_new < pid_old) return;
+        ok = !(pid_new < pid_old);
     }
-    best.t = t; best.type = type; best.idx = idx; best.side = side; best.inst = inst;
+    best.t = ok ? t : best.t; best.type = ok ? type : best.type; best.idx = ok ? idx : best.idx; best.side = ok ? side : best.side;
+    best.inst = ok ? inst : best.inst;
 }
 
 // ------------------------------------------------------------------ primitive tests (f64)
@@ -267,15 +268,30 @@ RT_DEV double box_side_t(const Ray& r, const RayPre& pre, const DBox& b, int s) 
 }
 // RectPrism = HittableList of six rects scanned in order with a shrinking closest_so_far
 // (hit.rs:660-690).  Returns t and the winning side (later side wins an exact tie).
+// Branch-free form of one side: the same t, the same hit point and the same comparisons as box_side_t + the scan's own tests, folded
+// into one predicate (a side whose t is not finite, or that misses the rect, or that lies outside [t_min, closest] changes nothing).
+// Round 2: early returns are what costs in the leaf code, which runs at 2-8 of 32 lanes (branch / reconvergence / instruction-fetch
+// stalls per useful instruction): box sides book-2 final +6.2 %, Cornell smoke +1.3 %; consider() 871 200-triangle mesh +3.0 %;
+// triangle test mesh +2.5 %; the same treatment LOSES on sphere_root (book-1 final -3 %) and is neutral on rect_t, which keep their
+// early returns (profiles/r2_61 ... r2_64).
+RT_DEV bool box_side_ok(const Ray& r, const RayPre& pre, const DBox& b, int s, double t_min, double closest, double& t) {
+    const int ax = s < 2 ? 2 : (s < 4 ? 1 : 0);
+    const int ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+    const double k = (s & 1) ? b.p0[ax] : b.p1[ax];
+    t = (k - axis_of(r.o, ax)) * axis_of(pre.inv_d, ax);
+    const double x = fma(t, axis_of(r.d, ia), axis_of(r.o, ia));
+    const double y = fma(t, axis_of(r.d, ib), axis_of(r.o, ib));
+    return (t < RT_INF) & (t > -RT_INF) & !(x < b.p0[ia]) & !(x > b.p1[ia]) & !(y < b.p0[ib]) & !(y > b.p1[ib]) & !(t < t_min) & !(t > closest);
+}
 RT_DEV double box_t(const Ray& r, const RayPre& pre, const DBox& b, double t_min, double t_max, uint32_t& side_out) {
     double closest = t_max;
     bool any = false;
     uint32_t side = 0;
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
-        const double t = box_side_t(r, pre, b, s);
-        if (t < t_min || t > closest || !(t < RT_INF)) continue;
-        closest = t; any = true; side = (uint32_t)s;
+        double t;
+        const bool ok = box_side_ok(r, pre, b, s, t_min, closest, t);
+        closest = ok ? t : closest; side = ok ? (uint32_t)s : side; any = any | ok;
     }
     side_out = side;
     return any ? closest : RT_INF;
@@ -287,15 +303,14 @@ RT_DEV double tri_t(const Ray& r, const DTri* __restrict__ tp, double t_min, dou
     const float4 q2 = __ldg(reinterpret_cast<const float4*>(tp) + 2);
     const D3 v0 = mk3(q0.x, q0.y, q0.z), v1 = mk3(q0.w, q1.x, q1.y), v2 = mk3(q1.z, q1.w, q2.x), n = mk3(q2.y, q2.z, q2.w);
     const double nd = dot(n, r.d);
-    if (fabs(nd) < 0.0001) return RT_INF;
     const double dd = __ldg(&tp->dd); // -(n . v0) with the exact f64 vertex (rt_types.h DTri)
+    // the reference's five tests (|n.d| cutoff, t range, three inclusive edge tests) as one predicate instead of five early returns:
+    // a rejected t still yields a point whose edge tests are ignored (see box_side_ok)
     const double t = -(dot(n, r.o) + dd) / nd;
-    if (t < t_min || t > t_max) return RT_INF;
     const D3 p = ray_at(r, t);
-    if (dot(n, cross(v1 - v0, p - v0)) < 0.0) return RT_INF;
-    if (dot(n, cross(v2 - v1, p - v1)) < 0.0) return RT_INF;
-    if (dot(n, cross(v0 - v2, p - v2)) < 0.0) return RT_INF;
-    return t;
+    const bool miss = (fabs(nd) < 0.0001) | (t < t_min) | (t > t_max) | (dot(n, cross(v1 - v0, p - v0)) < 0.0) | (dot(n, cross(v2 - v1, p - v1)) < 0.0) |
+                      (dot(n, cross(v0 - v2, p - v2)) < 0.0);
+    return miss ? RT_INF : t;
 }
 
 // ------------------------------------------------------------------ BVH traversal (aabb.rs:23-61, bvh.rs:97-112)
