@@ -519,9 +519,10 @@ __global__ void __launch_bounds__(256, RT_SHADE_MIN_BLOCKS) k_shade_all(const __
 #endif
 // Camera rays are generated 32 at a time by the whole warp into a per-warp buffer in shared memory, and ended lanes take theirs from
 // it: pixel jitter, lens-disk rejection loop and the two Philox blocks of a new path run at 32 lanes every third iteration or so
-// instead of at the ~10 lanes that happen to have ended in this one.  Measured (profiles/r2_57_ab_cam_batch.txt): book-1 final 70.3 ->
-// 68.2 ms; book-1 as shipped +-0, a bouncing-spheres frame -2.2 % (their pair walks over motion boxes / gravity tables miss the 9 KB
-// per CTA that the buffer takes from L1), so only the plain-sphere kernel on the 4-wide tree uses it (RT_CAM_BATCH = 0: none does).
+// instead of at the ~10 lanes that happen to have ended in this one.  Measured: book-1 final 70.3 -> 68.2 ms (profiles/r2_57_ab_cam_batch.txt);
+// on the sibling-pair kernels of the moving / gravity sphere scenes +-0 / -2.2 % (their walks miss the 9 KB per CTA that the buffer
+// takes from L1), on the same scenes' 4-wide kernels +5.4 % / +0.2 % (r2_67): the three sphere kernels on the 4-wide tree use it
+// (RT_CAM_BATCH = 0: none does).
 template <bool ON> struct CamBufferT {
     double v[4][7][32]; // [warp][o.x o.y o.z d.x d.y d.z time][entry]
     unsigned long long path_id[4][32];
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(128, MINB) k_mega(const __grid_constant__ Devi
     uint64_t path_id = 0;
     bool alive = false, exhausted = false;
     uint32_t my_segments = 0;
-    constexpr bool CAMB = RT_CAM_BATCH && WIDE && PM == 0x1u;
+    constexpr bool CAMB = RT_CAM_BATCH && WIDE && (PM == 0x1u || PM == 0x3u || PM == 0x5u);
     __shared__ CamBufferT<CAMB> cam;
     const uint32_t wid = threadIdx.x >> 5, ln = lane_id();
     uint32_t buf_head = 0, buf_count = 0; // warp-uniform

@@ -703,9 +703,16 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
         for (int inner = 0; inner < INNER && cur != DONE && !(cur & RT_LEAF_FLAG); ++inner) {
             float4 lx, hx, ly, hy, lz, hz, rf;
             if (MOTION) { // box(t) = box at the shutter's start + s * delta: 256 bytes per node
+                // (signed rows as below: start and end boxes are valid and the interpolation is monotonic, so lo(t) <= hi(t) holds)
                 const float4* __restrict__ q = mnodes4 + 16 * (size_t)cur;
-                lx = __ldg(q); hx = __ldg(q + 1); ly = __ldg(q + 2); hy = __ldg(q + 3); lz = __ldg(q + 4); hz = __ldg(q + 5); rf = __ldg(q + 6);
-                const float4 dlx = __ldg(q + 8), dhx = __ldg(q + 9), dly = __ldg(q + 10), dhy = __ldg(q + 11), dlz = __ldg(q + 12), dhz = __ldg(q + 13);
+                const float4* qx = RT_WIDE_SIGNED ? wide_row(q, sgx) : q;
+                const float4* qX = RT_WIDE_SIGNED ? wide_row(q, sgx ^ 16u) : q + 1;
+                const float4* qy = RT_WIDE_SIGNED ? wide_row(q, sgy) + 2 : q + 2;
+                const float4* qY = RT_WIDE_SIGNED ? wide_row(q, sgy ^ 16u) + 2 : q + 3;
+                const float4* qz = RT_WIDE_SIGNED ? wide_row(q, sgz) + 4 : q + 4;
+                const float4* qZ = RT_WIDE_SIGNED ? wide_row(q, sgz ^ 16u) + 4 : q + 5;
+                lx = __ldg(qx); hx = __ldg(qX); ly = __ldg(qy); hy = __ldg(qY); lz = __ldg(qz); hz = __ldg(qZ); rf = __ldg(q + 6);
+                const float4 dlx = __ldg(qx + 8), dhx = __ldg(qX + 8), dly = __ldg(qy + 8), dhy = __ldg(qY + 8), dlz = __ldg(qz + 8), dhz = __ldg(qZ + 8);
                 lx.x = fmaf(dlx.x, ms, lx.x); lx.y = fmaf(dlx.y, ms, lx.y); lx.z = fmaf(dlx.z, ms, lx.z); lx.w = fmaf(dlx.w, ms, lx.w);
                 hx.x = fmaf(dhx.x, ms, hx.x); hx.y = fmaf(dhx.y, ms, hx.y); hx.z = fmaf(dhx.z, ms, hx.z); hx.w = fmaf(dhx.w, ms, hx.w);
                 ly.x = fmaf(dly.x, ms, ly.x); ly.y = fmaf(dly.y, ms, ly.y); ly.z = fmaf(dly.z, ms, ly.z); ly.w = fmaf(dly.w, ms, ly.w);
@@ -722,7 +729,7 @@ RT_DEV void walk_wide(const DeviceScene& S, const Ray& r, const RayF& f, const R
             }
             if (COUNT) cnt->nodes += 4;
             unsigned long long k0, k1, k2, k3;
-            if (RT_WIDE_SIGNED && !MOTION) {
+            if (RT_WIDE_SIGNED) {
                 k0 = wide_key_nf(lx.x, hx.x, ly.x, hy.x, lz.x, hz.x, rf.x, f, tminf, tmaxf);
                 k1 = wide_key_nf(lx.y, hx.y, ly.y, hy.y, lz.y, hz.y, rf.y, f, tminf, tmaxf);
                 k2 = wide_key_nf(lx.z, hx.z, ly.z, hy.z, lz.z, hz.z, rf.z, f, tminf, tmaxf);

@@ -782,7 +782,10 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
     // +6 %) or a large triangle mesh (871 200 triangles +20 %); not GravitySphere scenes (-2 %).  rt_scene_set_bvh_width(4)
     // builds it for every main-world instance (the wavefront / generic kernels then walk it too: to be measured).
     const bool single_plain = HF.n_main_instances == 1 && media.empty() && instances[world_range[0].first].chain_len == 0;
-    const bool only_spheres = !spheres.empty() && movings.empty() && gravities.empty() && rects.empty() && boxes.empty() && tris.empty();
+    // (GravitySphere scenes, the animation config: -2 % on the wide tree in round 1, +11 % since the signed-row node test; MovingSphere
+    // scenes, book-1 as shipped: -7.6 % with the min / max form of the motion nodes, +8.2 % with their signed rows:
+    // profiles/r2_65_ab_wide_gravity_motion.txt, r2_66_ab_motion_signed.txt)
+    const bool only_spheres = (!spheres.empty() || !movings.empty() || !gravities.empty()) && rects.empty() && boxes.empty() && tris.empty();
     const bool big_mesh = tris.size() >= 4096 && spheres.empty() && movings.empty() && gravities.empty() && boxes.empty();
     // round 2: the two primitive-mask-specialised media kernels of the wavefront (Cornell smoke, book-2 final: media with the
     // single-sphere / single-box fast path over spheres, moving spheres, rects and boxes) walk it too: +2.5 % / +3.4 % with the
