@@ -381,10 +381,12 @@ RTB_EXPORT int32_t rt_scene_set_tuning(rt_scene* s, uint32_t wave_slots);
 #define RT_BVH_HOST_SAH 0
 #define RT_BVH_DEVICE_LBVH 1
 RTB_EXPORT int32_t rt_scene_set_bvh_builder(rt_scene* s, int32_t builder);
-/* Branching factor of the tree the fused kernels walk   [ref: src/bvh.rs:97-112, the binary BvhNode::hit].
- * 2: sibling pairs.  4: rt_scene_commit also collapses the tree of a scene with one wrapper-free instance and no media
- * into 128-byte 4-wide nodes (csrc/host/bvh_wide.hpp) and the fused kernels walk those; other scenes ignore it.
- * 0 (default): 4 where it measured faster (plain-sphere scenes, meshes of >= 4096 triangles), else 2.
+/* Branching factor of the tree the kernels walk   [ref: src/bvh.rs:97-112, the binary BvhNode::hit].
+ * 2: sibling pairs.  4: rt_scene_commit also collapses the trees of the main world's instances into 128-byte 4-wide nodes
+ * (csrc/host/bvh_wide.hpp); the kernels that have a 4-wide form walk those, the others ignore it.
+ * 0 (default): 4 where it measured faster - one wrapper-free instance without media that holds only spheres of any kind
+ * (Sphere, MovingSphere, GravitySphere) or a mesh of >= 4096 triangles (fused kernels), and scenes whose media all have a
+ * single-sphere / single-box boundary over spheres, moving spheres, rects and boxes (wavefront kernels) - else 2.
  * Results are identical (closest hit is topology independent). */
 RTB_EXPORT int32_t rt_scene_set_bvh_width(rt_scene* s, int32_t width);
 /* 4 if the last rt_scene_commit built the 4-wide collapse (the fused kernels then walk it), else 2; < 0 if not committed. */

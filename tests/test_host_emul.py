@@ -159,7 +159,7 @@ def test_wide_world_hit_equals_pair_world_hit(orc, emul, scene_id):
 
 def test_wide_collapse_is_built_only_where_asked_or_measured(emul):
     nbytes = emul.emul_sizeof_device_scene()
-    for scene_id, width, built in ((5, 0, True), (6, 0, True), (5, 2, False), (3, 0, False), (8, 0, False), (13, 0, True), (13, 2, False), (6, 4, True), (5, 4, True)):
+    for scene_id, width, built in ((5, 0, True), (6, 0, True), (5, 2, False), (3, 0, False), (8, 0, True), (99, 0, True), (8, 2, False), (13, 0, True), (13, 2, False), (6, 4, True), (5, 4, True)):
         s, ds = host_scene(emul, scene_id, width=width)
         assert (emul.emul_trace_batch(ds, None, 0, 0.001, 1.0, 0, 0, 1, None, None) == 0) == built, (scene_id, width)
         s.close()
