@@ -391,6 +391,33 @@ def test_device_lbvh_builder_parity(orc, scene_id, param, monkeypatch):
         g.set_bvh_builder(7)
 
 
+@pytest.mark.parametrize("scene_id", [5, 6])
+def test_wavefront_wide_walk_is_bit_identical_to_the_pair_walk(orc, scene_id):
+    # Cornell smoke / book-2 final: RT_MODE_AUTO renders them with the wavefront, whose two media kernels walk the main world's 4-wide
+    # tree since late round 2 (k_extend<..., WIDE>, auto width); the image equals the sibling-pair walk's bit for bit and the
+    # oracle's sums within the E2 bar.  book-2 final has two main-world instances (one under RotateY + Translate): one wide root each.
+    acc, segs = {}, {}
+    cfg = capi.make_config(64, 1.0, 6, 50, seed=5)
+    for width in (2, 4, 0):
+        g = rtb.new_scene()
+        g.world_build(scene_id, 0xB002, 0)
+        g.set_bvh_width(width)
+        g.commit()
+        assert g.bvh_width() == (2 if width == 2 else 4)
+        _, acc[width], st = g.render(cfg, want_accum=True)
+        segs[width] = st["segments"]
+        assert st["iterations"] > 1  # wavefront mode
+        g.close()
+    assert np.array_equal(acc[2], acc[4]) and np.array_equal(acc[2], acc[0]) and segs[2] == segs[4] == segs[0]
+    o = orc.new_scene()
+    o.world_build(scene_id, 0xB002, 0)
+    o.commit()
+    _, a_o, _ = o.render(cfg, want_accum=True)
+    rel = np.abs(acc[0] - a_o) / np.maximum(np.abs(a_o), 2.0 ** 32 * 1e-3)
+    assert (rel > 1e-5).any(axis=2).mean() < 0.02
+    o.close()
+
+
 @pytest.mark.parametrize("scene_id,param,env", [(13, 0, None), (8, 0, None), (14, 64, None), (14, 64, {"RTB200_MEGA_WAIT": "0"}), (10, 0, None),
                                                 (99, 0, None), (7, 0, None)])
 def test_wide_bvh_walk_is_bit_identical_to_the_pair_walk(orc, scene_id, param, env, monkeypatch):
