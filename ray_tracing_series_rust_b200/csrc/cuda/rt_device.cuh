@@ -56,7 +56,9 @@ RT_DEV D3 ray_at(const Ray& r, double t) { return mk3(fma(r.d.x, t, r.o.x), fma(
 // out-of-line copy 94.4 ms (the kernel stalled on instruction fetch for 19 % of its samples).  Resolving the samplers'
 // draw positions at compile time removes next_u32's word selection but was 1-8 % slower in every combination (fewer
 // instructions, slower kernel: at ~11 active lanes per instruction the bound is fetch / issue latency of divergent
-// code), so the samplers below go through next_u32.
+// code: four unrolled copies of the candidate).  What did pay, late in round 2, is ONE copy of the candidate that takes its
+// two / three words at once and picks them with selects (next2_pm1 / next3_pm1 below): book-1 final 80.8 -> 75.2 ms;
+// Philox inlined again with those: 82.1 ms; a single Philox call site per sampler: 76.7 ms (profiles/r2_52, r2_53).
 // ------------------------------------------------------------------ Philox-4x32-10 / PathRng
 RT_DEV uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

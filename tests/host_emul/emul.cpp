@@ -155,10 +155,13 @@ int32_t emul_trace_wide(const void* scene, const rt_ray* rays, int64_t n, double
 }
 
 // One path of k_mega / k_shade_all + k_extend, lane by lane: camera_first_ray -> (world_hit -> emitted / scatter)* -> fixed-point
-// accumulate (kernels.cu accumulate()).  Same device functions, same Philox streams as the kernels; wide != 0 walks Instance::root4.
+// accumulate (kernels.cu accumulate()).  Same device functions, same Philox streams as the kernels; wide bit 0 walks Instance::root4,
+// bit 1 shades in the fused kernels' order of operations.
 int32_t emul_render(const void* scene, int32_t W, int32_t H, int32_t spp_total, int32_t sample_begin, int32_t sample_end, int32_t max_depth, uint64_t seed,
                     int32_t wide, int64_t* accum, uint64_t* segments_out) {
     const DeviceScene& S = *static_cast<const DeviceScene*>(scene);
+    const bool fused_style = (wide & 2) != 0; // bit 1: shade as the fused kernels do (same draws in the same order, restructured)
+    wide &= 1;
     if (wide && !S.nodes4) return -1;
     uint64_t segments = 0;
     for (int32_t j = 0; j < H; ++j)
@@ -182,19 +185,32 @@ int32_t emul_render(const void* scene, int32_t W, int32_t H, int32_t spp_total, 
                         contrib = mkf3(tr * e.x, tg * e.y, tb * e.z);
                         break;
                     }
-                    PathRng g;
-                    g.init(seed, path_id, draw);
                     D3 dir = mk3(0, 0, 0);
                     F3 att = mkf3(0.f, 0.f, 0.f);
                     bool scattered;
-                    if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
-                    else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
-                    else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
-                    else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                    if (fused_style) { // as k_mega / k_mega_r shade: event opened before the material branch, one rejection loop for three materials
+                        PathRngOolBegun g;
+                        g.init(seed, path_id, draw);
+                        g.open_event();
+                        D3 rs = mk3(0, 0, 0);
+                        if (m.type != MAT_DIELECTRIC) rs = random_in_unit_sphere(g);
+                        if (m.type == MAT_LAMBERTIAN) scattered = lambertian_finish(S, m, h.p, h.n, h.u, h.v, rs, dir, att);
+                        else if (m.type == MAT_METAL) scattered = metal_finish(m, r.d, h.n, rs, dir, att);
+                        else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
+                        else scattered = isotropic_finish(S, m, h.p, h.u, h.v, rs, dir, att);
+                        draw = g.draw;
+                    } else { // as k_shade_all shades
+                        PathRng g;
+                        g.init(seed, path_id, draw);
+                        if (m.type == MAT_LAMBERTIAN) scattered = scatter_lambertian(S, m, h.p, h.n, h.u, h.v, g, dir, att);
+                        else if (m.type == MAT_METAL) scattered = scatter_metal(m, r.d, h.n, g, dir, att);
+                        else if (m.type == MAT_DIELECTRIC) scattered = scatter_dielectric(m, r.d, h.n, h.front, g, dir, att);
+                        else scattered = scatter_isotropic(S, m, h.p, h.u, h.v, g, dir, att);
+                        draw = g.draw;
+                    }
                     if (!(scattered && (int32_t)(segment + 1) < max_depth)) break;
                     tr *= att.x; tg *= att.y; tb *= att.z;
                     r.o = h.p; r.d = dir;
-                    draw = g.draw;
                 }
                 const double v[3] = {(double)contrib.x, (double)contrib.y, (double)contrib.z};
                 for (int c = 0; c < 3; ++c) { // kernels.cu accumulate(): 2^32 fixed point, one sample clamped to [0, 2^20]

@@ -298,3 +298,15 @@ def test_wide_stack_depth_stays_far_below_its_capacity(emul, scene_id, param, W,
     assert seg.value > W * H * spp and hist.sum() > 0
     assert int(np.nonzero(hist)[0].max()) < max_index
     s.close()
+
+
+@pytest.mark.parametrize("scene_id,param,W,H,spp", [(13, 0, 60, 40, 6), (99, 0, 64, 36, 4), (6, 0, 40, 40, 4), (5, 0, 40, 40, 6), (14, 32, 40, 40, 4), (1, 0, 48, 32, 4)])
+def test_fused_order_of_shading_draws_the_same_numbers(emul, scene_id, param, W, H, spp):
+    """The fused kernels open the scatter event before the branch on the material and run one rejection loop for Lambertian, Metal
+    and Isotropic lanes (lambertian_finish / metal_finish / isotropic_finish); k_shade_all calls scatter_* per material.  Same draws
+    in the same order: the two orders give the same int64 sums, bit for bit (on the GPU: test_fused_mode_is_bit_identical_to_wavefront)."""
+    s, ds = host_scene(emul, scene_id, param=param, width=2)
+    a0, s0 = emul_render(emul, ds, W, H, spp, 50, 33, wide=0)
+    a1, s1 = emul_render(emul, ds, W, H, spp, 50, 33, wide=2)
+    assert s0 == s1 and np.array_equal(a0, a1)
+    s.close()
