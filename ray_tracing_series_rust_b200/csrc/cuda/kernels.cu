@@ -1495,9 +1495,10 @@ cudaError_t launch_render(const DeviceScene& scene, const RenderJob& job, const 
                 J.chunk = (uint32_t)c;
             }
             const bool wrapper_free = !(scene.flags & 32u) && tune.prim_specialise == 2;
-            // resumable traversal: +7 % on the 871k-triangle mesh at 20 lanes, -4 .. -40 % on the sphere scenes, whose shading share
+            // resumable traversal: +7 % on the 871k-triangle mesh at 20 lanes (round 1), -4 .. -40 % on the sphere scenes, whose shading share
             // is too large to run it with half-empty warps (tools/explore.py ab RTB200_MEGA_WAIT ...)
-            const int mega_wait = tune.mega_wait >= 0 ? tune.mega_wait : ((scene.flags & 4u) ? 20 : 0);
+            // (re-swept on the final kernel, profiles/r2_68_mesh_wait_sweep.txt: 12 / 16 / 20 / 24 / 28 lanes -> 230 / 231.5 / 227 / 215 / 199 Mpaths/s)
+            const int mega_wait = tune.mega_wait >= 0 ? tune.mega_wait : ((scene.flags & 4u) ? 16 : 0);
             J.wait_thresh = (uint32_t)std::max(1, std::min(32, mega_wait));
             if (media) {
                 if (!(scene.flags & 2u)) k_mega<true, 3, true><<<148 * 3, 128, 0, stream>>>(scene, J, Q, d_accum);
