@@ -8,8 +8,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -78,6 +81,14 @@ public:
             nodes_.push_back(dummy);
         }
         const uint32_t n_all = (uint32_t)prims.size();
+        const bool timing = std::getenv("RTB200_COMMIT_TIMING") != nullptr && n_all >= 65536u;
+        auto tp0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (!timing) return;
+            const auto t = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[rtb200 commit]   sah %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+            tp0 = t;
+        };
         unsigned hw = std::thread::hardware_concurrency();
         const unsigned threads = n_all >= 32768u ? std::min(16u, std::max(1u, hw)) : 1u;
         // ---- top of the tree (serial): split until a range is a task
@@ -106,6 +117,7 @@ public:
                 stack.push_back({left, w.lo, mid, w.depth + 1});
             }
         }
+        lap("top (serial)");
         // ---- subtrees (parallel): every task owns a disjoint range of `prims`
         std::vector<Subtree> sub(tasks.size());
         auto run = [&](size_t k) { build_subtree(prims, tasks[k].lo, tasks[k].hi, tasks[k].depth, sub[k]); };
@@ -118,6 +130,7 @@ public:
                 pool.emplace_back([&]() { for (size_t k = next.fetch_add(1); k < tasks.size(); k = next.fetch_add(1)) run(k); });
             for (std::thread& th : pool) th.join();
         }
+        lap("subtrees");
         // ---- splice in depth-first order: rebase node links and typed leaf indices
         size_t total_nodes = nodes_.size(), total_leaf = 0;
         for (const Subtree& st : sub) { total_nodes += st.nodes.size(); total_leaf += st.leaf_order.size(); }
@@ -137,6 +150,7 @@ public:
             res.leaf_order.insert(res.leaf_order.end(), st.leaf_order.begin(), st.leaf_order.end());
             res.max_depth = std::max(res.max_depth, st.max_depth);
         }
+        lap("splice");
         return res;
     }
 

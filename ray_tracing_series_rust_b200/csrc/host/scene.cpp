@@ -13,6 +13,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -217,6 +218,22 @@ void number_leaves(rt_scene* s, int32_t id, int32_t& next) {
 }
 
 // ---------------------------------------------------------------- flattening
+// Mesh-sized host loops (871 200 triangles: boxes, build records, typed triangles) run in contiguous chunks on up to 16 threads;
+// every index is written by exactly one thread, so the arrays are those of the serial loop.
+template <class F> void parallel_chunks(size_t n, F&& body) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t threads = n >= 65536 ? std::min<size_t>(16, std::max(1u, hw)) : 1;
+    if (threads <= 1) { body((size_t)0, n); return; }
+    const size_t chunk = (n + threads - 1) / threads;
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < threads; ++t) {
+        const size_t b = std::min(n, t * chunk), e = std::min(n, b + chunk);
+        if (b < e) pool.emplace_back([&body, b, e]() { body(b, e); });
+    }
+    body((size_t)0, std::min(n, chunk));
+    for (std::thread& th : pool) th.join();
+}
+
 struct FlatPrim {
     uint32_t type;
     int32_t node;     // source node
@@ -309,20 +326,24 @@ struct Flattener {
             break;
         case N_MESH: {
             const MeshData& m = *n.mesh;
-            const size_t nt = m.faces.size() / 3;
-            ib.prims.reserve(ib.prims.size() + nt);
-            for (size_t t = 0; t < nt; ++t) {
-                FlatPrim q;
-                q.type = PRIM_TRI; q.node = id; q.sub = (uint32_t)t; q.mat = (uint32_t)n.mat; q.prim_id = (uint32_t)n.prim_base + (uint32_t)t;
-                const double* v0 = &m.verts[3 * (size_t)m.faces[3 * t]];
-                const double* v1 = &m.verts[3 * (size_t)m.faces[3 * t + 1]];
-                const double* v2 = &m.verts[3 * (size_t)m.faces[3 * t + 2]];
-                for (int a = 0; a < 3; ++a) {
-                    q.bmin[a] = std::fmin(v0[a], std::fmin(v1[a], v2[a]));
-                    q.bmax[a] = std::fmax(v0[a], std::fmax(v1[a], v2[a]));
+            const size_t nt = m.faces.size() / 3, base = ib.prims.size();
+            ib.prims.resize(base + nt);
+            FlatPrim* out = ib.prims.data() + base;
+            const int32_t mat = n.mat, prim_base = n.prim_base;
+            parallel_chunks(nt, [&m, out, id, mat, prim_base](size_t t0, size_t t1) {
+                for (size_t t = t0; t < t1; ++t) {
+                    FlatPrim q;
+                    q.type = PRIM_TRI; q.node = id; q.sub = (uint32_t)t; q.mat = (uint32_t)mat; q.prim_id = (uint32_t)prim_base + (uint32_t)t;
+                    const double* v0 = &m.verts[3 * (size_t)m.faces[3 * t]];
+                    const double* v1 = &m.verts[3 * (size_t)m.faces[3 * t + 1]];
+                    const double* v2 = &m.verts[3 * (size_t)m.faces[3 * t + 2]];
+                    for (int a = 0; a < 3; ++a) {
+                        q.bmin[a] = std::fmin(v0[a], std::fmin(v1[a], v2[a]));
+                        q.bmax[a] = std::fmax(v0[a], std::fmax(v1[a], v2[a]));
+                    }
+                    out[t] = q;
                 }
-                ib.prims.push_back(q);
-            }
+            });
             return;
         }
         default: return;
@@ -504,9 +525,17 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
     // domain radius: every coordinate the f32 slab test can see (boxes in instance space, camera origin)
     double R = 1.0;
     for (const WorldBuild& w : F.worlds)
-        for (const InstBuild& ib : w.inst)
-            for (const FlatPrim& p : ib.prims)
-                for (int a = 0; a < 3; ++a) { R = std::fmax(R, std::fabs(p.bmin[a])); R = std::fmax(R, std::fabs(p.bmax[a])); }
+        for (const InstBuild& ib : w.inst) {
+            std::mutex mu;
+            const FlatPrim* fp = ib.prims.data();
+            parallel_chunks(ib.prims.size(), [&](size_t i0, size_t i1) { // a maximum: the same value in any order
+                double r = 1.0;
+                for (size_t i = i0; i < i1; ++i)
+                    for (int a = 0; a < 3; ++a) { r = std::fmax(r, std::fabs(fp[i].bmin[a])); r = std::fmax(r, std::fabs(fp[i].bmax[a])); }
+                std::lock_guard<std::mutex> lock(mu);
+                R = std::fmax(R, r);
+            });
+        }
     if (s->camera.set)
         for (int a = 0; a < 3; ++a) R = std::fmax(R, 2.0 * std::fabs(s->camera.cam.origin[a]));
     s->domain_radius = R;
@@ -531,13 +560,26 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
     if (env_cp) bo.cost_prim = std::atof(env_cp);
 
     std::vector<MotionBox> mbox[PRIM_TYPE_COUNT];
+    // the shutter-end boxes are only read by the MovingSphere refit below (96 bytes per primitive: 84 MB for the 871 200-triangle mesh)
+    bool has_moving = false;
+    {
+        size_t per_type[PRIM_TYPE_COUNT] = {0, 0, 0, 0, 0, 0};
+        for (const WorldBuild& w : F.worlds)
+            for (const InstBuild& ib : w.inst)
+                for (const FlatPrim& p : ib.prims) ++per_type[p.type];
+        has_moving = per_type[PRIM_MOVING] != 0;
+        spheres.reserve(per_type[PRIM_SPHERE]); movings.reserve(per_type[PRIM_MOVING]); gravities.reserve(per_type[PRIM_GRAVITY]);
+        rects.reserve(per_type[PRIM_RECT]); boxes.reserve(per_type[PRIM_BOX]); tris.reserve(per_type[PRIM_TRI]);
+        for (int t = 0; t < (int)PRIM_TYPE_COUNT; ++t) { meta[t].reserve(per_type[t]); if (has_moving) mbox[t].reserve(per_type[t]); }
+    }
     std::vector<std::pair<uint32_t, uint32_t>> world_range(F.worlds.size());
     for (size_t wi = 0; wi < F.worlds.size(); ++wi) {
         world_range[wi].first = (uint32_t)instances.size();
         for (InstBuild& ib : F.worlds[wi].inst) {
             if (ib.prims.empty()) continue;
             std::vector<BuildPrim> bp(ib.prims.size());
-            for (size_t i = 0; i < ib.prims.size(); ++i) {
+            parallel_chunks(ib.prims.size(), [&](size_t i_begin, size_t i_end) {
+              for (size_t i = i_begin; i < i_end; ++i) {
                 for (int a = 0; a < 3; ++a) { bp[i].bmin[a] = ib.prims[i].bmin[a]; bp[i].bmax[a] = ib.prims[i].bmax[a]; }
                 bp[i].type = ib.prims[i].type;
                 bp[i].src = (uint32_t)i;
@@ -552,7 +594,8 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
                         bp[i].bmin[a] = c - r; bp[i].bmax[a] = c + r;
                     }
                 }
-            }
+              }
+            });
             pt.lap("build prims");
             BuildResult br;
             bool built = false;
@@ -586,10 +629,63 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
             pt.lap(built ? "bvh build (device)" : "bvh build (host SAH)");
             if (built && pt.on) std::fprintf(stderr, "[rtb200 commit]   of which device kernels %8.3f ms (%zu primitives)\n", (double)HF.device_build_ms, bp.size());
             max_depth = std::max(max_depth, br.max_depth);
+            // Triangles (the only mesh-sized type) are converted in parallel: slot k of this instance's triangles = the k-th triangle in
+            // leaf order, so the arrays are those of the serial loop; every other type keeps the serial loop below.
+            {
+                const size_t n_lo = br.leaf_order.size();
+                std::vector<uint32_t> tri_slot;
+                size_t ntri = 0;
+                for (size_t k = 0; k < n_lo; ++k) ntri += ib.prims[br.leaf_order[k]].type == PRIM_TRI ? 1u : 0u;
+                if (ntri) {
+                    tri_slot.resize(n_lo);
+                    uint32_t c = 0;
+                    for (size_t k = 0; k < n_lo; ++k) tri_slot[k] = ib.prims[br.leaf_order[k]].type == PRIM_TRI ? c++ : 0xffffffffu;
+                    const size_t tri_base = tris.size(), meta_base = meta[PRIM_TRI].size(), mbox_base = mbox[PRIM_TRI].size();
+                    tris.resize(tri_base + ntri);
+                    meta[PRIM_TRI].resize(meta_base + ntri);
+                    if (has_moving) mbox[PRIM_TRI].resize(mbox_base + ntri);
+                    parallel_chunks(n_lo, [&](size_t k0, size_t k1) {
+                        for (size_t k = k0; k < k1; ++k) {
+                            if (tri_slot[k] == 0xffffffffu) continue;
+                            const FlatPrim& p = ib.prims[br.leaf_order[k]];
+                            const Node& n = s->nodes[(size_t)p.node];
+                            if (has_moving) {
+                                MotionBox mb;
+                                for (int a = 0; a < 3; ++a) { mb.lo0[a] = mb.lo1[a] = p.bmin[a]; mb.hi0[a] = mb.hi1[a] = p.bmax[a]; }
+                                mbox[PRIM_TRI][mbox_base + tri_slot[k]] = mb;
+                            }
+                            PrimMeta pm; pm.mat_id = p.mat; pm.prim_id = p.prim_id;
+                            meta[PRIM_TRI][meta_base + tri_slot[k]] = pm;
+                            const double *v0, *v1, *v2;
+                            if (n.kind == N_MESH) {
+                                const MeshData& m = *n.mesh;
+                                v0 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub]];
+                                v1 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub + 1]];
+                                v2 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub + 2]];
+                            } else {
+                                v0 = &n.d[0]; v1 = &n.d[3]; v2 = &n.d[6];
+                            }
+                            // Triangle::new (hit.rs:96-107): unit normal of (v1-v0) x (v2-v0), computed in f64
+                            const double ax = v1[0] - v0[0], ay = v1[1] - v0[1], az = v1[2] - v0[2];
+                            const double bx = v2[0] - v0[0], by = v2[1] - v0[1], bz = v2[2] - v0[2];
+                            double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+                            const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
+                            nx /= len; ny /= len; nz /= len;
+                            DTri q;
+                            for (int a = 0; a < 3; ++a) { q.v0[a] = (float)v0[a]; q.v1[a] = (float)v1[a]; q.v2[a] = (float)v2[a]; }
+                            q.n[0] = (float)nx; q.n[1] = (float)ny; q.n[2] = (float)nz;
+                            q.dd = -((double)q.n[0] * v0[0] + (double)q.n[1] * v0[1] + (double)q.n[2] * v0[2]); // rounded normal, exact vertex (rt_types.h)
+                            q.pad_ = 0.0;
+                            tris[tri_base + tri_slot[k]] = q;
+                        }
+                    });
+                }
+            }
             for (uint32_t src : br.leaf_order) {
                 const FlatPrim& p = ib.prims[src];
+                if (p.type == PRIM_TRI) continue; // done above
                 const Node& n = s->nodes[(size_t)p.node];
-                {   // box at the start and at the end of the shutter, in typed (leaf) order; static primitives: the same box twice
+                if (has_moving) { // box at the start and at the end of the shutter, in typed (leaf) order; static primitives: the same box twice
                     MotionBox mb;
                     for (int a = 0; a < 3; ++a) { mb.lo0[a] = mb.lo1[a] = p.bmin[a]; mb.hi0[a] = mb.hi1[a] = p.bmax[a]; }
                     if (p.type == PRIM_MOVING) {
@@ -624,29 +720,7 @@ int32_t flatten_host(rt_scene* s, HostFlat& HF, bool allow_device_build = false)
                 } break;
                 case PRIM_RECT: { DRect q; q.a0 = n.d[0]; q.a1 = n.d[1]; q.b0 = n.d[2]; q.b1 = n.d[3]; q.k = n.d[4]; q.axis = n.axis; q.pad_ = 0; rects.push_back(q); } break;
                 case PRIM_BOX: { DBox q; for (int a = 0; a < 3; ++a) { q.p0[a] = n.d[a]; q.p1[a] = n.d[3 + a]; } boxes.push_back(q); } break;
-                default: {
-                    const double *v0, *v1, *v2;
-                    if (n.kind == N_MESH) {
-                        const MeshData& m = *n.mesh;
-                        v0 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub]];
-                        v1 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub + 1]];
-                        v2 = &m.verts[3 * (size_t)m.faces[3 * (size_t)p.sub + 2]];
-                    } else {
-                        v0 = &n.d[0]; v1 = &n.d[3]; v2 = &n.d[6];
-                    }
-                    // Triangle::new (hit.rs:96-107): unit normal of (v1-v0) x (v2-v0), computed in f64
-                    const double ax = v1[0] - v0[0], ay = v1[1] - v0[1], az = v1[2] - v0[2];
-                    const double bx = v2[0] - v0[0], by = v2[1] - v0[1], bz = v2[2] - v0[2];
-                    double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
-                    const double len = std::sqrt(nx * nx + ny * ny + nz * nz);
-                    nx /= len; ny /= len; nz /= len;
-                    DTri q;
-                    for (int a = 0; a < 3; ++a) { q.v0[a] = (float)v0[a]; q.v1[a] = (float)v1[a]; q.v2[a] = (float)v2[a]; }
-                    q.n[0] = (float)nx; q.n[1] = (float)ny; q.n[2] = (float)nz;
-                    q.dd = -((double)q.n[0] * v0[0] + (double)q.n[1] * v0[1] + (double)q.n[2] * v0[2]); // rounded normal, exact vertex (rt_types.h)
-                    q.pad_ = 0.0;
-                    tris.push_back(q);
-                } break;
+                default: break;
                 }
             }
             pt.lap("typed buffers");
