@@ -120,6 +120,37 @@ uint64_t emul_rng_convert_mismatches(uint64_t n_random, uint64_t seed) {
     return bad;
 }
 
+// next3_pm1 / next2_pm1 from every draw position 0..23 (aligned or not, block cached or not), interleaved with single draws, against a
+// second generator that only ever calls gen_range(-1, 1) / gen(): same values, same draw counter afterwards; -> number of mismatches
+uint64_t emul_rng_multi_draw_mismatches(uint64_t seed, uint64_t n_paths) {
+    uint64_t bad = 0;
+    auto same = [&](double x, double y) { if (std::memcmp(&x, &y, 8) != 0) ++bad; };
+    for (uint64_t path = 0; path < n_paths; ++path)
+        for (uint32_t start = 0; start < 24; ++start)
+            for (int warm = 0; warm < 2; ++warm) { // warm = 1: the block of `start` is already cached (one gen() taken first, from start - 1)
+                PathRng a, b;
+                const uint32_t s0 = warm && start ? start - 1 : start;
+                a.init(seed, path, s0); b.init(seed, path, s0);
+                if (warm && start) same(a.gen(), b.gen());
+                for (int round = 0; round < 5; ++round) {
+                    double x, y, z;
+                    if ((round + start) & 1) { a.next3_pm1(x, y, z); same(x, b.gen_range(-1.0, 1.0)); same(y, b.gen_range(-1.0, 1.0)); same(z, b.gen_range(-1.0, 1.0)); }
+                    else { a.next2_pm1(x, y); same(x, b.gen_range(-1.0, 1.0)); same(y, b.gen_range(-1.0, 1.0)); }
+                    if (round == 2) same(a.gen(), b.gen());
+                    if (a.draw != b.draw) ++bad;
+                }
+                PathRngOolBegun c; // the fused kernels' generator: open_event == begin_event of the plain one, begin_event a no-op
+                PathRng d;
+                c.init(seed, path, start); d.init(seed, path, start);
+                c.open_event(); c.begin_event(); d.begin_event();
+                double x, y, z;
+                c.next3_pm1(x, y, z);
+                same(x, d.gen_range(-1.0, 1.0)); same(y, d.gen_range(-1.0, 1.0)); same(z, d.gen_range(-1.0, 1.0));
+                if (c.draw != d.draw) ++bad;
+            }
+    return bad;
+}
+
 uint64_t emul_sizeof_device_scene(void) { return sizeof(DeviceScene); }
 
 // wide != 0: the main world through Instance::root4 (world_hit<..., WIDE = true>, what k_extend<..., WIDE> runs); needs t_min >= 0.

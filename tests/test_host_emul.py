@@ -310,3 +310,12 @@ def test_fused_order_of_shading_draws_the_same_numbers(emul, scene_id, param, W,
     a1, s1 = emul_render(emul, ds, W, H, spp, 50, 33, wide=2)
     assert s0 == s1 and np.array_equal(a0, a1)
     s.close()
+
+
+def test_multi_draw_samplers_equal_single_draws_from_any_position(emul):
+    """next3_pm1 / next2_pm1 (three / two words at once, picked with selects, at most one new Philox block) against single
+    gen_range(-1, 1) draws, from every draw position 0..23, with the start block cached or not, interleaved with single draws:
+    same doubles, same draw counter.  Covers the positions the renders never reach (their events start on block boundaries)."""
+    emul.emul_rng_multi_draw_mismatches.restype = C.c_uint64
+    emul.emul_rng_multi_draw_mismatches.argtypes = [C.c_uint64, C.c_uint64]
+    assert emul.emul_rng_multi_draw_mismatches(0xB200, 200) == 0
